@@ -1,0 +1,1020 @@
+// C-ABI implementation of include/arp_b200.h: handle, weight packing, TMA descriptors and the
+// stream-ordered pipeline   decode -> patch-embed GEMM -> 12 x [LN, QKV, attention, out-proj, LN, c_fc, c_proj]
+// -> reward head -> per-episode return-to-go scan.
+// Host logic only; every kernel lives in the .cuh next to this file.
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <string>
+#include <tuple>
+#include <vector>
+
+#include "../../include/arp_b200.h"
+#include "attention.cuh"
+#include "decode.cuh"
+#include "gemm_tcgen05.cuh"
+#include "head.cuh"
+#include "layernorm.cuh"
+#include "scan.cuh"
+
+using namespace arp;
+typedef __nv_bfloat16 bf16;
+
+// ------------------------------------------------------------------------------------------------
+// errors
+// ------------------------------------------------------------------------------------------------
+static thread_local std::string g_create_error;
+
+struct ArpHandle;
+static int fail(ArpHandle* h, int code, const char* fmt, ...);
+
+#define ARP_CUDA(h, expr)                                                                      \
+  do {                                                                                         \
+    cudaError_t _e = (expr);                                                                   \
+    if (_e != cudaSuccess)                                                                     \
+      return fail(h, ARP_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+  } while (0)
+
+#define ARP_TRY(expr)            \
+  do {                           \
+    int _r = (expr);             \
+    if (_r != ARP_OK) return _r; \
+  } while (0)
+
+// ------------------------------------------------------------------------------------------------
+// driver entry point for TMA descriptors (no link-time dependency on libcuda)
+// ------------------------------------------------------------------------------------------------
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static PFN_encodeTiled get_encode_tiled() {
+  static PFN_encodeTiled fn = nullptr;
+  if (fn) return fn;
+  void* p = nullptr;
+  cudaDriverEntryPointQueryResult q;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+      q != cudaDriverEntryPointSuccess)
+    return nullptr;
+  fn = reinterpret_cast<PFN_encodeTiled>(p);
+  return fn;
+}
+
+// ------------------------------------------------------------------------------------------------
+// handle
+// ------------------------------------------------------------------------------------------------
+struct LayerW {
+  float *ln1_g = nullptr, *ln1_b = nullptr, *ln2_g = nullptr, *ln2_b = nullptr;
+  bf16 *w_qkv = nullptr, *w_out = nullptr, *w_fc = nullptr, *w_proj = nullptr;
+  float *b_qkv = nullptr, *b_out = nullptr, *b_fc = nullptr, *b_proj = nullptr;
+};
+
+struct WeightSlot {
+  void** dst;      // device buffer to fill
+  int64_t numel;
+  bool as_bf16;    // GEMM operand (bf16) or fp32 parameter
+  bool required;
+  bool set;
+};
+
+struct TmapKey {
+  const void* ptr; uint64_t rows, cols, ld; uint32_t box_rows;
+  bool operator<(const TmapKey& o) const {
+    return std::tie(ptr, rows, cols, ld, box_rows) < std::tie(o.ptr, o.rows, o.cols, o.ld, o.box_rows);
+  }
+};
+
+struct ArpHandle {
+  ArpConfig cfg;
+  std::string err;
+  int64_t launches = 0;
+  int tokens = 0, grid = 0, kp = 0;  // 197, 14, 768
+  bool adapter = false, goal = false;
+  int n_scales = 0, feat_dim = 0;    // 13, 6656 for adapter heads
+
+  // weights
+  bf16* conv1 = nullptr;
+  float *class_emb = nullptr, *pos_emb = nullptr, *rowtab = nullptr;
+  float *ln_pre_g = nullptr, *ln_pre_b = nullptr, *ln_post_g = nullptr, *ln_post_b = nullptr;
+  float* proj = nullptr;
+  std::vector<LayerW> layers;
+  bf16 *inter_w = nullptr, *fc1_w = nullptr, *fc2_w = nullptr;
+  float *fc1_b = nullptr, *fc2_b = nullptr, *res_w = nullptr;
+  float res_sigmoid = 0.f;
+  bool finalized = false;
+  std::map<std::string, WeightSlot> slots;
+
+  // text
+  float* text = nullptr;
+  int n_text = 0, text_dim = 0;
+  float logit_scale = 0.f;
+
+  // decode tables
+  int *h_min = nullptr, *h_cnt = nullptr, *h_k = nullptr, *v_min = nullptr, *v_cnt = nullptr, *v_k = nullptr;
+  int h_ksize = 0, v_ksize = 0, max_rows = 0;
+  float* lut = nullptr;
+  int crop_top = 0, crop_left = 0, src_h = 0, src_w = 0;
+
+  // workspace (sized for cfg.max_batch frames)
+  float* x = nullptr;
+  bf16 *xn = nullptr, *qkv = nullptr, *attn = nullptr, *hid = nullptr;
+  bf16 *taps = nullptr, *featb = nullptr, *hid2 = nullptr;
+  float *featf = nullptr, *mlp = nullptr, *feat_clip = nullptr;
+  float* logits_ws = nullptr;
+
+  // scratch that grows with T (goal heads, host path)
+  void* scratch[2] = {nullptr, nullptr};  // [0] label temporaries, [1] device outputs of the host path
+  size_t scratch_bytes[2] = {0, 0};
+  uint8_t* stage_dev[2] = {nullptr, nullptr};
+  size_t stage_bytes = 0;
+  cudaStream_t copy_stream = nullptr, own_stream = nullptr;
+  cudaEvent_t ev_copied[2] = {nullptr, nullptr}, ev_consumed[2] = {nullptr, nullptr};
+
+  std::map<TmapKey, CUtensorMap> tmaps;
+  std::vector<void*> allocs;
+};
+
+static int fail(ArpHandle* h, int code, const char* fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  if (h) h->err = buf; else g_create_error = buf;
+  return code;
+}
+
+template <typename T>
+static int dev_alloc(ArpHandle* h, T** p, size_t count) {
+  void* q = nullptr;
+  ARP_CUDA(h, cudaMalloc(&q, count * sizeof(T) + 256));
+  h->allocs.push_back(q);
+  *p = reinterpret_cast<T*>(q);
+  return ARP_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Pillow resample tables (libImaging/Resample.c precompute_coeffs + normalize_coeffs_8bpc)
+// ------------------------------------------------------------------------------------------------
+static double bicubic_filter(double x) {
+  const double a = -0.5;
+  if (x < 0.0) x = -x;
+  if (x < 1.0) return ((a + 2.0) * x - (a + 3.0)) * x * x + 1;
+  if (x < 2.0) return (((x - 5) * x + 8) * x - 4) * a;
+  return 0.0;
+}
+
+static void pil_bicubic_tables(int in_size, int out_size, std::vector<int>& xmin_v, std::vector<int>& cnt_v,
+                               std::vector<int>& kk, int& ksize) {
+  double scale = static_cast<double>(in_size) / out_size;
+  double filterscale = scale < 1.0 ? 1.0 : scale;
+  const double support = 2.0 * filterscale;
+  ksize = static_cast<int>(std::ceil(support)) * 2 + 1;
+  xmin_v.assign(out_size, 0);
+  cnt_v.assign(out_size, 0);
+  kk.assign(static_cast<size_t>(out_size) * ksize, 0);
+  std::vector<double> k(ksize);
+  for (int xx = 0; xx < out_size; ++xx) {
+    const double center = 0.0 + (xx + 0.5) * scale;
+    double ww = 0.0;
+    const double ss = 1.0 / filterscale;
+    int xmin = static_cast<int>(center - support + 0.5);
+    if (xmin < 0) xmin = 0;
+    int xmax = static_cast<int>(center + support + 0.5);
+    if (xmax > in_size) xmax = in_size;
+    xmax -= xmin;
+    for (int x = 0; x < xmax; ++x) {
+      const double w = bicubic_filter((x + xmin - center + 0.5) * ss);
+      k[x] = w;
+      ww += w;
+    }
+    for (int x = 0; x < xmax; ++x)
+      if (ww != 0.0) k[x] /= ww;
+    for (int x = 0; x < xmax; ++x) {
+      const double v = k[x] * (1 << 22);
+      kk[static_cast<size_t>(xx) * ksize + x] = v < 0 ? static_cast<int>(-0.5 + v) : static_cast<int>(0.5 + v);
+    }
+    xmin_v[xx] = xmin;
+    cnt_v[xx] = xmax;
+  }
+}
+
+static const float kClipMean[3] = {0.48145466f, 0.4578275f, 0.40821073f};
+static const float kClipStd[3] = {0.26862954f, 0.26130258f, 0.27577711f};
+
+template <typename T>
+static int upload(ArpHandle* h, T** dst, const std::vector<T>& v) {
+  ARP_TRY(dev_alloc(h, dst, v.size()));
+  ARP_CUDA(h, cudaMemcpy(*dst, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
+  return ARP_OK;
+}
+
+static int build_decode_tables(ArpHandle* h) {
+  const ArpConfig& c = h->cfg;
+  h->src_h = c.in_h;
+  h->src_w = c.in_w;
+  h->crop_top = h->crop_left = 0;
+  if (c.use_crop) {
+    if (c.preprocess == ARP_PRE_PIL_BICUBIC) {
+      // torchvision CenterCrop(image_size // 2) with image_size = shape[-2] (label_reward.py:96,104):
+      // square crop, origin int(round((dim - crop) / 2.0))
+      const int cs = c.in_w / 2;  // g[key].shape[-2] is W for [T,F,H,W,3]
+      h->src_h = h->src_w = cs;
+      h->crop_top = static_cast<int>(std::nearbyint((c.in_h - cs) / 2.0));
+      h->crop_left = static_cast<int>(std::nearbyint((c.in_w - cs) / 2.0));
+    } else {
+      // center_crop(images, (image_size//2, image_size//2)) (label_reward.py:15-36, :203): origin int((dim-crop)/2)
+      const int cs = c.in_w / 2;
+      h->src_h = h->src_w = cs;
+      h->crop_top = (c.in_h - cs) / 2;
+      h->crop_left = (c.in_w - cs) / 2;
+    }
+  }
+  if (h->src_h <= 0 || h->src_w <= 0 || h->crop_top < 0 || h->crop_top + h->src_h > c.in_h)
+    return fail(h, ARP_ERR_INVALID, "bad crop geometry for %dx%d", c.in_h, c.in_w);
+  if (c.preprocess == ARP_PRE_PIL_BICUBIC) {
+    // Resize(224) scales the SHORTER side to 224 keeping aspect; the path only meets square frames.
+    if (h->src_h != h->src_w) return fail(h, ARP_ERR_INVALID, "non-square frames are not supported (%dx%d)", h->src_h, h->src_w);
+    std::vector<int> xm, xc, xk, ym, yc, yk;
+    pil_bicubic_tables(h->src_w, DEC_OUT, xm, xc, xk, h->h_ksize);
+    pil_bicubic_tables(h->src_h, DEC_OUT, ym, yc, yk, h->v_ksize);
+    if (h->h_ksize > 64 || h->v_ksize > 64) return fail(h, ARP_ERR_INVALID, "downscale factor too large");
+    h->max_rows = 0;
+    for (int b = 0; b < DEC_OUT / DEC_BAND; ++b) {
+      const int lo = ym[b * DEC_BAND], hi = ym[b * DEC_BAND + DEC_BAND - 1] + yc[b * DEC_BAND + DEC_BAND - 1];
+      h->max_rows = std::max(h->max_rows, hi - lo);
+    }
+    ARP_TRY(upload(h, &h->h_min, xm)); ARP_TRY(upload(h, &h->h_cnt, xc)); ARP_TRY(upload(h, &h->h_k, xk));
+    ARP_TRY(upload(h, &h->v_min, ym)); ARP_TRY(upload(h, &h->v_cnt, yc)); ARP_TRY(upload(h, &h->v_k, yk));
+    std::vector<float> lut(3 * 256);
+    for (int ch = 0; ch < 3; ++ch)
+      for (int u = 0; u < 256; ++u) {
+        volatile float v = static_cast<float>(u) / 255.0f;  // ToTensor: u8 -> f32, div 255
+        volatile float w = v - kClipMean[ch];               // Normalize: sub mean, div std (fp32, separately rounded)
+        lut[ch * 256 + u] = w / kClipStd[ch];
+      }
+    ARP_TRY(upload(h, &h->lut, lut));
+  } else {
+    const float sc = static_cast<float>(h->src_h) / DEC_OUT;
+    h->max_rows = static_cast<int>(sc * DEC_BAND) + 4;
+    if (h->max_rows > h->src_h) h->max_rows = h->src_h;
+    h->h_ksize = h->v_ksize = 0;
+  }
+  return ARP_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// weights
+// ------------------------------------------------------------------------------------------------
+static void add_slot(ArpHandle* h, const std::string& name, void** dst, int64_t numel, bool as_bf16, bool required) {
+  h->slots[name] = WeightSlot{dst, numel, as_bf16, required, false};
+}
+
+static void register_slots(ArpHandle* h) {
+  const ArpConfig& c = h->cfg;
+  const int W = c.width, P = c.patch;
+  add_slot(h, "visual.conv1.weight", (void**)&h->conv1, (int64_t)W * 3 * P * P, true, true);
+  add_slot(h, "visual.class_embedding", (void**)&h->class_emb, W, false, true);
+  add_slot(h, "visual.positional_embedding", (void**)&h->pos_emb, (int64_t)h->tokens * W, false, true);
+  add_slot(h, "visual.ln_pre.weight", (void**)&h->ln_pre_g, W, false, true);
+  add_slot(h, "visual.ln_pre.bias", (void**)&h->ln_pre_b, W, false, true);
+  add_slot(h, "visual.ln_post.weight", (void**)&h->ln_post_g, W, false, true);
+  add_slot(h, "visual.ln_post.bias", (void**)&h->ln_post_b, W, false, true);
+  add_slot(h, "visual.proj", (void**)&h->proj, (int64_t)W * c.embed_dim, false, true);
+  h->layers.resize(c.layers);
+  for (int l = 0; l < c.layers; ++l) {
+    LayerW& L = h->layers[l];
+    const std::string p = "visual.transformer.resblocks." + std::to_string(l) + ".";
+    add_slot(h, p + "ln_1.weight", (void**)&L.ln1_g, W, false, true);
+    add_slot(h, p + "ln_1.bias", (void**)&L.ln1_b, W, false, true);
+    add_slot(h, p + "ln_2.weight", (void**)&L.ln2_g, W, false, true);
+    add_slot(h, p + "ln_2.bias", (void**)&L.ln2_b, W, false, true);
+    add_slot(h, p + "attn.in_proj_weight", (void**)&L.w_qkv, (int64_t)3 * W * W, true, true);
+    add_slot(h, p + "attn.in_proj_bias", (void**)&L.b_qkv, 3 * W, false, true);
+    add_slot(h, p + "attn.out_proj.weight", (void**)&L.w_out, (int64_t)W * W, true, true);
+    add_slot(h, p + "attn.out_proj.bias", (void**)&L.b_out, W, false, true);
+    add_slot(h, p + "mlp.c_fc.weight", (void**)&L.w_fc, (int64_t)4 * W * W, true, true);
+    add_slot(h, p + "mlp.c_fc.bias", (void**)&L.b_fc, 4 * W, false, true);
+    add_slot(h, p + "mlp.c_proj.weight", (void**)&L.w_proj, (int64_t)4 * W * W, true, true);
+    add_slot(h, p + "mlp.c_proj.bias", (void**)&L.b_proj, W, false, true);
+  }
+  if (h->adapter) {
+    const int64_t D = h->feat_dim;                       // 13 * 512
+    const int64_t Din = (int64_t)c.layers * W;           // 12 * 768
+    const int64_t Dmid = (int64_t)c.layers * c.embed_dim;  // 12 * 512 (text_dim * num_clip_layers)
+    add_slot(h, "image_intermediate_linear.weight", (void**)&h->inter_w, Dmid * Din, true, true);
+    add_slot(h, "image_adapter.layers.0.weight", (void**)&h->fc1_w, 2 * D * D, true, true);
+    add_slot(h, "image_adapter.layers.0.bias", (void**)&h->fc1_b, 2 * D, false, true);
+    add_slot(h, "image_adapter.layers.3.weight", (void**)&h->fc2_w, 2 * D * D, true, true);
+    add_slot(h, "image_adapter.layers.3.bias", (void**)&h->fc2_b, D, false, true);
+    add_slot(h, "image_residual_weight", (void**)&h->res_w, 1, false, true);
+  }
+}
+
+template <typename S, typename D>
+__global__ void convert_kernel(const S* __restrict__ src, D* __restrict__ dst, size_t n) {
+  for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x)
+    dst[i] = static_cast<D>(static_cast<float>(src[i]));
+}
+
+template <typename S, typename D>
+static void launch_convert(ArpHandle* h, const void* src, void* dst, size_t n, cudaStream_t st) {
+  const int blocks = static_cast<int>(std::min<size_t>((n + 255) / 256, 148 * 16));
+  convert_kernel<S, D><<<blocks, 256, 0, st>>>(static_cast<const S*>(src), static_cast<D*>(dst), n);
+  h->launches++;
+}
+
+__global__ void build_rowtab_kernel(const float* __restrict__ pos, const float* __restrict__ cls,
+                                    float* __restrict__ tab, int tokens, int W) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= tokens * W) return;
+  tab[i] = pos[i] + (i < W ? cls[i] : 0.f);
+}
+
+// ------------------------------------------------------------------------------------------------
+// C ABI: lifetime
+// ------------------------------------------------------------------------------------------------
+extern "C" int arp_abi_version(void) { return ARP_B200_ABI_VERSION; }
+
+extern "C" const char* arp_last_error(const ArpHandle* h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+extern "C" int64_t arp_launch_count(const ArpHandle* h) { return h ? h->launches : 0; }
+
+template <typename K>
+static int set_smem(ArpHandle* h, K kernel, int bytes) {
+  ARP_CUDA(h, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+  return ARP_OK;
+}
+
+extern "C" void arp_destroy(ArpHandle* h) {
+  if (!h) return;
+  cudaSetDevice(h->cfg.device);
+  cudaDeviceSynchronize();
+  for (void* p : h->allocs) cudaFree(p);
+  for (int i = 0; i < 2; ++i) if (h->scratch[i]) cudaFree(h->scratch[i]);
+  for (int i = 0; i < 2; ++i) {
+    if (h->stage_dev[i]) cudaFree(h->stage_dev[i]);
+    if (h->ev_copied[i]) cudaEventDestroy(h->ev_copied[i]);
+    if (h->ev_consumed[i]) cudaEventDestroy(h->ev_consumed[i]);
+  }
+  if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
+  if (h->own_stream) cudaStreamDestroy(h->own_stream);
+  delete h;
+}
+
+extern "C" int arp_create(const ArpConfig* cfg, ArpHandle** out) {
+  if (!cfg || !out) return fail(nullptr, ARP_ERR_INVALID, "null argument");
+  if (cfg->struct_size != (int32_t)sizeof(ArpConfig))
+    return fail(nullptr, ARP_ERR_INVALID, "ArpConfig.struct_size %d != %zu", cfg->struct_size, sizeof(ArpConfig));
+  *out = nullptr;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0 || cfg->device < 0 || cfg->device >= ndev)
+    return fail(nullptr, ARP_ERR_NO_DEVICE, "no CUDA device %d (count %d); this library has no CPU path", cfg->device, ndev);
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, cfg->device) != cudaSuccess || prop.major != 10)
+    return fail(nullptr, ARP_ERR_NO_DEVICE, "device %d is sm_%d%d; arp_b200 is built for sm_100a only", cfg->device,
+                prop.major, prop.minor);
+  if (cfg->width != 768 || cfg->embed_dim != 512 || cfg->heads * 64 != cfg->width)
+    return fail(nullptr, ARP_ERR_INVALID, "only ViT-B geometry is built (width 768, 64-wide heads, embed 512)");
+  if (cfg->patch != 16 && cfg->patch != 32) return fail(nullptr, ARP_ERR_INVALID, "patch must be 16 or 32");
+  if (cfg->layers < 1 || cfg->layers > 48 || cfg->max_batch < 1 || cfg->in_h < 8 || cfg->in_w < 8)
+    return fail(nullptr, ARP_ERR_INVALID, "bad layers / max_batch / frame size");
+  if (cfg->head < 0 || cfg->head > ARP_HEAD_ADAPTER_GOAL || cfg->preprocess < 0 || cfg->preprocess > 1)
+    return fail(nullptr, ARP_ERR_INVALID, "bad head / preprocess enum");
+  if (!get_encode_tiled()) return fail(nullptr, ARP_ERR_CUDA, "cuTensorMapEncodeTiled not available from the driver");
+
+  ArpHandle* h = new ArpHandle();
+  h->cfg = *cfg;
+  auto bail = [&](int code) { g_create_error = h->err; arp_destroy(h); return code; };
+  if (cudaSetDevice(cfg->device) != cudaSuccess) { h->err = "cudaSetDevice failed"; return bail(ARP_ERR_CUDA); }
+  h->grid = DEC_OUT / cfg->patch;
+  h->tokens = h->grid * h->grid + 1;
+  h->kp = 3 * cfg->patch * cfg->patch;
+  h->adapter = cfg->head == ARP_HEAD_ADAPTER || cfg->head == ARP_HEAD_ADAPTER_ENSEMBLE || cfg->head == ARP_HEAD_ADAPTER_GOAL;
+  h->goal = cfg->head == ARP_HEAD_CLIP_GOAL || cfg->head == ARP_HEAD_ADAPTER_GOAL;
+  h->n_scales = cfg->layers + 1;
+  h->feat_dim = h->adapter ? h->n_scales * cfg->embed_dim : cfg->embed_dim;
+  if (h->adapter && h->n_scales != 13) { h->err = "adapter heads are built for 12-layer CLIP (13 scales)"; return bail(ARP_ERR_INVALID); }
+
+  int r = build_decode_tables(h);
+  if (r != ARP_OK) return bail(r);
+  register_slots(h);
+
+  const size_t B = cfg->max_batch, M = B * h->tokens, W = cfg->width;
+#define CREATE_TRY(e) do { int _r = (e); if (_r != ARP_OK) return bail(_r); } while (0)
+  CREATE_TRY(dev_alloc(h, &h->x, M * W));
+  CREATE_TRY(dev_alloc(h, &h->xn, M * W));
+  CREATE_TRY(dev_alloc(h, &h->qkv, M * 3 * W));
+  CREATE_TRY(dev_alloc(h, &h->attn, M * W));
+  CREATE_TRY(dev_alloc(h, &h->hid, M * std::max<size_t>(4 * W, h->kp)));
+  CREATE_TRY(dev_alloc(h, &h->rowtab, (size_t)h->tokens * W));
+  CREATE_TRY(dev_alloc(h, &h->feat_clip, B * cfg->embed_dim));
+  CREATE_TRY(dev_alloc(h, &h->logits_ws, B * HEAD_MAX_TEXT));
+  if (h->adapter) {
+    const size_t D = h->feat_dim;
+    CREATE_TRY(dev_alloc(h, &h->taps, B * cfg->layers * W));
+    CREATE_TRY(dev_alloc(h, &h->featf, B * D));
+    CREATE_TRY(dev_alloc(h, &h->featb, B * D));
+    CREATE_TRY(dev_alloc(h, &h->hid2, B * 2 * D));
+    CREATE_TRY(dev_alloc(h, &h->mlp, B * D));
+  }
+  // weight buffers
+  for (auto& kv : h->slots) {
+    WeightSlot& s = kv.second;
+    void* p = nullptr;
+    if (cudaMalloc(&p, s.numel * (s.as_bf16 ? 2 : 4) + 256) != cudaSuccess) { h->err = "cudaMalloc(weights) failed"; return bail(ARP_ERR_CUDA); }
+    h->allocs.push_back(p);
+    *s.dst = p;
+  }
+  // opt-in shared memory
+  CREATE_TRY(set_smem(h, gemm_bf16_tcgen05_kernel<bf16, ACT_NONE>, GEMM_SMEM_BYTES));
+  CREATE_TRY(set_smem(h, gemm_bf16_tcgen05_kernel<bf16, ACT_QUICKGELU>, GEMM_SMEM_BYTES));
+  CREATE_TRY(set_smem(h, gemm_bf16_tcgen05_kernel<bf16, ACT_RELU>, GEMM_SMEM_BYTES));
+  CREATE_TRY(set_smem(h, gemm_bf16_tcgen05_kernel<float, ACT_NONE>, GEMM_SMEM_BYTES));
+  CREATE_TRY(set_smem(h, gemm_bf16_tcgen05_kernel<float, ACT_QUICKGELU>, GEMM_SMEM_BYTES));
+  CREATE_TRY(set_smem(h, gemm_bf16_tcgen05_kernel<float, ACT_RELU>, GEMM_SMEM_BYTES));
+  CREATE_TRY(set_smem(h, attention_kernel<197>, AttnCfg<197>::SMEM));
+  CREATE_TRY(set_smem(h, attention_kernel<50>, AttnCfg<50>::SMEM));
+  CREATE_TRY(set_smem(h, decode_kernel, 160 * 1024));
+  if (cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking) != cudaSuccess) {
+    h->err = "cudaStreamCreate failed";
+    return bail(ARP_ERR_CUDA);
+  }
+  for (int i = 0; i < 2; ++i) {
+    cudaEventCreateWithFlags(&h->ev_copied[i], cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&h->ev_consumed[i], cudaEventDisableTiming);
+  }
+#undef CREATE_TRY
+  *out = h;
+  return ARP_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// C ABI: weights / text
+// ------------------------------------------------------------------------------------------------
+static bool is_ignored_key(const std::string& n) {
+  static const char* prefixes[] = {"transformer.", "token_embedding.", "positional_embedding", "ln_final.",
+                                   "text_projection", "logit_scale", "text_intermediate_linear.", "text_adapter.",
+                                   "text_residual_weight", "inverse_layer.", "lambda_id", "input_resolution",
+                                   "context_length", "vocab_size", "image_intermediate_linear.", "image_adapter.",
+                                   "image_residual_weight"};
+  for (const char* p : prefixes)
+    if (n.compare(0, strlen(p), p) == 0) return true;
+  return false;
+}
+
+extern "C" int arp_set_weight(ArpHandle* h, const char* name, const void* data, int32_t dtype, const int64_t* shape,
+                              int32_t ndim, void* stream) {
+  if (!h || !name || !data || (ndim > 0 && !shape)) return fail(h, ARP_ERR_INVALID, "null argument");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  std::string key(name);
+  if (key.compare(0, 11, "clip_model.") == 0) key = key.substr(11);  // adapter checkpoints nest CLIP (finetune.py:164)
+  auto it = h->slots.find(key);
+  if (it == h->slots.end()) {
+    if (is_ignored_key(key)) return ARP_OK;
+    return fail(h, ARP_ERR_UNKNOWN_KEY, "unknown weight '%s'", name);
+  }
+  WeightSlot& s = it->second;
+  int64_t numel = 1;
+  for (int i = 0; i < ndim; ++i) numel *= shape[i];
+  if (numel != s.numel) return fail(h, ARP_ERR_INVALID, "weight '%s': %lld elements, expected %lld", name, (long long)numel, (long long)s.numel);
+  ARP_CUDA(h, cudaSetDevice(h->cfg.device));
+  void* dst = *s.dst;
+  const size_t n = static_cast<size_t>(numel);
+  if (s.as_bf16) {
+    if (dtype == ARP_F32) launch_convert<float, bf16>(h, data, dst, n, st);
+    else if (dtype == ARP_F16) launch_convert<__half, bf16>(h, data, dst, n, st);
+    else if (dtype == ARP_BF16) ARP_CUDA(h, cudaMemcpyAsync(dst, data, n * 2, cudaMemcpyDeviceToDevice, st));
+    else return fail(h, ARP_ERR_INVALID, "bad dtype %d", dtype);
+  } else {
+    if (dtype == ARP_F32) ARP_CUDA(h, cudaMemcpyAsync(dst, data, n * 4, cudaMemcpyDeviceToDevice, st));
+    else if (dtype == ARP_F16) launch_convert<__half, float>(h, data, dst, n, st);
+    else if (dtype == ARP_BF16) launch_convert<bf16, float>(h, data, dst, n, st);
+    else return fail(h, ARP_ERR_INVALID, "bad dtype %d", dtype);
+  }
+  ARP_CUDA(h, cudaGetLastError());
+  s.set = true;
+  h->finalized = false;
+  return ARP_OK;
+}
+
+extern "C" int arp_missing_weights(const ArpHandle* h, char* names_out, int64_t names_cap) {
+  if (!h) return -1;
+  int missing = 0;
+  std::string names;
+  for (const auto& kv : h->slots)
+    if (kv.second.required && !kv.second.set) {
+      ++missing;
+      names += kv.first;
+      names += '\n';
+    }
+  if (names_out && names_cap > 0) {
+    const size_t n = std::min<size_t>(names.size(), static_cast<size_t>(names_cap - 1));
+    memcpy(names_out, names.data(), n);
+    names_out[n] = 0;
+  }
+  return missing;
+}
+
+static int finalize_weights(ArpHandle* h, cudaStream_t st) {
+  if (h->finalized) return ARP_OK;
+  char buf[256];
+  const int miss = arp_missing_weights(h, buf, sizeof(buf));
+  if (miss) return fail(h, ARP_ERR_STATE, "%d weights not set, first: %.200s", miss, buf);
+  const int n = h->tokens * h->cfg.width;
+  build_rowtab_kernel<<<(n + 255) / 256, 256, 0, st>>>(h->pos_emb, h->class_emb, h->rowtab, h->tokens, h->cfg.width);
+  h->launches++;
+  if (h->adapter) {
+    float w = 0.f;
+    ARP_CUDA(h, cudaMemcpyAsync(&w, h->res_w, 4, cudaMemcpyDeviceToHost, st));
+    ARP_CUDA(h, cudaStreamSynchronize(st));
+    h->res_sigmoid = 1.0f / (1.0f + expf(-w));
+  }
+  ARP_CUDA(h, cudaGetLastError());
+  h->finalized = true;
+  return ARP_OK;
+}
+
+extern "C" int arp_set_text(ArpHandle* h, const float* text_emb_dev, int32_t n_text, int32_t dim,
+                            float logit_scale_exp, void* stream) {
+  if (!h || !text_emb_dev) return fail(h, ARP_ERR_INVALID, "null argument");
+  if (n_text < 1 || n_text > HEAD_MAX_TEXT) return fail(h, ARP_ERR_INVALID, "n_text must be in [1,%d]", HEAD_MAX_TEXT);
+  if (dim != h->feat_dim) return fail(h, ARP_ERR_INVALID, "text dim %d, head expects %d", dim, h->feat_dim);
+  ARP_CUDA(h, cudaSetDevice(h->cfg.device));
+  if (!h->text) ARP_TRY(dev_alloc(h, &h->text, (size_t)HEAD_MAX_TEXT * h->feat_dim));
+  ARP_CUDA(h, cudaMemcpyAsync(h->text, text_emb_dev, (size_t)n_text * dim * 4, cudaMemcpyDeviceToDevice,
+                              static_cast<cudaStream_t>(stream)));
+  h->n_text = n_text;
+  h->text_dim = dim;
+  h->logit_scale = logit_scale_exp;
+  return ARP_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// launch helpers
+// ------------------------------------------------------------------------------------------------
+static int get_tmap(ArpHandle* h, const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows,
+                    const CUtensorMap** out) {
+  TmapKey key{ptr, rows, cols, ld, box_rows};
+  auto it = h->tmaps.find(key);
+  if (it == h->tmaps.end()) {
+    if (h->tmaps.size() > 4096) h->tmaps.clear();
+    CUtensorMap m;
+    cuuint64_t gdim[2] = {cols, rows};
+    cuuint64_t gstr[1] = {ld * 2};
+    cuuint32_t box[2] = {GEMM_BK, box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    if ((reinterpret_cast<uintptr_t>(ptr) & 15) || (gstr[0] & 15))
+      return fail(h, ARP_ERR_INVALID, "GEMM operand must be 16-byte aligned with a 16-byte multiple row pitch");
+    CUresult r = get_encode_tiled()(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), gdim, gstr, box,
+                                    estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(h, ARP_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d) rows=%llu cols=%llu", (int)r, (unsigned long long)rows, (unsigned long long)cols);
+    it = h->tmaps.emplace(key, m).first;
+  }
+  *out = &it->second;
+  return ARP_OK;
+}
+
+// a_rows_alloc: rows addressable behind `a` (>= M); the descriptor covers them so that reading a partly
+// filled workspace never depends on M (rows are independent; rows >= M are computed and dropped).
+static int launch_gemm(ArpHandle* h, const bf16* a, int64_t a_rows_alloc, const bf16* w, void* out, bool out_f32,
+                       int act, int64_t M, int N, int K, int ldo, const float* bias, const float* resid, int ldr,
+                       const float* rowtab, int period, cudaStream_t st) {
+  if (M <= 0) return ARP_OK;
+  if (N % GEMM_BN || K % GEMM_BK) return fail(h, ARP_ERR_INVALID, "GEMM needs N %% 256 == 0 and K %% 64 == 0 (N=%d K=%d)", N, K);
+  if (M > 0x7fffffff / 2) return fail(h, ARP_ERR_INVALID, "GEMM M too large");
+  const CUtensorMap *ta, *tb;
+  ARP_TRY(get_tmap(h, a, (uint64_t)a_rows_alloc, (uint64_t)K, (uint64_t)K, GEMM_BM, &ta));
+  ARP_TRY(get_tmap(h, w, (uint64_t)N, (uint64_t)K, (uint64_t)K, GEMM_BN, &tb));
+  GemmArgs g;
+  g.M = (int)M; g.N = N; g.K = K; g.out = out; g.ldo = ldo; g.bias = bias; g.resid = resid; g.ldr = ldr;
+  g.rowtab = rowtab; g.period = period > 0 ? period : 1;
+  const int tiles = (int)((M + GEMM_BM - 1) / GEMM_BM) * (N / GEMM_BN);
+  const int grid = std::min(tiles, kNumSMs);
+#define GEMM_CASE(T, A) gemm_bf16_tcgen05_kernel<T, A><<<grid, GEMM_THREADS, GEMM_SMEM_BYTES, st>>>(*ta, *tb, g)
+  if (out_f32) {
+    if (act == ACT_NONE) GEMM_CASE(float, ACT_NONE);
+    else if (act == ACT_QUICKGELU) GEMM_CASE(float, ACT_QUICKGELU);
+    else GEMM_CASE(float, ACT_RELU);
+  } else {
+    if (act == ACT_NONE) GEMM_CASE(bf16, ACT_NONE);
+    else if (act == ACT_QUICKGELU) GEMM_CASE(bf16, ACT_QUICKGELU);
+    else GEMM_CASE(bf16, ACT_RELU);
+  }
+#undef GEMM_CASE
+  h->launches++;
+  ARP_CUDA(h, cudaGetLastError());
+  return ARP_OK;
+}
+
+static int launch_decode(ArpHandle* h, const uint8_t* ob, int64_t n, int64_t stride, void* out, int out_kind,
+                         cudaStream_t st) {
+  if (n <= 0) return ARP_OK;
+  DecodeArgs a;
+  memset(&a, 0, sizeof(a));
+  a.ob = ob; a.frame_stride = stride; a.in_w = h->cfg.in_w;
+  a.crop_top = h->crop_top; a.crop_left = h->crop_left; a.src_h = h->src_h; a.src_w = h->src_w;
+  a.T = (int)n; a.mode = h->cfg.preprocess; a.out_kind = out_kind;
+  a.h_min = h->h_min; a.h_cnt = h->h_cnt; a.h_k = h->h_k; a.h_ksize = h->h_ksize;
+  a.v_min = h->v_min; a.v_cnt = h->v_cnt; a.v_k = h->v_k; a.v_ksize = h->v_ksize;
+  a.lut = h->lut;
+  for (int c = 0; c < 3; ++c) { a.mean[c] = kClipMean[c]; a.stdv[c] = kClipStd[c]; }
+  a.out = out; a.patch = h->cfg.patch; a.grid = h->grid; a.tokens = h->tokens; a.max_rows = h->max_rows;
+  const int smem = dec_smem_bytes(h->src_w, h->max_rows, h->h_ksize, h->v_ksize, out_kind);
+  if (smem > 160 * 1024) return fail(h, ARP_ERR_INVALID, "frame too large for the decode kernel (%d B smem)", smem);
+  // grid.y is limited to 65535 frames per launch
+  for (int64_t f0 = 0; f0 < n; f0 += 32768) {
+    const int cnt = (int)std::min<int64_t>(32768, n - f0);
+    DecodeArgs b = a;
+    b.ob = ob + f0 * stride;
+    b.T = cnt;
+    if (out_kind == DEC_OUT_PATCH_BF16) b.out = static_cast<bf16*>(out) + (size_t)f0 * h->tokens * h->kp;
+    else b.out = static_cast<float*>(out) + (size_t)f0 * 3 * DEC_OUT * DEC_OUT;
+    decode_kernel<<<dim3(DEC_OUT / DEC_BAND, cnt), DEC_THREADS, smem, st>>>(b);
+    h->launches++;
+  }
+  ARP_CUDA(h, cudaGetLastError());
+  return ARP_OK;
+}
+
+static int launch_ln_bf16(ArpHandle* h, const float* x, const float* g, const float* b, bf16* y, int64_t M,
+                          cudaStream_t st) {
+  if (M <= 0) return ARP_OK;
+  layernorm_f32_bf16_kernel<768><<<(unsigned)((M + 7) / 8), 256, 0, st>>>(x, g, b, y, (int)M, 1e-5f);
+  h->launches++;
+  ARP_CUDA(h, cudaGetLastError());
+  return ARP_OK;
+}
+
+static int launch_attention(ArpHandle* h, const bf16* qkv, bf16* out, int B, int tokens, cudaStream_t st) {
+  if (B <= 0) return ARP_OK;
+  const float scale_log2e = 0.125f * 1.4426950408889634f;
+  for (int b0 = 0; b0 < B; b0 += 32768) {
+    const int cnt = std::min(32768, B - b0);
+    const bf16* q = qkv + (size_t)b0 * tokens * 3 * h->cfg.width;
+    bf16* o = out + (size_t)b0 * tokens * h->cfg.width;
+    if (tokens == 197)
+      attention_kernel<197><<<dim3(h->cfg.heads, cnt), ATT_THREADS, AttnCfg<197>::SMEM, st>>>(q, o, h->cfg.width, scale_log2e);
+    else if (tokens == 50)
+      attention_kernel<50><<<dim3(h->cfg.heads, cnt), ATT_THREADS, AttnCfg<50>::SMEM, st>>>(q, o, h->cfg.width, scale_log2e);
+    else
+      return fail(h, ARP_ERR_INVALID, "attention is built for 197 or 50 tokens, got %d", tokens);
+    h->launches++;
+  }
+  ARP_CUDA(h, cudaGetLastError());
+  return ARP_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// the encoder: n frames (n <= max_batch) -> residual stream x after the last block (+ CLS taps)
+// ------------------------------------------------------------------------------------------------
+static int encode_chunk(ArpHandle* h, const uint8_t* ob, int64_t n, int64_t stride, cudaStream_t st) {
+  const ArpConfig& c = h->cfg;
+  const int W = c.width;
+  const int64_t M = n * h->tokens;
+  const int64_t Mcap = (int64_t)c.max_batch * h->tokens;
+  bf16* patches = h->hid;  // aliases the MLP hidden buffer (dead until layer 0's c_fc)
+  ARP_TRY(launch_decode(h, ob, n, stride, patches, DEC_OUT_PATCH_BF16, st));
+  // patch embed (+ positional embedding, + class embedding on the all-zero row 0 of each frame)
+  ARP_TRY(launch_gemm(h, patches, Mcap, h->conv1, h->x, true, ACT_NONE, M, W, h->kp, W, nullptr, nullptr, 0,
+                      h->rowtab, h->tokens, st));
+  layernorm_f32_inplace_kernel<768><<<(unsigned)((M + 7) / 8), 256, 0, st>>>(h->x, h->ln_pre_g, h->ln_pre_b, (int)M, 1e-5f);
+  h->launches++;
+  for (int l = 0; l < c.layers; ++l) {
+    const LayerW& L = h->layers[l];
+    ARP_TRY(launch_ln_bf16(h, h->x, L.ln1_g, L.ln1_b, h->xn, M, st));
+    ARP_TRY(launch_gemm(h, h->xn, Mcap, L.w_qkv, h->qkv, false, ACT_NONE, M, 3 * W, W, 3 * W, L.b_qkv, nullptr, 0,
+                        nullptr, 0, st));
+    ARP_TRY(launch_attention(h, h->qkv, h->attn, (int)n, h->tokens, st));
+    ARP_TRY(launch_gemm(h, h->attn, Mcap, L.w_out, h->x, true, ACT_NONE, M, W, W, W, L.b_out, h->x, W, nullptr, 0, st));
+    ARP_TRY(launch_ln_bf16(h, h->x, L.ln2_g, L.ln2_b, h->xn, M, st));
+    ARP_TRY(launch_gemm(h, h->xn, Mcap, L.w_fc, h->hid, false, ACT_QUICKGELU, M, 4 * W, W, 4 * W, L.b_fc, nullptr, 0,
+                        nullptr, 0, st));
+    ARP_TRY(launch_gemm(h, h->hid, Mcap, L.w_proj, h->x, true, ACT_NONE, M, W, 4 * W, W, L.b_proj, h->x, W, nullptr,
+                        0, st));
+    if (h->adapter) {
+      gather_cls_bf16_kernel<768><<<(unsigned)((n + 7) / 8), 256, 0, st>>>(h->x, h->taps, (int)n, h->tokens,
+                                                                         c.layers * W, l * W);
+      h->launches++;
+    }
+  }
+  ARP_CUDA(h, cudaGetLastError());
+  return ARP_OK;
+}
+
+// heads. reward_out [n] / logits_out [n, n_text] / feat_out [n, feat_dim] may each be null.
+static int head_chunk(ArpHandle* h, int64_t n, float* reward_out, float* logits_out, float* feat_out,
+                      cudaStream_t st) {
+  const ArpConfig& c = h->cfg;
+  const bool need_text = reward_out || logits_out;
+  if (need_text && !h->goal && !h->text) return fail(h, ARP_ERR_STATE, "arp_set_text has not been called");
+  if (!h->adapter) {
+    clip_head_kernel<768, 512><<<(unsigned)n, 256, 0, st>>>(
+        h->x, h->tokens, h->ln_post_g, h->ln_post_b, 1e-5f, h->proj, (need_text && !h->goal) ? h->text : nullptr,
+        h->n_text, h->logit_scale, c.reduce, feat_out, c.embed_dim, 0, logits_out, h->goal ? nullptr : reward_out);
+    h->launches++;
+  } else {
+    const int D = h->feat_dim, Dmid = c.layers * c.embed_dim, Din = c.layers * c.width;
+    const int64_t B = c.max_batch;
+    // final CLIP feature -> last 512 columns of feat (un-normalised, clip_multiscale_adapter.py:136,145)
+    clip_head_kernel<768, 512><<<(unsigned)n, 256, 0, st>>>(h->x, h->tokens, h->ln_post_g, h->ln_post_b, 1e-5f,
+                                                            h->proj, nullptr, 0, 0.f, 0, h->featf, D, Dmid, nullptr,
+                                                            nullptr);
+    h->launches++;
+    // image_intermediate_linear (no bias) over the 12 CLS taps -> first 6144 columns (:143-144)
+    ARP_TRY(launch_gemm(h, h->taps, B, h->inter_w, h->featf, true, ACT_NONE, n, Dmid, Din, D, nullptr, nullptr, 0,
+                        nullptr, 0, st));
+    f32_to_bf16_kernel<<<kNumSMs * 4, 256, 0, st>>>(h->featf, h->featb, (size_t)n * D);
+    h->launches++;
+    // AdapterMLP: Linear -> Identity -> ReLU -> Linear (finetune_module/layers.py:42-49)
+    ARP_TRY(launch_gemm(h, h->featb, B, h->fc1_w, h->hid2, false, ACT_RELU, n, 2 * D, D, 2 * D, h->fc1_b, nullptr, 0,
+                        nullptr, 0, st));
+    ARP_TRY(launch_gemm(h, h->hid2, B, h->fc2_w, h->mlp, true, ACT_NONE, n, D, 2 * D, D, h->fc2_b, nullptr, 0, nullptr,
+                        0, st));
+    const bool ens = c.head == ARP_HEAD_ADAPTER_ENSEMBLE;
+    adapter_head_kernel<13, 512><<<(unsigned)n, 13 * 32, 0, st>>>(
+        h->featf, h->mlp, h->res_sigmoid, (need_text && !h->goal) ? h->text : nullptr,
+        (need_text && !h->goal) ? h->n_text : 0, h->logit_scale, ens ? 1 : 0, c.reduce, logits_out,
+        h->goal ? nullptr : reward_out, feat_out);
+    h->launches++;
+  }
+  ARP_CUDA(h, cudaGetLastError());
+  return ARP_OK;
+}
+
+// adapter_head_kernel writes the gated, un-normalised feature when asked; normalise rows for encode_image parity
+__global__ void l2_normalize_rows_kernel(float* __restrict__ f, int dim, int64_t n) {
+  const int64_t r = static_cast<int64_t>(blockIdx.x) * 8 + (threadIdx.x >> 5);
+  if (r >= n) return;
+  const int lane = threadIdx.x & 31;
+  float* p = f + r * dim;
+  float s = 0.f;
+  for (int k = lane; k < dim; k += 32) s = fmaf(p[k], p[k], s);
+  s = warp_sum(s);
+  const float inv = 1.0f / fmaxf(sqrtf(s), 1e-12f);
+  for (int k = lane; k < dim; k += 32) p[k] *= inv;
+}
+
+__global__ void episode_goal_kernel(const long long* __restrict__ ep_off, int n_eps, long long T,
+                                    long long* __restrict__ frame_goal) {
+  const int e = blockIdx.x;
+  const long long lo = ep_off[e], hi = min(ep_off[e + 1], T);
+  for (long long t = lo + threadIdx.x; t < hi; t += blockDim.x) frame_goal[t] = hi - 1;
+}
+
+static int ensure_scratch(ArpHandle* h, int slot, size_t bytes) {
+  if (h->scratch_bytes[slot] >= bytes) return ARP_OK;
+  if (h->scratch[slot]) { cudaDeviceSynchronize(); cudaFree(h->scratch[slot]); h->scratch[slot] = nullptr; h->scratch_bytes[slot] = 0; }
+  ARP_CUDA(h, cudaMalloc(&h->scratch[slot], bytes));
+  h->scratch_bytes[slot] = bytes;
+  return ARP_OK;
+}
+
+// temporaries of one label call, carved from scratch slot 0
+struct LabelTmp {
+  float* r = nullptr;            // [T] rewards when the caller did not ask for them
+  float* g = nullptr;            // [T] return-to-go, likewise
+  long long* frame_goal = nullptr;  // [T] goal-conditioned heads: index of the episode's last frame
+  float* feats = nullptr;        // [T, feat_dim] goal-conditioned heads
+};
+
+static int carve_label_tmp(ArpHandle* h, int64_t T, LabelTmp* t) {
+  auto al = [](size_t b) { return (b + 255) & ~static_cast<size_t>(255); };
+  const size_t b_r = al((size_t)T * 4), b_goal = h->goal ? al((size_t)T * 8) : 0;
+  const size_t b_feat = h->goal ? al((size_t)T * h->feat_dim * 4) : 0;
+  ARP_TRY(ensure_scratch(h, 0, 2 * b_r + b_goal + b_feat + 256));
+  uint8_t* p = reinterpret_cast<uint8_t*>(h->scratch[0]);
+  t->r = reinterpret_cast<float*>(p); p += b_r;
+  t->g = reinterpret_cast<float*>(p); p += b_r;
+  if (h->goal) {
+    t->frame_goal = reinterpret_cast<long long*>(p); p += b_goal;
+    t->feats = reinterpret_cast<float*>(p);
+  }
+  return ARP_OK;
+}
+
+static int check_ready(ArpHandle* h, const void* ob, int64_t T, int64_t stride, cudaStream_t st) {
+  if (!h) return ARP_ERR_INVALID;
+  if (T < 0 || (T > 0 && !ob)) return fail(h, ARP_ERR_INVALID, "bad frame buffer / T");
+  if (T > 0 && stride < (int64_t)h->cfg.in_h * h->cfg.in_w * 3) return fail(h, ARP_ERR_INVALID, "row stride %lld smaller than one frame", (long long)stride);
+  ARP_CUDA(h, cudaSetDevice(h->cfg.device));
+  return finalize_weights(h, st);
+}
+
+// ------------------------------------------------------------------------------------------------
+// C ABI: hot path
+// ------------------------------------------------------------------------------------------------
+extern "C" int arp_compute_reward(ArpHandle* h, const uint8_t* ob_dev, int64_t T, int64_t row_stride_bytes,
+                                  float* reward_dev, float* logits_dev, void* stream) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  ARP_TRY(check_ready(h, ob_dev, T, row_stride_bytes, st));
+  if (h->goal) return fail(h, ARP_ERR_INVALID, "goal-conditioned heads need episode boundaries: use arp_label");
+  const int64_t B = h->cfg.max_batch;
+  for (int64_t t0 = 0; t0 < T; t0 += B) {
+    const int64_t n = std::min(B, T - t0);
+    ARP_TRY(encode_chunk(h, ob_dev + t0 * row_stride_bytes, n, row_stride_bytes, st));
+    ARP_TRY(head_chunk(h, n, reward_dev ? reward_dev + t0 : nullptr,
+                       logits_dev ? logits_dev + t0 * h->n_text : nullptr, nullptr, st));
+  }
+  return ARP_OK;
+}
+
+extern "C" int arp_encode_image(ArpHandle* h, const uint8_t* ob_dev, int64_t T, int64_t row_stride_bytes,
+                                float* feat_dev, void* stream) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  ARP_TRY(check_ready(h, ob_dev, T, row_stride_bytes, st));
+  if (!feat_dev) return fail(h, ARP_ERR_INVALID, "null output");
+  const int64_t B = h->cfg.max_batch;
+  for (int64_t t0 = 0; t0 < T; t0 += B) {
+    const int64_t n = std::min(B, T - t0);
+    ARP_TRY(encode_chunk(h, ob_dev + t0 * row_stride_bytes, n, row_stride_bytes, st));
+    ARP_TRY(head_chunk(h, n, nullptr, nullptr, feat_dev + t0 * h->feat_dim, st));
+  }
+  if (h->adapter && T > 0) {
+    l2_normalize_rows_kernel<<<(unsigned)((T + 7) / 8), 256, 0, st>>>(feat_dev, h->feat_dim, T);
+    h->launches++;
+    ARP_CUDA(h, cudaGetLastError());
+  }
+  return ARP_OK;
+}
+
+static int scan_launch(ArpHandle* h, const float* reward, int64_t T, const int64_t* ep_off, int n_eps, int F,
+                       float gamma, float* rtg, float* rs, float* gs, cudaStream_t st) {
+  if (n_eps <= 0 || T <= 0) return ARP_OK;
+  if (F < 1 || F > 64) return fail(h, ARP_ERR_INVALID, "num_frames must be in [1,64]");
+  if (gs && !rtg) return fail(h, ARP_ERR_INVALID, "rtg_stacked needs an rtg buffer");
+  rtg_scan_stack_kernel<<<n_eps, SCAN_THREADS, 0, st>>>(reward, reinterpret_cast<const long long*>(ep_off), T, F,
+                                                       gamma, rtg, rs, gs);
+  h->launches++;
+  ARP_CUDA(h, cudaGetLastError());
+  return ARP_OK;
+}
+
+extern "C" int arp_scan_only(ArpHandle* h, const float* reward_dev, int64_t T, const int64_t* ep_offsets_dev,
+                             int32_t n_eps, int32_t num_frames, float gamma, float* rtg_dev,
+                             float* reward_stacked_dev, float* rtg_stacked_dev, void* stream) {
+  if (!h || !reward_dev || !ep_offsets_dev) return fail(h, ARP_ERR_INVALID, "null argument");
+  ARP_CUDA(h, cudaSetDevice(h->cfg.device));
+  return scan_launch(h, reward_dev, T, ep_offsets_dev, n_eps, num_frames, gamma, rtg_dev, reward_stacked_dev,
+                     rtg_stacked_dev, static_cast<cudaStream_t>(stream));
+}
+
+static int label_device(ArpHandle* h, const uint8_t* ob_dev, int64_t T, int64_t stride, const int64_t* ep_off,
+                        int n_eps, int F, float* reward, float* rtg, float* rs, float* gs, cudaStream_t st);
+
+extern "C" int arp_label(ArpHandle* h, const uint8_t* ob_dev, int64_t T, int64_t row_stride_bytes,
+                         const int64_t* ep_offsets_dev, int32_t n_eps, int32_t num_frames, float* reward_dev,
+                         float* rtg_dev, float* reward_stacked_dev, float* rtg_stacked_dev, void* stream) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  ARP_TRY(check_ready(h, ob_dev, T, row_stride_bytes, st));
+  if (!ep_offsets_dev || n_eps < 0) return fail(h, ARP_ERR_INVALID, "bad episode offsets");
+  return label_device(h, ob_dev, T, row_stride_bytes, ep_offsets_dev, n_eps, num_frames, reward_dev, rtg_dev,
+                      reward_stacked_dev, rtg_stacked_dev, st);
+}
+
+// goal heads: rewards from feature distances to the episode's last frame (label_reward.py:159-162, :192-195)
+static int goal_rewards(ArpHandle* h, const LabelTmp& tmp, int64_t T, const int64_t* ep_off, int n_eps, float* r,
+                        cudaStream_t st) {
+  if (h->adapter) {
+    l2_normalize_rows_kernel<<<(unsigned)((T + 7) / 8), 256, 0, st>>>(tmp.feats, h->feat_dim, T);
+    h->launches++;
+  }
+  ARP_CUDA(h, cudaMemsetAsync(tmp.frame_goal, 0, (size_t)T * 8, st));
+  if (n_eps > 0) {
+    episode_goal_kernel<<<n_eps, 128, 0, st>>>(reinterpret_cast<const long long*>(ep_off), n_eps, T, tmp.frame_goal);
+    h->launches++;
+  }
+  goal_distance_kernel<<<(unsigned)((T + 7) / 8), 256, 0, st>>>(tmp.feats, h->feat_dim, tmp.frame_goal, T,
+                                                               h->cfg.head == ARP_HEAD_CLIP_GOAL ? -1.f : 1.f, r);
+  h->launches++;
+  ARP_CUDA(h, cudaGetLastError());
+  return ARP_OK;
+}
+
+static int label_device(ArpHandle* h, const uint8_t* ob_dev, int64_t T, int64_t stride, const int64_t* ep_off,
+                        int n_eps, int F, float* reward, float* rtg, float* rs, float* gs, cudaStream_t st) {
+  if (T == 0) return ARP_OK;
+  LabelTmp tmp;
+  ARP_TRY(carve_label_tmp(h, T, &tmp));
+  float* r = reward ? reward : tmp.r;
+  float* g = rtg ? rtg : tmp.g;
+  const int64_t B = h->cfg.max_batch;
+  for (int64_t t0 = 0; t0 < T; t0 += B) {
+    const int64_t n = std::min(B, T - t0);
+    ARP_TRY(encode_chunk(h, ob_dev + t0 * stride, n, stride, st));
+    if (!h->goal) ARP_TRY(head_chunk(h, n, r + t0, nullptr, nullptr, st));
+    else ARP_TRY(head_chunk(h, n, nullptr, nullptr, tmp.feats + t0 * h->feat_dim, st));
+  }
+  if (h->goal) ARP_TRY(goal_rewards(h, tmp, T, ep_off, n_eps, r, st));
+  return scan_launch(h, r, T, ep_off, n_eps, F, 1.0f, g, rs, gs, st);
+}
+
+extern "C" int arp_label_host(ArpHandle* h, const uint8_t* ob_host, int64_t T, int64_t row_stride_bytes,
+                              const int64_t* ep_offsets_host, int32_t n_eps, int32_t num_frames, float* reward_host,
+                              float* rtg_host, float* reward_stacked_host, float* rtg_stacked_host) {
+  if (!h) return ARP_ERR_INVALID;
+  cudaStream_t st = h->own_stream;
+  ARP_TRY(check_ready(h, ob_host, T, row_stride_bytes, st));
+  if (!ep_offsets_host || n_eps < 0) return fail(h, ARP_ERR_INVALID, "bad episode offsets");
+  if (num_frames < 1 || num_frames > 64) return fail(h, ARP_ERR_INVALID, "num_frames must be in [1,64]");
+  if (T == 0) return ARP_OK;
+  const ArpConfig& c = h->cfg;
+  const size_t frame_bytes = (size_t)c.in_h * c.in_w * 3;
+  const int64_t B = c.max_batch;
+  const int F = num_frames;
+  if (h->stage_bytes < frame_bytes * B) {
+    for (int i = 0; i < 2; ++i) {
+      if (h->stage_dev[i]) cudaFree(h->stage_dev[i]);
+      h->stage_dev[i] = nullptr;
+      ARP_CUDA(h, cudaMalloc((void**)&h->stage_dev[i], frame_bytes * B));
+    }
+    h->stage_bytes = frame_bytes * B;
+  }
+  // device outputs (scratch slot 1): [ep_off (n_eps+1) i64][reward T][rtg T][reward_stacked T*F][rtg_stacked T*F]
+  const size_t off_bytes = (((size_t)(n_eps + 1) * 8) + 255) & ~(size_t)255;
+  ARP_TRY(ensure_scratch(h, 1, off_bytes + (size_t)T * 4 * (2 + 2 * F) + 1024));
+  LabelTmp tmp;
+  ARP_TRY(carve_label_tmp(h, T, &tmp));
+  int64_t* d_off = reinterpret_cast<int64_t*>(h->scratch[1]);
+  float* d_r = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(h->scratch[1]) + off_bytes);
+  float* d_g = d_r + T;
+  float* d_rs = d_g + T;
+  float* d_gs = d_rs + (size_t)T * F;
+  ARP_CUDA(h, cudaMemcpyAsync(d_off, ep_offsets_host, (size_t)(n_eps + 1) * 8, cudaMemcpyHostToDevice, st));
+  // double-buffered: chunk i+1's frames (only the scored image of each row) cross PCIe while chunk i is encoded
+  const int64_t nchunks = (T + B - 1) / B;
+  int rc = ARP_OK;
+  for (int64_t ci = 0; ci < nchunks && rc == ARP_OK; ++ci) {
+    const int buf = (int)(ci & 1);
+    const int64_t t0 = ci * B, n = std::min(B, T - t0);
+    if (ci >= 2) cudaStreamWaitEvent(h->copy_stream, h->ev_consumed[buf], 0);
+    cudaError_t e = cudaMemcpy2DAsync(h->stage_dev[buf], frame_bytes, ob_host + t0 * row_stride_bytes,
+                                      (size_t)row_stride_bytes, frame_bytes, (size_t)n, cudaMemcpyHostToDevice,
+                                      h->copy_stream);
+    if (e != cudaSuccess) { rc = fail(h, ARP_ERR_CUDA, "H2D frames failed: %s", cudaGetErrorString(e)); break; }
+    cudaEventRecord(h->ev_copied[buf], h->copy_stream);
+    cudaStreamWaitEvent(st, h->ev_copied[buf], 0);
+    if ((rc = encode_chunk(h, h->stage_dev[buf], n, (int64_t)frame_bytes, st)) != ARP_OK) break;
+    if (!h->goal) rc = head_chunk(h, n, d_r + t0, nullptr, nullptr, st);
+    else rc = head_chunk(h, n, nullptr, nullptr, tmp.feats + t0 * h->feat_dim, st);
+    cudaEventRecord(h->ev_consumed[buf], st);
+  }
+  if (rc == ARP_OK && h->goal) rc = goal_rewards(h, tmp, T, d_off, n_eps, d_r, st);
+  if (rc == ARP_OK) rc = scan_launch(h, d_r, T, d_off, n_eps, F, 1.0f, d_g, d_rs, d_gs, st);
+  if (rc == ARP_OK) {
+    cudaError_t e = cudaSuccess;
+    if (reward_host && e == cudaSuccess) e = cudaMemcpyAsync(reward_host, d_r, (size_t)T * 4, cudaMemcpyDeviceToHost, st);
+    if (rtg_host && e == cudaSuccess) e = cudaMemcpyAsync(rtg_host, d_g, (size_t)T * 4, cudaMemcpyDeviceToHost, st);
+    if (reward_stacked_host && e == cudaSuccess) e = cudaMemcpyAsync(reward_stacked_host, d_rs, (size_t)T * F * 4, cudaMemcpyDeviceToHost, st);
+    if (rtg_stacked_host && e == cudaSuccess) e = cudaMemcpyAsync(rtg_stacked_host, d_gs, (size_t)T * F * 4, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) rc = fail(h, ARP_ERR_CUDA, "label_host tail failed: %s", cudaGetErrorString(e));
+  }
+  cudaStreamSynchronize(h->copy_stream);
+  cudaStreamSynchronize(st);
+  return rc;
+}
+
+// ------------------------------------------------------------------------------------------------
+// C ABI: seams / unit-test hooks
+// ------------------------------------------------------------------------------------------------
+extern "C" int arp_decode_only(ArpHandle* h, const uint8_t* ob_dev, int64_t T, int64_t row_stride_bytes,
+                               float* chw_dev, void* stream) {
+  if (!h || !chw_dev || (T > 0 && !ob_dev)) return fail(h, ARP_ERR_INVALID, "null argument");
+  ARP_CUDA(h, cudaSetDevice(h->cfg.device));
+  return launch_decode(h, ob_dev, T, row_stride_bytes, chw_dev, DEC_OUT_CHW_F32, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int arp_gemm_bf16(ArpHandle* h, const void* a_dev, const void* w_dev, void* out_dev, int32_t out_dtype,
+                             int64_t M, int32_t N, int32_t K, const float* bias_dev, const float* resid_dev,
+                             int32_t act, void* stream) {
+  if (!h || !a_dev || !w_dev || !out_dev) return fail(h, ARP_ERR_INVALID, "null argument");
+  if (act < 0 || act > 2 || (out_dtype != ARP_F32 && out_dtype != ARP_BF16)) return fail(h, ARP_ERR_INVALID, "bad act / out_dtype");
+  ARP_CUDA(h, cudaSetDevice(h->cfg.device));
+  return launch_gemm(h, static_cast<const bf16*>(a_dev), M, static_cast<const bf16*>(w_dev), out_dev,
+                     out_dtype == ARP_F32, act, M, N, K, N, bias_dev, resid_dev, N, nullptr, 0,
+                     static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int arp_layernorm_bf16(ArpHandle* h, const float* x_dev, const float* gamma_dev, const float* beta_dev,
+                                  void* y_dev, int64_t M, void* stream) {
+  if (!h || !x_dev || !gamma_dev || !beta_dev || !y_dev) return fail(h, ARP_ERR_INVALID, "null argument");
+  ARP_CUDA(h, cudaSetDevice(h->cfg.device));
+  return launch_ln_bf16(h, x_dev, gamma_dev, beta_dev, static_cast<bf16*>(y_dev), M, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int arp_attention(ArpHandle* h, const void* qkv_dev, void* out_dev, int32_t B, int32_t tokens,
+                             void* stream) {
+  if (!h || !qkv_dev || !out_dev) return fail(h, ARP_ERR_INVALID, "null argument");
+  ARP_CUDA(h, cudaSetDevice(h->cfg.device));
+  return launch_attention(h, static_cast<const bf16*>(qkv_dev), static_cast<bf16*>(out_dev), B, tokens,
+                          static_cast<cudaStream_t>(stream));
+}

@@ -1,0 +1,184 @@
+// Reward heads (SURVEY.md §2 K9 / K10 epilogues): everything after the last resblock, fused per frame.
+//
+//  clip head      f = ln_post(x[:,0]) @ proj ; reward = exp(logit_scale) * <f/|f|, t/|t|>
+//                 (openai/CLIP VisionTransformer tail + CLIP.forward, called at label_reward.py:141-145)
+//  adapter head   a = sigma(w) * feat + (1 - sigma(w)) * mlp(feat) ; L2-normalise ; same cosine
+//                 (finetune_module/clip_multiscale_adapter.py:145-151, label_reward.py:213-228);
+//                 "ensemble" variant normalises each of the 13 512-wide scales separately and
+//                 averages the 13 cosines (label_reward.py:217-222).
+//  Text embeddings arrive already L2-normalised (cached once per run; the reference re-runs the
+//  text tower every episode, label_reward.py:135-138). All n_text cosines are produced; `reduce`
+//  picks row 0 (what the reference actually does — SURVEY.md Q1) or the mean.
+// fp32 throughout: these are a few hundred KFLOP per frame, L2-resident weights.
+#pragma once
+
+#include "common.cuh"
+
+namespace arp {
+
+constexpr int HEAD_MAX_TEXT = 16;
+enum HeadReduce : int { REDUCE_FIRST = 0, REDUCE_MEAN = 1 };
+
+template <int NT>
+__device__ __forceinline__ float block_sum(float v, float* scratch) {
+  // all NT threads call; returns the total to every thread
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  v = warp_sum(v);
+  __syncthreads();
+  if (lane == 0) scratch[warp] = v;
+  __syncthreads();
+  float t = 0.f;
+#pragma unroll
+  for (int i = 0; i < NT / 32; ++i) t += scratch[i];
+  return t;
+}
+
+// One CTA (256 threads) per frame.
+//   x        fp32 [B*tokens, W]   residual stream after the last block (row b*tokens = class token)
+//   proj     fp32 [W, E]
+//   text     fp32 [n_text, E] unit rows (may be null when only features are wanted)
+//   feat_out fp32 [B, ld_feat] : un-normalised f written at column feat_col0 (adapter / goal modes) or null
+//   logits   fp32 [B, n_text] or null ; reward fp32 [B] or null
+template <int W, int E>
+__global__ void __launch_bounds__(256)
+clip_head_kernel(const float* __restrict__ x, int tokens, const float* __restrict__ ln_g,
+                 const float* __restrict__ ln_b, float eps, const float* __restrict__ proj,
+                 const float* __restrict__ text, int n_text, float scale, int reduce,
+                 float* __restrict__ feat_out, int ld_feat, int feat_col0, float* __restrict__ logits,
+                 float* __restrict__ reward) {
+  static_assert(W % 256 == 0 && E % 256 == 0, "head widths must be multiples of the CTA size");
+  __shared__ float s_f[W];
+  __shared__ float s_y[E];
+  __shared__ float s_red[8];
+  const int b = blockIdx.x, tid = threadIdx.x;
+  const float* xr = x + static_cast<size_t>(b) * tokens * W;
+
+  float v[W / 256];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < W / 256; ++i) { v[i] = xr[tid + i * 256]; s += v[i]; }
+  const float mean = block_sum<256>(s, s_red) * (1.0f / W);
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < W / 256; ++i) { const float d = v[i] - mean; q += d * d; }
+  const float rstd = rsqrtf(block_sum<256>(q, s_red) * (1.0f / W) + eps);
+#pragma unroll
+  for (int i = 0; i < W / 256; ++i) {
+    const int c = tid + i * 256;
+    s_f[c] = (v[i] - mean) * rstd * ln_g[c] + ln_b[c];
+  }
+  __syncthreads();
+
+  float y[E / 256];
+#pragma unroll
+  for (int j = 0; j < E / 256; ++j) y[j] = 0.f;
+#pragma unroll 4
+  for (int k = 0; k < W; ++k) {
+    const float fk = s_f[k];
+#pragma unroll
+    for (int j = 0; j < E / 256; ++j) y[j] = fmaf(fk, __ldg(proj + static_cast<size_t>(k) * E + tid + j * 256), y[j]);
+  }
+  float n2 = 0.f;
+#pragma unroll
+  for (int j = 0; j < E / 256; ++j) {
+    s_y[tid + j * 256] = y[j];
+    n2 += y[j] * y[j];
+    if (feat_out) feat_out[static_cast<size_t>(b) * ld_feat + feat_col0 + tid + j * 256] = y[j];
+  }
+  const float inv_norm = 1.0f / sqrtf(block_sum<256>(n2, s_red));
+  if (text == nullptr) return;
+
+  // cosines: warp w handles texts w, w+8, ...
+  __shared__ float s_logit[HEAD_MAX_TEXT];
+  const int warp = tid >> 5, lane = tid & 31;
+  for (int t = warp; t < n_text; t += 8) {
+    float d = 0.f;
+    for (int k = lane; k < E; k += 32) d = fmaf(s_y[k], __ldg(text + static_cast<size_t>(t) * E + k), d);
+    d = warp_sum(d);
+    if (lane == 0) {
+      const float lg = scale * (d * inv_norm);
+      s_logit[t] = lg;
+      if (logits) logits[static_cast<size_t>(b) * n_text + t] = lg;
+    }
+  }
+  __syncthreads();
+  if (tid == 0 && reward) {
+    float r = s_logit[0];
+    if (reduce == REDUCE_MEAN) {
+      for (int t = 1; t < n_text; ++t) r += s_logit[t];
+      r /= static_cast<float>(n_text);
+    }
+    reward[b] = r;
+  }
+}
+
+// Adapter gate + normalise + cosine. One CTA per frame, one warp per 512-wide scale (S warps).
+//   feat, mlp fp32 [B, S*E]; text fp32 [n_text, S*E] (unit over S*E, or per-scale unit when ensemble)
+template <int S, int E>
+__global__ void __launch_bounds__(S * 32)
+adapter_head_kernel(const float* __restrict__ feat, const float* __restrict__ mlp, float res,
+                    const float* __restrict__ text, int n_text, float scale, int ensemble, int reduce,
+                    float* __restrict__ logits, float* __restrict__ reward, float* __restrict__ adapted_out) {
+  __shared__ float s_n2[S];
+  __shared__ float s_dot[S][HEAD_MAX_TEXT];
+  const int b = blockIdx.x, sidx = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const size_t base = static_cast<size_t>(b) * S * E + static_cast<size_t>(sidx) * E;
+  float a[E / 32];
+  float n2 = 0.f;
+#pragma unroll
+  for (int i = 0; i < E / 32; ++i) {
+    const int c = lane + i * 32;
+    a[i] = res * feat[base + c] + (1.0f - res) * mlp[base + c];
+    n2 += a[i] * a[i];
+    if (adapted_out) adapted_out[base + c] = a[i];
+  }
+  n2 = warp_sum(n2);
+  if (lane == 0) s_n2[sidx] = n2;
+  for (int t = 0; t < n_text; ++t) {
+    const float* tr = text + static_cast<size_t>(t) * S * E + static_cast<size_t>(sidx) * E;
+    float d = 0.f;
+#pragma unroll
+    for (int i = 0; i < E / 32; ++i) d = fmaf(a[i], __ldg(tr + lane + i * 32), d);
+    d = warp_sum(d);
+    if (lane == 0) s_dot[sidx][t] = d;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float racc = 0.f;
+    const int n_use = reduce == REDUCE_MEAN ? n_text : 1;
+    for (int t = 0; t < n_text; ++t) {
+      float lg;
+      if (ensemble) {
+        float acc = 0.f;
+        for (int s = 0; s < S; ++s) acc += s_dot[s][t] / fmaxf(sqrtf(s_n2[s]), 1e-12f);
+        lg = scale * acc / static_cast<float>(S);
+      } else {
+        float tot = 0.f, d = 0.f;
+        for (int s = 0; s < S; ++s) { tot += s_n2[s]; d += s_dot[s][t]; }
+        lg = scale * (d / fmaxf(sqrtf(tot), 1e-12f));
+      }
+      if (logits) logits[static_cast<size_t>(b) * n_text + t] = lg;
+      if (t < n_use) racc += lg;
+    }
+    if (reward) reward[b] = racc / static_cast<float>(n_use);
+  }
+}
+
+// Goal-conditioned reward (label_reward.py:148-163,180-196): r_t = sign * || f_t - f_goal ||_2 where the
+// goal is the LAST frame of the episode. One warp per frame. sign = -1 for "clip_goal_conditioned",
+// +1 for the adapter "_goal_conditioned" variant (the reference omits the minus there, :193-195).
+__global__ void __launch_bounds__(256)
+goal_distance_kernel(const float* __restrict__ feat, int dim, const long long* __restrict__ frame_goal,
+                     long long T, float sign, float* __restrict__ reward) {
+  const long long t = static_cast<long long>(blockIdx.x) * 8 + (threadIdx.x >> 5);
+  if (t >= T) return;
+  const int lane = threadIdx.x & 31;
+  const float* a = feat + t * dim;
+  const float* g = feat + frame_goal[t] * dim;
+  float s = 0.f;
+  for (int k = lane; k < dim; k += 32) { const float d = a[k] - g[k]; s = fmaf(d, d, s); }
+  s = warp_sum(s);
+  if (lane == 0) reward[t] = sign * sqrtf(s);
+}
+
+}  // namespace arp

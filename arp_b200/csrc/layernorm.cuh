@@ -1,0 +1,113 @@
+// LayerNorm and the small row-wise kernels around the ViT residual stream
+// (CLIP computes LayerNorm in fp32, eps = 1e-5 — in-tree mirror
+// arp_dt/models/openai/layers.py:9,246-248,322,331).
+//
+// All are HBM-bound: one warp per 768-wide row, the row lives in registers
+// (24 floats / lane, float4 loads), two-pass mean/variance, warp-shuffle reductions.
+#pragma once
+
+#include "common.cuh"
+
+namespace arp {
+
+template <int W>
+struct RowRegs {
+  static_assert(W % 128 == 0, "row width must be a multiple of 128");
+  static constexpr int kVec = W / 128;  // float4 per lane
+  float4 v[kVec];
+};
+
+template <int W>
+__device__ __forceinline__ void ln_row(const float* __restrict__ x, const float* __restrict__ gamma,
+                                       const float* __restrict__ beta, float eps, RowRegs<W>& r) {
+  const int lane = threadIdx.x & 31;
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < RowRegs<W>::kVec; ++i) {
+    r.v[i] = *reinterpret_cast<const float4*>(x + (i * 32 + lane) * 4);
+    s += (r.v[i].x + r.v[i].y) + (r.v[i].z + r.v[i].w);
+  }
+  const float mean = warp_sum(s) * (1.0f / W);
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < RowRegs<W>::kVec; ++i) {
+    const float a = r.v[i].x - mean, b = r.v[i].y - mean, c = r.v[i].z - mean, d = r.v[i].w - mean;
+    q += (a * a + b * b) + (c * c + d * d);
+  }
+  const float rstd = rsqrtf(warp_sum(q) * (1.0f / W) + eps);
+#pragma unroll
+  for (int i = 0; i < RowRegs<W>::kVec; ++i) {
+    const float4 g = __ldg(reinterpret_cast<const float4*>(gamma + (i * 32 + lane) * 4));
+    const float4 b = __ldg(reinterpret_cast<const float4*>(beta + (i * 32 + lane) * 4));
+    r.v[i].x = (r.v[i].x - mean) * rstd * g.x + b.x;
+    r.v[i].y = (r.v[i].y - mean) * rstd * g.y + b.y;
+    r.v[i].z = (r.v[i].z - mean) * rstd * g.z + b.z;
+    r.v[i].w = (r.v[i].w - mean) * rstd * g.w + b.w;
+  }
+}
+
+// y(bf16)[M,W] = LN(x fp32 [M,W])                 (ln_1 / ln_2 feeding the QKV and c_fc GEMMs)
+template <int W>
+__global__ void __launch_bounds__(256)
+layernorm_f32_bf16_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
+                          const float* __restrict__ beta, __nv_bfloat16* __restrict__ y, int M, float eps) {
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= M) return;
+  const int lane = threadIdx.x & 31;
+  RowRegs<W> r;
+  ln_row<W>(x + static_cast<size_t>(row) * W, gamma, beta, eps, r);
+  uint2* out = reinterpret_cast<uint2*>(y + static_cast<size_t>(row) * W);
+#pragma unroll
+  for (int i = 0; i < RowRegs<W>::kVec; ++i)
+    out[i * 32 + lane] = make_uint2(pack_bf16(r.v[i].x, r.v[i].y), pack_bf16(r.v[i].z, r.v[i].w));
+}
+
+// x fp32 [M,W] = LN(x) in place                    (ln_pre)
+template <int W>
+__global__ void __launch_bounds__(256)
+layernorm_f32_inplace_kernel(float* __restrict__ x, const float* __restrict__ gamma,
+                             const float* __restrict__ beta, int M, float eps) {
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= M) return;
+  const int lane = threadIdx.x & 31;
+  RowRegs<W> r;
+  float* xr = x + static_cast<size_t>(row) * W;
+  ln_row<W>(xr, gamma, beta, eps, r);
+#pragma unroll
+  for (int i = 0; i < RowRegs<W>::kVec; ++i) reinterpret_cast<float4*>(xr)[i * 32 + lane] = r.v[i];
+}
+
+// taps(bf16)[B, ld_taps] columns [layer*W, (layer+1)*W) = x[b*tokens + 0, :]
+// The CLS row of every resblock output; replaces the reference's forward hooks
+// (finetune_module/utils.py:6-18, clip_multiscale_adapter.py:138-143).
+template <int W>
+__global__ void __launch_bounds__(256)
+gather_cls_bf16_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ taps, int B, int tokens,
+                       int ld_taps, int col0) {
+  const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (b >= B) return;
+  const int lane = threadIdx.x & 31;
+  const float4* src = reinterpret_cast<const float4*>(x + static_cast<size_t>(b) * tokens * W);
+  uint2* dst = reinterpret_cast<uint2*>(taps + static_cast<size_t>(b) * ld_taps + col0);
+#pragma unroll
+  for (int i = 0; i < W / 128; ++i) {
+    const float4 v = src[i * 32 + lane];
+    dst[i * 32 + lane] = make_uint2(pack_bf16(v.x, v.y), pack_bf16(v.z, v.w));
+  }
+}
+
+// fp32 -> bf16 conversion of a contiguous buffer (weights at load time, adapter features).
+__global__ void __launch_bounds__(256)
+f32_to_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, size_t n) {
+  size_t i = (static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x) * 4;
+  const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x * 4;
+  for (; i + 3 < n; i += stride) {
+    const float4 v = *reinterpret_cast<const float4*>(src + i);
+    *reinterpret_cast<uint2*>(dst + i) = make_uint2(pack_bf16(v.x, v.y), pack_bf16(v.z, v.w));
+  }
+  if (i < n) {  // ragged tail (n % 4 != 0): at most one thread lands here
+    for (size_t j = i; j < n; ++j) dst[j] = __float2bfloat16_rn(src[j]);
+  }
+}
+
+}  // namespace arp

@@ -1,0 +1,167 @@
+/* arp_b200.h — C ABI of the B200-native reward-labeling hot path.
+ *
+ * The reference (csmile-1006/ARP) has no FFI for this path: it is plain Python calling PyTorch
+ * (arp_dt/label_reward.py). This header is the boundary a maintainer would bind from that Python
+ * with ctypes: plain pointers and sizes, no torch types, int status codes,
+ * nothing thrown across the ABI. Each entry point names the reference code it replaces.
+ *
+ * Conventions
+ *   - one ArpHandle per GPU, used from one host thread at a time;
+ *   - device pointers are caller-owned; work is stream-ordered on the `stream` argument
+ *     (a cudaStream_t passed as void*; NULL = the legacy default stream);
+ *   - return 0 (ARP_OK) or a negative ArpStatus; arp_last_error() gives the message;
+ *   - there is NO CPU fallback: without an sm_100 device arp_create fails with ARP_ERR_NO_DEVICE.
+ */
+#ifndef ARP_B200_H_
+#define ARP_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ARP_B200_ABI_VERSION 1
+
+#if defined(__GNUC__)
+#define ARP_API __attribute__((visibility("default")))
+#else
+#define ARP_API
+#endif
+
+typedef enum ArpStatus {
+  ARP_OK = 0,
+  ARP_ERR_INVALID = -1,     /* bad argument / unsupported geometry */
+  ARP_ERR_CUDA = -2,        /* a CUDA runtime / driver call failed */
+  ARP_ERR_STATE = -3,       /* weights or text embeddings not set yet */
+  ARP_ERR_NO_DEVICE = -4,   /* no CUDA device, or not compute capability 10.x */
+  ARP_ERR_UNKNOWN_KEY = -5  /* arp_set_weight: name is not part of the model */
+} ArpStatus;
+
+/* label_reward.py:109-121 vs clip_multiscale_adapter.py:121-133 */
+typedef enum ArpPreprocess { ARP_PRE_PIL_BICUBIC = 0, ARP_PRE_BILINEAR = 1 } ArpPreprocess;
+/* label_reward.py:128 "clip" | :166 "clip_ft" | :217-222 3-D feature branch | :148,180 goal-conditioned */
+typedef enum ArpHead {
+  ARP_HEAD_CLIP = 0,
+  ARP_HEAD_ADAPTER = 1,
+  ARP_HEAD_ADAPTER_ENSEMBLE = 2,
+  ARP_HEAD_CLIP_GOAL = 3,
+  ARP_HEAD_ADAPTER_GOAL = 4
+} ArpHead;
+/* label_reward.py:142-145: row 0 of logits_per_text is what the reference takes;
+ * MEAN is the envs/vl_reward.py:19-22 behaviour. */
+typedef enum ArpReduce { ARP_REDUCE_FIRST = 0, ARP_REDUCE_MEAN = 1 } ArpReduce;
+
+typedef enum ArpDType { ARP_F32 = 0, ARP_BF16 = 1, ARP_F16 = 2 } ArpDType;
+
+typedef struct ArpHandle ArpHandle;
+
+typedef struct ArpConfig {
+  int32_t struct_size; /* sizeof(ArpConfig), for forward compatibility */
+  int32_t device;      /* CUDA device ordinal */
+  int32_t patch;       /* 16 = ViT-B/16 (label_reward.py:126), 32 = ViT-B/32 */
+  int32_t width;       /* 768 */
+  int32_t layers;      /* 12 */
+  int32_t heads;       /* 12 (width / 64) */
+  int32_t embed_dim;   /* 512 */
+  int32_t in_h, in_w;  /* dataset frame size (64 or 256 for procgen) */
+  int32_t use_crop;    /* label_reward.py:90-106: centre crop to (H//2, W//2) before the resize */
+  int32_t preprocess;  /* ArpPreprocess */
+  int32_t head;        /* ArpHead */
+  int32_t reduce;      /* ArpReduce */
+  int32_t max_batch;   /* frames per internal chunk (workspace is sized for this) */
+} ArpConfig;
+
+/* ------------------------------------------------------------------------------------------------
+ * lifetime
+ * ---------------------------------------------------------------------------------------------- */
+/* replaces clip.load("ViT-B/16", device) + transform construction (label_reward.py:89-130, :165-178) */
+ARP_API int arp_create(const ArpConfig* cfg, ArpHandle** out);
+ARP_API void arp_destroy(ArpHandle* h);
+ARP_API const char* arp_last_error(const ArpHandle* h); /* h may be NULL: last error of arp_create */
+ARP_API int arp_abi_version(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * weights: one call per state_dict entry, names exactly as in openai/CLIP's state_dict
+ * ("visual.conv1.weight", "visual.transformer.resblocks.3.attn.in_proj_weight", "visual.proj", ...)
+ * and, for the adapter heads, finetune_module/clip_multiscale_adapter.py's
+ * ("image_intermediate_linear.weight", "image_adapter.layers.0.weight", "image_adapter.layers.3.bias",
+ *  "image_residual_weight"). `data` is a DEVICE pointer to a contiguous tensor of `dtype`; the library
+ * keeps its own packed copy (bf16 for GEMM operands, fp32 for norms / biases / tables).
+ * Text-tower keys are accepted and ignored (ARP_OK); unknown keys give ARP_ERR_UNKNOWN_KEY.
+ * replaces model.load_state_dict(torch.load(model_ckpt_dir), strict=False) (label_reward.py:175-176)
+ * ---------------------------------------------------------------------------------------------- */
+ARP_API int arp_set_weight(ArpHandle* h, const char* name, const void* data, int32_t dtype, const int64_t* shape,
+                   int32_t ndim, void* stream);
+/* number of weights still missing for the configured head (0 = ready) */
+ARP_API int arp_missing_weights(const ArpHandle* h, char* names_out, int64_t names_cap);
+
+/* Cached instruction embedding(s): fp32 [n_text, dim] DEVICE rows, already L2-normalised
+ * (per 512-wide scale for ARP_HEAD_ADAPTER_ENSEMBLE); dim = 512 (clip) or 6656 (adapter heads).
+ * logit_scale_exp = model.logit_scale.exp() (label_reward.py:141, :213-216).
+ * replaces clip.tokenize + encode_text, which the reference re-runs every episode (:135-138). */
+ARP_API int arp_set_text(ArpHandle* h, const float* text_emb_dev, int32_t n_text, int32_t dim, float logit_scale_exp,
+                 void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * the hot path
+ * ---------------------------------------------------------------------------------------------- */
+/* Score T dataset rows and build the per-episode return-to-go tokens. Replaces the whole episode loop
+ * label_reward.py:265-271 (compute_reward + discount_cumsum + stack_outputs x2).
+ *   ob_dev            uint8, row t's image to score starts at ob_dev + t*row_stride_bytes
+ *                     (for the reference layout ob[T,F,H,W,3] pass &ob[0,F-1] and stride F*H*W*3: label_reward.py:268)
+ *   ep_offsets_dev    int64 [n_eps+1] DEVICE: episode e = rows [off[e], min(off[e+1], T))   (:82-83, :267)
+ *   num_frames        F of the stacked outputs (:81)
+ *   reward_dev        fp32 [T] per-frame reward (may be NULL)
+ *   rtg_dev           fp32 [T] per-frame return-to-go (may be NULL)
+ *   reward_stacked_dev, rtg_stacked_dev   fp32 [T,F] = the two datasets the reference writes (:270-271)
+ */
+ARP_API int arp_label(ArpHandle* h, const uint8_t* ob_dev, int64_t T, int64_t row_stride_bytes,
+              const int64_t* ep_offsets_dev, int32_t n_eps, int32_t num_frames, float* reward_dev, float* rtg_dev,
+              float* reward_stacked_dev, float* rtg_stacked_dev, void* stream);
+
+/* Same contract with HOST buffers (pageable or pinned): frames are streamed to the device in chunks on
+ * a copy stream, overlapped with compute, and the four outputs are copied back. This is the call a
+ * drop-in label_reward() makes per image key; it synchronises before returning. */
+ARP_API int arp_label_host(ArpHandle* h, const uint8_t* ob_host, int64_t T, int64_t row_stride_bytes,
+                   const int64_t* ep_offsets_host, int32_t n_eps, int32_t num_frames, float* reward_host,
+                   float* rtg_host, float* reward_stacked_host, float* rtg_stacked_host);
+
+/* compute_reward only (label_reward.py:132-146 / :200-230): per-frame rewards, optional [T,n_text] logits. */
+ARP_API int arp_compute_reward(ArpHandle* h, const uint8_t* ob_dev, int64_t T, int64_t row_stride_bytes, float* reward_dev,
+                       float* logits_dev, void* stream);
+
+/* model.encode_image (un-normalised, [T, embed_dim]) resp. the adapter's encode_image ([T, 13*512], normalised).
+ * Goal-conditioned heads and parity tests use it (label_reward.py:156, :187). */
+ARP_API int arp_encode_image(ArpHandle* h, const uint8_t* ob_dev, int64_t T, int64_t row_stride_bytes, float* feat_dev,
+                     void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * seams of the reference (unit-test hooks; same kernels the hot path runs)
+ * ---------------------------------------------------------------------------------------------- */
+/* transform(img) for every row (label_reward.py:92-121) or model.preprocess (clip_multiscale_adapter.py:121-133):
+ * fp32 [T,3,224,224] */
+ARP_API int arp_decode_only(ArpHandle* h, const uint8_t* ob_dev, int64_t T, int64_t row_stride_bytes, float* chw_dev,
+                    void* stream);
+/* discount_cumsum + stack_outputs (label_reward.py:232-254). Needs no weights. h may come from any config. */
+ARP_API int arp_scan_only(ArpHandle* h, const float* reward_dev, int64_t T, const int64_t* ep_offsets_dev, int32_t n_eps,
+                  int32_t num_frames, float gamma, float* rtg_dev, float* reward_stacked_dev,
+                  float* rtg_stacked_dev, void* stream);
+/* C[M,N] = act(A[M,K] W[N,K]^T + bias) (+ resid): the tcgen05 GEMM behind every linear layer.
+ * A, W bf16 device; out bf16 (out_dtype=ARP_BF16) or fp32; act 0 none, 1 QuickGELU, 2 ReLU;
+ * bias / resid fp32 or NULL; N % 256 == 0, K % 64 == 0. */
+ARP_API int arp_gemm_bf16(ArpHandle* h, const void* a_dev, const void* w_dev, void* out_dev, int32_t out_dtype, int64_t M,
+                  int32_t N, int32_t K, const float* bias_dev, const float* resid_dev, int32_t act, void* stream);
+/* y = LayerNorm(x) over 768-wide rows, fp32 in, bf16 out */
+ARP_API int arp_layernorm_bf16(ArpHandle* h, const float* x_dev, const float* gamma_dev, const float* beta_dev, void* y_dev,
+                       int64_t M, void* stream);
+/* softmax(QK^T/8)V for qkv bf16 [B*tokens, 3*width] -> bf16 [B*tokens, width]; tokens = 197 or 50 */
+ARP_API int arp_attention(ArpHandle* h, const void* qkv_dev, void* out_dev, int32_t B, int32_t tokens, void* stream);
+
+/* counters: kernels launched by this handle since creation (bench.py's gpu_launches) */
+ARP_API int64_t arp_launch_count(const ArpHandle* h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ARP_B200_H_ */
