@@ -175,7 +175,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
           }
           if (ACT == ACT_QUICKGELU) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = v[j] / (1.0f + __expf(-1.702f * v[j]));
+            for (int j = 0; j < 32; ++j) v[j] = __fdividef(v[j], 1.0f + __expf(-1.702f * v[j]));
           } else if (ACT == ACT_RELU) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.0f);

@@ -1,0 +1,351 @@
+"""Drop-in for the reference's offline reward labeler, `arp_dt/label_reward.py`.
+
+Same entry point, same arguments and defaults (label_reward.py:44-60), same CLI flags (:295-312), same
+`model_type` names and checkpoint format, same output datasets
+    f"{img_key}_{model_type}_reward[_{inst_type}]",  f"{img_key}_{model_type}_pos_rtg[_{inst_type}]"
+as float32 [T, num_frames] (:257-289) — but every frame is scored by the native sm_100a library
+(include/arp_b200.h) instead of a Python loop over PyTorch calls:
+
+    reference (per episode, :265-271)                      here (per slab of many episodes)
+    -------------------------------------------------      ----------------------------------------------
+    g[img_key][traj, -1]  (host gather)                    strided host pointer -> cudaMemcpy2DAsync
+    [preprocess(img) for img in imgs]  (PIL, 1 thread)     fused decode kernel (Pillow-exact)
+    clip.tokenize + text tower, every episode              text embedding cached once per run
+    model(images, text)                                    tcgen05 ViT + fused cosine head
+    discount_cumsum / stack_outputs  (python loops)        per-episode scan + window stack kernel
+
+There is no CPU fallback: without the built library and a B200 this module raises.
+
+Keyword-only extensions (all optional; defaults reproduce the reference):
+    clip_state_dict  CLIP weights (openai/CLIP state_dict keys). The reference downloads pretrained
+                     weights inside clip.load (:126); offline, pass them here or set ARP_CLIP_CHECKPOINT.
+    arch             "ViT-B/16" (what the reference hard-codes) or "ViT-B/32".
+    reduce           "first" (reference behaviour) or "mean" (envs/vl_reward.py semantics).
+    max_batch        frames per device chunk.      slab_frames  frames per host slab.
+    device           CUDA ordinal (default: LOCAL_RANK or 0).
+    distributed      shard episodes over torch.distributed ranks (default: on when a process group exists).
+"""
+from __future__ import annotations
+
+import argparse
+import os
+
+import numpy as np
+import torch
+
+from . import capi
+from .instructions import get_clip_instruct, get_clip_special_instruct
+from .sharding import gather_rows, partition_episodes
+from .store import open_store
+from .text_tower import adapter_text_embedding, clip_text_embedding
+from .tokenizer import tokenize
+from .weights import load_checkpoint
+
+
+def center_crop(image, crop_size):
+    """label_reward.py:15-36 (imported by envs/vl_reward.py:6 and envs/rollout_procgen.py:14): [N,H,W,C] centre crop."""
+    _, H, W, _ = image.shape
+    ch, cw = crop_size
+    top, left = int((H - ch) / 2), int((W - cw) / 2)
+    return image[:, top:top + ch, left:left + cw, :]
+
+
+def episode_index(g, done_key=None):
+    """label_reward.py:71-87 — (len_data, num_frames, g_traj_idx)."""
+    if done_key is None:
+        for cand in ("done", "rewards", "is_terminal"):
+            if g.get(cand):
+                done_key = cand
+                break
+        else:
+            raise ValueError
+    try:
+        len_data, num_frames = g[done_key].shape[:2]
+        idx = list(np.nonzero(np.asarray(g[done_key][:, -1]))[0] + 1)
+        idx.insert(0, 0)
+    except Exception:  # noqa: BLE001 — the reference's bare `except:` fallback for the "time" layout (:84-87)
+        len_data, num_frames = g["time"].shape[:2]
+        idx = list(np.where(np.asarray(g["time"][:, -1, 0]) == 1.0)[0])
+        idx.append(len(g["time"]))
+    return int(len_data), int(num_frames), [int(i) for i in idx]
+
+
+def _head_for(model_type: str) -> tuple[int, int]:
+    """model_type -> (ArpHead, ArpPreprocess), following the dispatch at label_reward.py:123-230."""
+    if model_type == "clip":
+        return capi.HEAD_CLIP, capi.PRE_PIL_BICUBIC
+    if model_type == "clip_goal_conditioned":
+        return capi.HEAD_CLIP_GOAL, capi.PRE_PIL_BICUBIC
+    if model_type.startswith("clip_"):
+        # Only "clip_ft" constructs a model in the reference (:166-173); other clip_* names crash there
+        # (SURVEY.md Q3). They are served by the same CLIPMultiscaleAdapter weights.
+        if "_goal_conditioned" in model_type:
+            return capi.HEAD_ADAPTER_GOAL, capi.PRE_BILINEAR
+        if "ensemble" in model_type:
+            return capi.HEAD_ADAPTER_ENSEMBLE, capi.PRE_BILINEAR
+        return capi.HEAD_ADAPTER, capi.PRE_BILINEAR
+    raise ValueError(f"unsupported model_type {model_type!r}: the labeler only defines clip* reward models")
+
+
+def _resolve_clip_weights(clip_state_dict, arch: str) -> dict:
+    if clip_state_dict is not None:
+        return clip_state_dict
+    path = os.environ.get("ARP_CLIP_CHECKPOINT")
+    if path:
+        return load_checkpoint(path)
+    try:  # the reference's own route, if the real package and its cached weights exist
+        import clip  # type: ignore
+        model, _ = clip.load(arch, device="cpu")
+        return model.state_dict()
+    except Exception as e:  # noqa: BLE001
+        raise RuntimeError(
+            "CLIP weights unavailable: pass clip_state_dict=..., set ARP_CLIP_CHECKPOINT to a state_dict file, "
+            "or install openai/CLIP with its cached checkpoint (the reference downloads it in clip.load, "
+            "label_reward.py:126)") from e
+
+
+class RewardLabeler:
+    """Model + cached instruction embedding on one GPU; label() scores slabs of episodes.
+
+    This is the object form of the closures `compute_reward` / `discount_cumsum` / `stack_outputs`
+    that the reference builds inside label_reward() (:132-254)."""
+
+    def __init__(self, model_type: str, text, frame_hw: tuple[int, int], *, model_ckpt_dir=None,
+                 clip_state_dict=None, arch: str = "ViT-B/16", use_crop: bool = False, reduce: str = "first",
+                 max_batch: int = 512, device: int | None = None):
+        head, pre = _head_for(model_type)
+        adapter = head in (capi.HEAD_ADAPTER, capi.HEAD_ADAPTER_ENSEMBLE, capi.HEAD_ADAPTER_GOAL)
+        if adapter:
+            assert model_ckpt_dir is not None, "specify model_ckpt_dir"  # label_reward.py:174
+        if device is None:
+            device = int(os.environ.get("LOCAL_RANK", "0"))
+        self.model_type, self.device_index = model_type, device
+        patch = 32 if arch.endswith("/32") else 16
+        self.engine = capi.Engine(device=device, patch=patch, in_h=frame_hw[0], in_w=frame_hw[1],
+                                  use_crop=bool(use_crop), preprocess=pre, head=head,
+                                  reduce=capi.REDUCE_MEAN if reduce == "mean" else capi.REDUCE_FIRST,
+                                  max_batch=max_batch)
+        dev = self.engine.device
+        if adapter:
+            sd = load_checkpoint(model_ckpt_dir) if not isinstance(model_ckpt_dir, dict) else model_ckpt_dir
+            if not any(k.startswith("clip_model.") for k in sd):
+                # strict=False load in the reference (:176): CLIP tensors missing from the checkpoint keep
+                # the values clip.load gave them.
+                base = _resolve_clip_weights(clip_state_dict, arch)
+                sd = {**{"clip_model." + k: v for k, v in base.items()}, **sd}
+        else:
+            sd = _resolve_clip_weights(clip_state_dict, arch)
+        missing = self.engine.load_state_dict(sd, strict=False)
+        if missing:
+            raise RuntimeError(f"checkpoint lacks {len(missing)} tensors the {model_type} path needs, e.g. {missing[:3]}")
+        self.goal = self.engine.goal
+        if not self.goal:
+            texts = list(text) if isinstance(text, (list, tuple)) else [text]
+            tokens = tokenize(texts)
+            if adapter:
+                emb, scale = adapter_text_embedding(sd, tokens, dev, ensemble=head == capi.HEAD_ADAPTER_ENSEMBLE)
+            else:
+                emb, scale = clip_text_embedding(sd, tokens, dev)
+            self.engine.set_text(emb, scale)
+
+    def label_slab(self, ob: np.ndarray, ep_offsets: np.ndarray, num_frames: int):
+        """ob: host uint8 [T,F,H,W,3] (or [T,H,W,3]); ep_offsets: int64 [n+1] relative to the slab.
+        Returns host (reward[T], rtg[T], reward_stacked[T,F], rtg_stacked[T,F])."""
+        return self.engine.label_host(ob, ep_offsets, num_frames)
+
+    def close(self):
+        self.engine.close()
+
+
+def _slabs(ep_offsets: np.ndarray, e_lo: int, e_hi: int, slab_frames: int):
+    """Group whole episodes [e_lo, e_hi) into slabs of at most ~slab_frames frames (at least one episode)."""
+    e = e_lo
+    while e < e_hi:
+        j = e + 1
+        while j < e_hi and ep_offsets[j + 1] - ep_offsets[e] <= slab_frames:
+            j += 1
+        yield e, j
+        e = j
+
+
+def _rows_array(ds, lo: int, hi: int) -> np.ndarray:
+    """Rows [lo, hi) of an image dataset as a C-contiguous host array WITHOUT touching the frames that
+    are not scored when the container allows it (memory-mapped store); h5py reads only `[:, -1]`."""
+    arr = getattr(ds, "array", None)
+    if arr is not None and arr.flags.c_contiguous:
+        return arr[lo:hi]                       # strided pointer goes straight to arp_label_host
+    return np.ascontiguousarray(ds[lo:hi, -1])  # label_reward.py:268 — last stacked frame only
+
+
+def label_reward(
+    env_name,
+    distribution_mode,
+    num_levels,
+    start_level,
+    text,
+    base_path,
+    data_path=None,
+    image_keys="ob",
+    num_demonstrations=500,
+    num_frames=8,
+    env_type=None,
+    model_type="clip",
+    model_ckpt_dir=None,
+    use_crop=False,
+    inst_type="none",
+    *,
+    clip_state_dict=None,
+    arch="ViT-B/16",
+    reduce="first",
+    max_batch=512,
+    slab_frames=16384,
+    device=None,
+    distributed=None,
+):
+    image_keys = image_keys.split(", ")
+    if data_path is None:
+        dirname = (
+            f"{env_name}_{distribution_mode}_level{start_level}to{num_levels}_num{num_demonstrations}_frame{num_frames}"
+        )
+        if env_type != "none":
+            dirname += f"_{env_type}"
+        data_path = os.path.join(base_path, dirname, "data.hdf5")
+
+    import torch.distributed as dist
+    if distributed is None:
+        distributed = dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+    rank = dist.get_rank() if distributed else 0
+    world = dist.get_world_size() if distributed else 1
+
+    g = open_store(data_path, "a" if rank == 0 else "r")
+    try:
+        len_data, num_frames, g_traj_idx = episode_index(g)  # num_frames comes from the file (Q4)
+        n_eps = len(g_traj_idx) - 1
+        off = np.minimum(np.asarray(g_traj_idx, dtype=np.int64), len_data)  # min(idx[i+1], len_data) (:267)
+        H, W = g[image_keys[0]].shape[-3:-1]
+        if use_crop:
+            print(f"image_size: {g[image_keys[0]].shape[-2]}")  # label_reward.py:104-105
+
+        labeler = RewardLabeler(model_type, text, (int(H), int(W)), model_ckpt_dir=model_ckpt_dir,
+                                clip_state_dict=clip_state_dict, arch=arch, use_crop=use_crop, reduce=reduce,
+                                max_batch=max_batch, device=device)
+        target_keys = [f"{model_type}_reward", f"{model_type}_pos_rtg"]
+        if inst_type != "none":
+            target_keys = [f"{x}_{inst_type}" for x in target_keys]
+
+        shards = partition_episodes(off, world)
+        e_lo, e_hi = shards[rank]
+        for img_key in image_keys:
+            ds = g[img_key]
+            parts_r, parts_g = [], []
+            for s_lo, s_hi in _slabs(off, e_lo, e_hi, slab_frames):
+                lo, hi = int(off[s_lo]), int(off[s_hi])
+                if hi <= lo:
+                    continue
+                r, _, rs, gs = labeler.label_slab(_rows_array(ds, lo, hi), off[s_lo:s_hi + 1] - lo, num_frames)
+                if labeler.goal:
+                    rs, gs = _goal_float64(r, off[s_lo:s_hi + 1] - lo, num_frames)
+                parts_r.append(rs)
+                parts_g.append(gs)
+            empty = np.zeros((0, num_frames), np.float64 if labeler.goal else np.float32)
+            rs = np.concatenate(parts_r) if parts_r else empty
+            gs = np.concatenate(parts_g) if parts_g else empty
+            if distributed:
+                rows = [int(off[b] - off[a]) for a, b in shards]
+                backend = dist.get_backend()
+                dev = labeler.engine.device if backend == "nccl" else torch.device("cpu")
+                both = torch.from_numpy(np.stack([rs, gs], axis=1)).to(dev)  # [n, 2, F]: one collective
+                full = gather_rows(both, rows, dst=0)
+                if rank == 0:
+                    full = full.cpu().numpy()
+                    rs, gs = np.ascontiguousarray(full[:, 0]), np.ascontiguousarray(full[:, 1])
+            if rank == 0:
+                _write_labels(g, img_key, target_keys, (rs, gs), off, n_eps, len_data, num_frames)
+        labeler.close()
+    finally:
+        g.close()
+    if distributed:
+        dist.barrier()
+
+
+def _goal_float64(r: np.ndarray, ep_off: np.ndarray, num_frames: int):
+    """Goal-conditioned rewards are a float64 array in the reference (np.array of .item() values,
+    label_reward.py:160-162,193-195), so its discount_cumsum / stack_outputs run in float64 and the
+    datasets are float64. The per-frame distances come from the GPU in fp32 (exactly what .item()
+    widens); the O(T) float64 scan is done here, sequentially right-to-left like :252-253."""
+    r64 = r.astype(np.float64)
+    g64 = np.empty_like(r64)
+    for lo, hi in zip(ep_off[:-1], ep_off[1:]):
+        if hi > lo:
+            g64[lo:hi] = np.cumsum(r64[lo:hi][::-1])[::-1]
+    F = num_frames
+    idx = np.arange(len(r64))
+    start = np.repeat(ep_off[:-1], np.diff(ep_off))
+    win = np.maximum(start[:, None], idx[:, None] - (F - 1 - np.arange(F))[None, :])
+    return r64[win], g64[win]
+
+
+def _write_labels(g, img_key, target_keys, data, off, n_eps, len_data, num_frames):
+    """label_reward.py:260-289: create on the first episode (gzip, chunks (1,F), maxshape (len_data,F)) and
+    append per episode — equivalently one dataset holding rows [0, off[-1]); when the key already exists the
+    reference assigns in place by row index (:288-289)."""
+    labeled = int(off[n_eps]) if n_eps > 0 else 0
+    for _key, arr in zip(target_keys, data):
+        key = f"{img_key}_{_key}"
+        if n_eps == 0:
+            continue
+        existing = g.get(key)
+        if not existing:
+            g.create_dataset(key, compression="gzip", chunks=(1, num_frames), maxshape=(len_data, num_frames),
+                             data=arr[:labeled])
+        else:
+            existing[0:labeled] = arr[:labeled]
+
+
+def main():
+    parser = argparse.ArgumentParser(description="Process rollout training arguments.")
+    parser.add_argument("--env_name", type=str, default="coinrun")
+    parser.add_argument("--env_type", type=str, default="none")
+    parser.add_argument("--num_levels", type=int, default=500)
+    parser.add_argument("--start_level", type=int, default=0)
+    parser.add_argument("--distribution_mode", type=str, default="hard")
+    parser.add_argument("--image_keys", type=str, default="ob")
+    parser.add_argument("--data_path", type=str, default=None)
+    parser.add_argument("--base_path", type=str, default="./demonstrations")
+    parser.add_argument("--num_demonstrations", type=int, default=500)
+    parser.add_argument("--save_type", type=str, default="npy", choices=["npy", "hdf5"])  # parsed, unused (:306)
+    parser.add_argument("--num_frames", type=int, default=8)
+    parser.add_argument("--model_type", type=str, default="clip")
+    parser.add_argument("--model_ckpt_dir", type=str, default=None)
+    parser.add_argument("--use_crop", type=bool, default=False)  # any non-empty string is True, as in :311
+    parser.add_argument("--inst_type", type=str, default="none")
+    # extensions
+    parser.add_argument("--arch", type=str, default="ViT-B/16")
+    parser.add_argument("--reduce", type=str, default="first", choices=["first", "mean"])
+    parser.add_argument("--max_batch", type=int, default=512)
+    args = parser.parse_args()
+
+    env_name = f"{args.env_name}" if args.env_type == "none" else f"{args.env_name}_{args.env_type}"
+    if args.inst_type != "none":
+        text = get_clip_special_instruct(env_name, args.inst_type)
+    else:
+        text = get_clip_instruct(env_name)
+    print(f"[INFO] env_name: {env_name}\t instruction: {text}")
+
+    if "RANK" in os.environ and int(os.environ.get("WORLD_SIZE", "1")) > 1:
+        import torch.distributed as dist
+        torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", "0")))
+        dist.init_process_group("nccl")
+
+    label_reward(
+        env_name=args.env_name, env_type=args.env_type, distribution_mode=args.distribution_mode,
+        image_keys=args.image_keys, data_path=args.data_path, text=text, num_levels=args.num_levels,
+        start_level=args.start_level, num_demonstrations=args.num_demonstrations, num_frames=args.num_frames,
+        base_path=args.base_path, model_type=args.model_type, model_ckpt_dir=args.model_ckpt_dir,
+        use_crop=args.use_crop, inst_type=args.inst_type, arch=args.arch, reduce=args.reduce,
+        max_batch=args.max_batch,
+    )
+
+
+if __name__ == "__main__":
+    main()
