@@ -1,0 +1,370 @@
+"""Parity tests proper (-m gpu): the CUDA path, called through the C ABI, against the oracle on the same
+seeded inputs and against the golden fixtures the reference itself produced.
+
+Bars: bit-exact for integer / byte / index / scan-order work; for the bf16 tensor-core model path the
+tolerances are the ones named in tests/_util.py (and DESIGN.md §Parity)."""
+import numpy as np
+import pytest
+import torch
+
+from _util import (LOGIT_SCALE_RANDOM_INIT, TOL_COS_ABS, TOL_REWARD_REL_CORRELATED, TOL_REWARD_REL_TO_MAX, golden_names,
+                   load_golden, rebuild_inputs)
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def capi():
+    from arp_b200 import capi as m
+    from arp_b200.build import build
+    build()
+    return m
+
+
+@pytest.fixture(scope="module")
+def eng(capi):
+    e = capi.Engine(device=0, patch=16, in_h=64, in_w=64, max_batch=64)
+    yield e
+    e.close()
+
+
+def relerr(a, b):
+    a, b = a.float(), b.float()
+    return float((a - b).abs().max() / b.abs().max().clamp_min(1e-30))
+
+
+# ------------------------------------------------------------------------------------------------
+# kernels against plain PyTorch fp32 of the same op (floating-point kernels)
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("M,N,K,act,bias,resid,out_dtype", [
+    (128, 256, 64, 0, False, False, torch.float32),      # one tile, one k-block
+    (197, 768, 768, 0, True, False, torch.float32),      # ragged M tail (TMA zero fill + clipped store)
+    (1, 256, 64, 0, True, True, torch.float32),          # single row
+    (197 * 160, 768, 768, 0, True, True, torch.float32),  # out_proj shape: persistent loop, in-place style residual
+    (197 * 64, 2304, 768, 0, True, False, torch.bfloat16),   # QKV
+    (197 * 64, 3072, 768, 1, True, False, torch.bfloat16),   # c_fc + QuickGELU
+    (197 * 64, 768, 3072, 0, True, True, torch.float32),     # c_proj + residual
+    (100, 13312, 6656, 2, True, False, torch.bfloat16),      # adapter fc1 + ReLU
+    (100, 6144, 9216, 0, False, False, torch.float32),       # adapter intermediate linear
+])
+def test_gemm_vs_torch(eng, M, N, K, act, bias, resid, out_dtype):
+    dev = eng.device
+    g = torch.Generator(device=dev).manual_seed(M + N + K)
+    a = (torch.randn(M, K, device=dev, generator=g) * 0.5).bfloat16()
+    w = (torch.randn(N, K, device=dev, generator=g) * 0.05).bfloat16()
+    b = torch.randn(N, device=dev, generator=g) if bias else None
+    r = torch.randn(M, N, device=dev, generator=g) if resid else None
+    out = eng.gemm(a, w, bias=b, resid=r, act=act, out_dtype=out_dtype)
+    ref = a.float() @ w.float().t()
+    if bias:
+        ref = ref + b
+    if act == 1:
+        ref = ref * torch.sigmoid(1.702 * ref)
+    elif act == 2:
+        ref = torch.relu(ref)
+    if resid:
+        ref = ref + r
+    assert torch.isfinite(out.float()).all()
+    assert relerr(out, ref) < (1e-2 if out_dtype == torch.bfloat16 else 3e-5)   # bf16 output rounding / fp32 accumulate
+
+
+def test_gemm_residual_in_place(eng):
+    """The residual stream is updated in place (out aliases resid) on the hot path."""
+    dev = eng.device
+    a = torch.randn(300, 768, device=dev).bfloat16()
+    w = (torch.randn(768, 768, device=dev) * 0.05).bfloat16()
+    x = torch.randn(300, 768, device=dev)
+    ref = x + a.float() @ w.float().t()
+    import ctypes as C
+    eng._check(eng._lib.arp_gemm_bf16(eng._h, C.c_void_p(a.data_ptr()), C.c_void_p(w.data_ptr()),
+                                      C.c_void_p(x.data_ptr()), 0, 300, 768, 768, None, C.c_void_p(x.data_ptr()), 0,
+                                      C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+    assert relerr(x, ref) < 3e-5
+
+
+def test_layernorm_vs_torch(eng):
+    dev = eng.device
+    x = torch.randn(1003, 768, device=dev) * 3 + 1
+    g, b = torch.randn(768, device=dev), torch.randn(768, device=dev)
+    ref = torch.nn.functional.layer_norm(x, (768,), g, b, 1e-5)
+    assert relerr(eng.layernorm(x, g, b), ref) < 8e-3     # bf16 output rounding (2^-8 relative)
+
+
+@pytest.mark.parametrize("B,L", [(5, 197), (7, 50), (1, 197)])
+def test_attention_vs_torch(eng, B, L):
+    dev = eng.device
+    qkv = (torch.randn(B * L, 2304, device=dev) * 1.5).bfloat16()
+    out = eng.attention(qkv, B, L)
+    q, k, v = qkv.float().view(B, L, 3, 12, 64).permute(2, 0, 3, 1, 4)
+    ref = (torch.softmax(q @ k.transpose(-1, -2) * 0.125, -1) @ v).permute(0, 2, 1, 3).reshape(B * L, 768)
+    assert relerr(out, ref) < 2e-2                        # bf16 P and bf16 output
+
+
+# ------------------------------------------------------------------------------------------------
+# byte / index / order-exact kernels against the oracle: bit-exact
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("size,crop", [(64, False), (64, True), (256, False), (256, True), (128, False), (224, False)])
+def test_decode_bicubic_bit_exact(capi, size, crop):
+    from oracle import port
+    e = capi.Engine(device=0, patch=16, in_h=size, in_w=size, use_crop=crop, max_batch=8)
+    rng = np.random.default_rng(size + crop)
+    T, F = 5, 3
+    ob = rng.integers(0, 256, size=(T, F, size, size, 3), dtype=np.uint8)
+    yy, xx = np.mgrid[0:size, 0:size]
+    ob[0, -1] = np.stack([yy * 255 // size, xx * 255 // size, (yy + xx) * 255 // (2 * size)], -1).astype(np.uint8)
+    ob[1, -1] = np.where(rng.random((size, size, 3)) < 0.5, 0, 255).astype(np.uint8)
+    out = e.decode_only(torch.from_numpy(ob).cuda()).cpu().numpy()
+    tf = port.transform_pil(crop, size)
+    for t in range(T):
+        assert np.array_equal(out[t], tf(ob[t, -1]).numpy()), f"frame {t}"          # the reference's own PIL calls
+    assert np.array_equal(out[2], port.transform_restated(ob[2, -1], crop))          # and the integer restatement
+    e.close()
+
+
+@pytest.mark.parametrize("size,crop", [(64, False), (256, False), (64, True), (224, False)])
+def test_decode_bilinear_vs_oracle(capi, size, crop):
+    from oracle import port
+    e = capi.Engine(device=0, patch=16, in_h=size, in_w=size, use_crop=crop, preprocess=capi.PRE_BILINEAR,
+                    head=capi.HEAD_ADAPTER, max_batch=8)
+    ob = np.random.default_rng(size).integers(0, 256, size=(4, 2, size, size, 3), dtype=np.uint8)
+    out = e.decode_only(torch.from_numpy(ob).cuda()).cpu()
+    imgs = ob[:, -1]
+    if crop:
+        imgs = port.center_crop_np(imgs, (size // 2, size // 2))
+    ref = port.preprocess_bilinear(torch.from_numpy(np.ascontiguousarray(imgs)))
+    assert float((out - ref).abs().max()) < 1e-5          # north_star's fp32 tolerance (float op order only)
+    e.close()
+
+
+def _oracle_scan(r, off, F):
+    from oracle import cport
+    g = np.empty_like(r)
+    rs = np.empty((len(r), F), np.float32)
+    gs = np.empty((len(r), F), np.float32)
+    for lo, hi in zip(off[:-1], off[1:]):
+        if hi > lo:
+            g[lo:hi] = cport.discount_cumsum(r[lo:hi])
+            rs[lo:hi] = cport.stack_outputs(r[lo:hi], F)
+            gs[lo:hi] = cport.stack_outputs(g[lo:hi], F)
+    return g, rs, gs
+
+
+@pytest.mark.parametrize("F", [1, 4, 8])
+def test_scan_stack_bit_exact(eng, F):
+    from oracle import port
+    rng = np.random.default_rng(F)
+    lens = rng.integers(1, 300, size=60).tolist() + [999, 1, 2048, 2049, 5000]       # chunk-boundary and max sizes
+    off = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
+    r = (rng.standard_normal(off[-1]) * 0.3).astype(np.float32)
+    g, rs, gs = (t.cpu().numpy() for t in eng.scan_only(torch.from_numpy(r), torch.from_numpy(off), F))
+    ref_g, ref_rs, ref_gs = _oracle_scan(r, off, F)
+    assert np.array_equal(g, ref_g) and np.array_equal(rs, ref_rs) and np.array_equal(gs, ref_gs)
+    # python-loop restatement on one episode too
+    assert np.array_equal(g[off[3]:off[4]], port.discount_cumsum(r[off[3]:off[4]]))
+
+
+def test_scan_full_size_10k_episodes(eng):
+    """BASELINE configs[4] size: 10k episodes, ~1.4M frames — against the C oracle, bit-exact."""
+    rng = np.random.default_rng(7)
+    lens = rng.integers(32, 256, size=10_000)
+    off = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
+    r = (rng.standard_normal(off[-1]) * 0.1).astype(np.float32)
+    g, rs, gs = (t.cpu().numpy() for t in eng.scan_only(torch.from_numpy(r), torch.from_numpy(off), 8))
+    ref_g, ref_rs, ref_gs = _oracle_scan(r, off, 8)
+    assert np.array_equal(g, ref_g) and np.array_equal(rs, ref_rs) and np.array_equal(gs, ref_gs)
+
+
+def test_scan_ignores_rows_after_last_done(eng):
+    r = torch.arange(10, dtype=torch.float32)
+    off = torch.tensor([0, 4, 7])                                    # rows 7..9 belong to no episode
+    g, rs, gs = eng.scan_only(r, off, 2)
+    assert g[:7].tolist() == [6, 6, 5, 3, 15, 11, 6]
+    # offsets beyond T are clamped like min(idx[i+1], len_data) (label_reward.py:267)
+    g2, _, _ = eng.scan_only(r[:6], torch.tensor([0, 4, 7]), 2)
+    assert g2.tolist() == [6, 6, 5, 3, 9, 5]
+
+
+# ------------------------------------------------------------------------------------------------
+# the whole drop-in against what the reference produced
+# ------------------------------------------------------------------------------------------------
+def _run_product(tmp_path, meta, data, clip_sd, adapter_sd, **kw):
+    from arp_b200.label_reward import label_reward
+    from arp_b200.store import NpyStore
+    from arp_b200.synth import write_dataset
+    path = tmp_path / "ds"
+    s = NpyStore(path, "w")
+    write_dataset(s, data)
+    s.close()
+    ckpt = None
+    if adapter_sd is not None:
+        ckpt = tmp_path / "best_checkpoint.pt"
+        torch.save(adapter_sd, ckpt)
+    label_reward("coinrun", "hard", 500, 0, meta["text"], str(tmp_path), data_path=str(path),
+                 model_type=meta["model_type"], model_ckpt_dir=str(ckpt) if ckpt else None,
+                 use_crop=meta.get("use_crop", False), inst_type=meta.get("inst_type", "none"),
+                 clip_state_dict=clip_sd, arch=meta["arch"], max_batch=kw.get("max_batch", 64), env_type="none")
+    s = NpyStore(path, "r")
+    out = {k: np.array(s[k][:]) for k in s.keys() if k.startswith("ob_")}
+    s.close()
+    return out
+
+
+@pytest.mark.parametrize("name", golden_names())
+def test_label_reward_matches_reference_golden(tmp_path, name):
+    from oracle import port
+    meta, gold = load_golden(name)
+    data, clip_sd, adapter_sd = rebuild_inputs(meta)
+    out = _run_product(tmp_path, meta, data, clip_sd, adapter_sd)
+    assert sorted(out) == sorted(gold), "dataset keys must be the reference's"
+    F = data["done"].shape[1]
+    idx = port.episode_index(data["done"][:, -1])
+    goal = "goal_conditioned" in meta["model_type"]
+    for key, ref in gold.items():
+        got = out[key]
+        assert got.shape == ref.shape and got.dtype == ref.dtype, key
+    rk = [k for k in gold if "_pos_rtg" not in k][0]
+    gk = [k for k in gold if "_pos_rtg" in k][0]
+    r, r_ref = out[rk][:, -1], gold[rk][:, -1]
+    if goal:
+        # feature distances: ||f_t - f_T||, relative to the largest distance
+        assert np.abs(r - r_ref).max() <= 2e-2 * np.abs(r_ref).max()
+    else:
+        dcos = np.abs(r - r_ref).max() / LOGIT_SCALE_RANDOM_INIT
+        assert dcos <= TOL_COS_ABS, f"|dcos| {dcos:.2e}"
+        assert np.abs(r - r_ref).max() <= TOL_REWARD_REL_TO_MAX * np.abs(r_ref).max()
+    # return-to-go: episode boundaries and add order are exact — re-running the oracle's scan on OUR rewards
+    # must give OUR rtg bit for bit, and the windows are pure gathers
+    for lo, hi in zip(idx[:-1], idx[1:]):
+        g_or = port.discount_cumsum(r[lo:hi])
+        assert np.array_equal(out[gk][lo:hi], port.stack_outputs(g_or, F)), "rtg scan/stack not bit-exact"
+        assert np.array_equal(out[rk][lo:hi], port.stack_outputs(r[lo:hi], F)), "reward stack not bit-exact"
+    assert np.abs(out[gk] - gold[gk]).max() <= (2e-2 if goal else TOL_REWARD_REL_TO_MAX) * max(np.abs(gold[gk]).max(), 1e-6) * 4
+
+
+def test_rerun_overwrites_in_place_and_is_idempotent(tmp_path):
+    """label_reward.py:288-289: when the keys already exist the datasets are assigned in place."""
+    meta, gold = load_golden("g3_clip_b32_crop")
+    data, clip_sd, _ = rebuild_inputs(meta)
+    a = _run_product(tmp_path, meta, data, clip_sd, None)
+    from arp_b200.label_reward import label_reward
+    label_reward("coinrun", "hard", 500, 0, meta["text"], str(tmp_path), data_path=str(tmp_path / "ds"),
+                 model_type="clip", use_crop=True, clip_state_dict=clip_sd, arch=meta["arch"], max_batch=16,
+                 env_type="none")
+    from arp_b200.store import NpyStore
+    s = NpyStore(tmp_path / "ds", "r")
+    for k, v in a.items():
+        assert np.array_equal(np.array(s[k][:]), v)       # same bits whatever the chunking (rows are independent)
+    s.close()
+
+
+def test_multi_instruction_first_vs_mean(capi):
+    """BASELINE configs[3]: n_text cosines per frame; `first` is the reference (Q1), `mean` is envs/vl_reward.py."""
+    from oracle import port
+    from arp_b200.text_tower import clip_text_embedding
+    from arp_b200.tokenizer import tokenize
+    model = port.clip_shim.build("ViT-B/32", 0)
+    sd = model.state_dict()
+    texts = ["The agent must navigate a maze to find the line.", "The agent navigate to the yellow object.",
+             "navigate a maze to collect the red line."]
+    ob = np.random.default_rng(0).integers(0, 256, size=(9, 1, 64, 64, 3), dtype=np.uint8)
+    ref_first = port.compute_reward_clip(model, ob[:, -1], texts, reduce="first")
+    ref_mean = port.compute_reward_clip(model, ob[:, -1], texts, reduce="mean")
+    for reduce, ref in ((capi.REDUCE_FIRST, ref_first), (capi.REDUCE_MEAN, ref_mean)):
+        e = capi.Engine(device=0, patch=32, in_h=64, in_w=64, max_batch=4, reduce=reduce)
+        e.load_state_dict(sd)
+        emb, scale = clip_text_embedding(sd, tokenize(texts), e.device)
+        e.set_text(emb, scale)
+        r, lg = e.compute_reward(torch.from_numpy(ob).cuda(), want_logits=True)
+        r, lg = r.cpu().numpy(), lg.cpu().numpy()
+        assert lg.shape == (9, 3)
+        assert np.abs(r - ref).max() / scale <= TOL_COS_ABS
+        if reduce == capi.REDUCE_FIRST:
+            assert np.array_equal(r, lg[:, 0])
+        else:
+            assert np.allclose(r, lg.mean(1), rtol=1e-6, atol=1e-7)
+        e.close()
+    # the product's cached text embedding equals the oracle's text tower
+    with torch.no_grad():
+        t = model.encode_text(port.clip_shim.tokenize(texts))
+        t = t / t.norm(dim=1, keepdim=True)
+    assert float((emb.cpu() - t).abs().max()) < 1e-5
+
+
+def test_correlated_text_reward_relative_tolerance(capi):
+    """north_star: rewards within 1e-3 relative in bf16. Well-conditioned variant: the text
+    embedding is the unit mean image feature plus noise, so cos is O(0.3-0.9) as with pretrained weights."""
+    from oracle import port
+    model = port.clip_shim.build("ViT-B/16", 0)
+    sd = model.state_dict()
+    rng = np.random.default_rng(5)
+    from arp_b200.synth import structured_frames
+    ob = structured_frames(24, 64, rng)[:, None]
+    tf = port.transform_pil(False)
+    with torch.no_grad():
+        f = model.encode_image(torch.stack([tf(im) for im in ob[:, 0]]))
+    fn = f / f.norm(dim=1, keepdim=True)
+    g = torch.Generator().manual_seed(0)
+    t = fn.mean(0, keepdim=True) + 0.05 * torch.randn(1, 512, generator=g)
+    t = t / t.norm(dim=1, keepdim=True)
+    scale = 100.0                                        # pretrained CLIP's exp(logit_scale)
+    ref = (scale * fn @ t.t())[:, 0].numpy()
+    e = capi.Engine(device=0, patch=16, in_h=64, in_w=64, max_batch=16)
+    e.load_state_dict(sd)
+    e.set_text(t, scale)
+    r = e.compute_reward(torch.from_numpy(ob).cuda()).cpu().numpy()
+    e.close()
+    rel = np.abs(r - ref) / np.abs(ref)
+    assert np.abs(ref).min() > 10.0                      # cos > 0.1: the case is well conditioned
+    assert rel.max() <= TOL_REWARD_REL_CORRELATED, f"max relative reward error {rel.max():.2e}"
+
+
+def test_device_and_host_entry_points_agree(capi):
+    """arp_label (device buffers) and arp_label_host (host buffers, chunked H2D) are the same computation."""
+    from arp_b200.weights import random_clip_state_dict
+    e = capi.Engine(device=0, patch=16, in_h=64, in_w=64, max_batch=32)
+    e.load_state_dict(random_clip_state_dict("ViT-B/16", 0, "cuda"))
+    e.set_text(torch.nn.functional.normalize(torch.randn(2, 512), dim=1), 14.3)
+    rng = np.random.default_rng(0)
+    lens = rng.integers(1, 40, size=9)
+    off = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
+    ob = rng.integers(0, 256, size=(int(off[-1]) + 3, 4, 64, 64, 3), dtype=np.uint8)   # 3 unlabeled tail rows
+    h = e.label_host(ob, off, 4)
+    d = [t.cpu().numpy() for t in e.label(torch.from_numpy(ob).cuda(), torch.from_numpy(off), 4)]
+    n = int(off[-1])
+    for a, b in zip(h, d):
+        assert np.array_equal(a[:n], b[:n])
+    assert e.launch_count > 0
+    e.close()
+
+
+def test_encode_image_vs_oracle(capi):
+    from oracle import port
+    model = port.clip_shim.build("ViT-B/16", 0)
+    e = capi.Engine(device=0, patch=16, in_h=256, in_w=256, max_batch=8)
+    e.load_state_dict(model.state_dict())
+    ob = np.random.default_rng(2).integers(0, 256, size=(10, 1, 256, 256, 3), dtype=np.uint8)
+    tf = port.transform_pil(False)
+    with torch.no_grad():
+        ref = model.encode_image(torch.stack([tf(im) for im in ob[:, 0]]))
+    f = e.encode_image(torch.from_numpy(ob).cuda()).cpu()
+    cos = torch.nn.functional.cosine_similarity(f, ref, dim=1)
+    assert float(cos.min()) > 0.9999 and relerr(f, ref) < 1e-2
+    e.close()
+
+
+def test_errors_are_reported_not_thrown(capi):
+    e = capi.Engine(device=0, patch=16, in_h=64, in_w=64, max_batch=8)
+    ob = torch.zeros(2, 1, 64, 64, 3, dtype=torch.uint8, device="cuda")
+    with pytest.raises(capi.ArpError) as ei:
+        e.compute_reward(ob)                              # weights not set
+    assert ei.value.code == capi.ARP_ERR_STATE
+    with pytest.raises(capi.ArpError) as ei:
+        e.set_weight("visual.proj", torch.zeros(3, 3))
+    assert ei.value.code == capi.ARP_ERR_INVALID
+    with pytest.raises(capi.ArpError) as ei:
+        e.set_weight("no.such.key", torch.zeros(3))
+    assert ei.value.code == capi.ARP_ERR_UNKNOWN_KEY
+    assert e.set_weight("transformer.resblocks.0.ln_1.weight", torch.zeros(512)) is True   # text tower: accepted, ignored
+    e.close()
+    with pytest.raises(capi.ArpError):
+        capi.Engine(device=0, patch=14)
