@@ -29,7 +29,13 @@ EXPORTS = (
     "arp_create", "arp_destroy", "arp_last_error", "arp_abi_version", "arp_set_weight", "arp_missing_weights",
     "arp_set_text", "arp_label", "arp_label_host", "arp_compute_reward", "arp_encode_image", "arp_decode_only",
     "arp_scan_only", "arp_gemm_bf16", "arp_layernorm_bf16", "arp_attention", "arp_launch_count",
+    "arp_profile_begin", "arp_profile_end",
 )
+PROFILE_CLASSES = ("gemm", "attention", "layernorm", "decode", "head", "scan", "other")
+
+
+class ArpProfileStats(C.Structure):
+    _fields_ = [("launches", C.c_int64), ("total_ms", C.c_double), ("flops", C.c_double), ("bytes", C.c_double)]
 
 
 class ArpConfig(C.Structure):
@@ -82,6 +88,8 @@ def load_library() -> C.CDLL:
     lib.arp_attention.argtypes = [vp, vp, vp, i32, i32, vp]
     lib.arp_launch_count.argtypes = [vp]
     lib.arp_launch_count.restype = i64
+    lib.arp_profile_begin.argtypes = [vp]
+    lib.arp_profile_end.argtypes = [vp, C.POINTER(ArpProfileStats), i32]
     for name in EXPORTS:
         if name not in ("arp_destroy", "arp_last_error", "arp_launch_count"):
             getattr(lib, name).restype = C.c_int
@@ -139,6 +147,16 @@ class Engine:
     @property
     def launch_count(self) -> int:
         return int(self._lib.arp_launch_count(self._h))
+
+    def profile_begin(self):
+        self._check(self._lib.arp_profile_begin(self._h))
+
+    def profile_end(self) -> dict:
+        """{class: {launches, total_ms, flops, bytes}} of the launches since profile_begin (device-synchronising)."""
+        arr = (ArpProfileStats * len(PROFILE_CLASSES))()
+        self._check(self._lib.arp_profile_end(self._h, arr, len(PROFILE_CLASSES)))
+        return {n: {"launches": int(a.launches), "total_ms": a.total_ms, "flops": a.flops, "bytes": a.bytes}
+                for n, a in zip(PROFILE_CLASSES, arr)}
 
     # -- weights / text ---------------------------------------------------------------------------
     def set_weight(self, name: str, tensor: torch.Tensor, strict: bool = True) -> bool:

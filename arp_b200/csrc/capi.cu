@@ -137,6 +137,34 @@ struct ArpHandle {
 
   std::map<TmapKey, CUtensorMap> tmaps;
   std::vector<void*> allocs;
+
+  // optional per-kernel-class timing (arp_profile_begin/end): CUDA events bracket every launch on its stream
+  bool profiling = false;
+  struct ProfRec { int cls; double flops; double bytes; cudaEvent_t e0, e1; };
+  std::vector<ProfRec> prof;
+  std::vector<cudaEvent_t> event_pool;
+};
+
+enum ProfClass { PC_GEMM = 0, PC_ATTENTION = 1, PC_LAYERNORM = 2, PC_DECODE = 3, PC_HEAD = 4, PC_SCAN = 5, PC_OTHER = 6, PC_COUNT = 7 };
+
+static cudaEvent_t prof_event(ArpHandle* h) {
+  if (!h->event_pool.empty()) { cudaEvent_t e = h->event_pool.back(); h->event_pool.pop_back(); return e; }
+  cudaEvent_t e = nullptr;
+  cudaEventCreate(&e);
+  return e;
+}
+
+// RAII bracket: records an event before and after the launches issued inside its scope
+struct ProfScope {
+  ArpHandle* h; cudaStream_t st; size_t idx; bool on;
+  ProfScope(ArpHandle* h_, int cls, double flops, double bytes, cudaStream_t st_) : h(h_), st(st_), idx(0), on(h_->profiling) {
+    if (!on) return;
+    ArpHandle::ProfRec r{cls, flops, bytes, prof_event(h), prof_event(h)};
+    cudaEventRecord(r.e0, st);
+    idx = h->prof.size();
+    h->prof.push_back(r);
+  }
+  ~ProfScope() { if (on) cudaEventRecord(h->prof[idx].e1, st); }
 };
 
 static int fail(ArpHandle* h, int code, const char* fmt, ...) {
@@ -346,6 +374,36 @@ extern "C" const char* arp_last_error(const ArpHandle* h) { return h ? h->err.c_
 
 extern "C" int64_t arp_launch_count(const ArpHandle* h) { return h ? h->launches : 0; }
 
+extern "C" int arp_profile_begin(ArpHandle* h) {
+  if (!h) return ARP_ERR_INVALID;
+  for (auto& r : h->prof) { h->event_pool.push_back(r.e0); h->event_pool.push_back(r.e1); }
+  h->prof.clear();
+  h->profiling = true;
+  return ARP_OK;
+}
+
+extern "C" int arp_profile_end(ArpHandle* h, ArpProfileStats* out, int32_t n_classes) {
+  if (!h || !out || n_classes < 1) return fail(h, ARP_ERR_INVALID, "null argument");
+  h->profiling = false;
+  ARP_CUDA(h, cudaSetDevice(h->cfg.device));
+  ARP_CUDA(h, cudaDeviceSynchronize());
+  for (int i = 0; i < n_classes; ++i) out[i] = ArpProfileStats{0, 0.0, 0.0, 0.0};
+  for (auto& r : h->prof) {
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, r.e0, r.e1);
+    if (r.cls < n_classes) {
+      out[r.cls].launches += 1;
+      out[r.cls].total_ms += ms;
+      out[r.cls].flops += r.flops;
+      out[r.cls].bytes += r.bytes;
+    }
+    h->event_pool.push_back(r.e0);
+    h->event_pool.push_back(r.e1);
+  }
+  h->prof.clear();
+  return ARP_OK;
+}
+
 template <typename K>
 static int set_smem(ArpHandle* h, K kernel, int bytes) {
   ARP_CUDA(h, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
@@ -363,6 +421,8 @@ extern "C" void arp_destroy(ArpHandle* h) {
     if (h->ev_copied[i]) cudaEventDestroy(h->ev_copied[i]);
     if (h->ev_consumed[i]) cudaEventDestroy(h->ev_consumed[i]);
   }
+  for (auto& r : h->prof) { cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); }
+  for (cudaEvent_t e : h->event_pool) cudaEventDestroy(e);
   if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
   if (h->own_stream) cudaStreamDestroy(h->own_stream);
   delete h;
@@ -599,6 +659,8 @@ static int launch_gemm(ArpHandle* h, const bf16* a, int64_t a_rows_alloc, const 
   g.rowtab = rowtab; g.period = period > 0 ? period : 1;
   const int tiles = (int)((M + GEMM_BM - 1) / GEMM_BM) * (N / GEMM_BN);
   const int grid = std::min(tiles, kNumSMs);
+  ProfScope prof(h, PC_GEMM, 2.0 * (double)M * N * K,
+                 (double)M * K * 2 + (double)N * K * 2 + (double)M * N * (out_f32 ? 4 : 2) + (resid ? (double)M * N * 4 : 0), st);
 #define GEMM_CASE(T, A) gemm_bf16_tcgen05_kernel<T, A><<<grid, GEMM_THREADS, GEMM_SMEM_BYTES, st>>>(*ta, *tb, g)
   if (out_f32) {
     if (act == ACT_NONE) GEMM_CASE(float, ACT_NONE);
@@ -630,6 +692,9 @@ static int launch_decode(ArpHandle* h, const uint8_t* ob, int64_t n, int64_t str
   a.out = out; a.patch = h->cfg.patch; a.grid = h->grid; a.tokens = h->tokens; a.max_rows = h->max_rows;
   const int smem = dec_smem_bytes(h->src_w, h->max_rows, h->h_ksize, h->v_ksize, out_kind);
   if (smem > 160 * 1024) return fail(h, ARP_ERR_INVALID, "frame too large for the decode kernel (%d B smem)", smem);
+  ProfScope prof(h, PC_DECODE, 0.0,
+                 (double)n * ((double)h->src_h * h->src_w * 3 +
+                              (out_kind == DEC_OUT_PATCH_BF16 ? (double)h->tokens * h->kp * 2 : 3.0 * DEC_OUT * DEC_OUT * 4)), st);
   // grid.y is limited to 65535 frames per launch
   for (int64_t f0 = 0; f0 < n; f0 += 32768) {
     const int cnt = (int)std::min<int64_t>(32768, n - f0);
@@ -648,6 +713,7 @@ static int launch_decode(ArpHandle* h, const uint8_t* ob, int64_t n, int64_t str
 static int launch_ln_bf16(ArpHandle* h, const float* x, const float* g, const float* b, bf16* y, int64_t M,
                           cudaStream_t st) {
   if (M <= 0) return ARP_OK;
+  ProfScope prof(h, PC_LAYERNORM, 0.0, (double)M * 768 * 6, st);
   layernorm_f32_bf16_kernel<768><<<(unsigned)((M + 7) / 8), 256, 0, st>>>(x, g, b, y, (int)M, 1e-5f);
   h->launches++;
   ARP_CUDA(h, cudaGetLastError());
@@ -657,6 +723,8 @@ static int launch_ln_bf16(ArpHandle* h, const float* x, const float* g, const fl
 static int launch_attention(ArpHandle* h, const bf16* qkv, bf16* out, int B, int tokens, cudaStream_t st) {
   if (B <= 0) return ARP_OK;
   const float scale_log2e = 0.125f * 1.4426950408889634f;
+  ProfScope prof(h, PC_ATTENTION, 4.0 * (double)B * h->cfg.heads * tokens * tokens * ATT_DH,
+                 (double)B * tokens * h->cfg.width * 2 * 4, st);
   for (int b0 = 0; b0 < B; b0 += 32768) {
     const int cnt = std::min(32768, B - b0);
     const bf16* q = qkv + (size_t)b0 * tokens * 3 * h->cfg.width;
@@ -686,8 +754,11 @@ static int encode_chunk(ArpHandle* h, const uint8_t* ob, int64_t n, int64_t stri
   // patch embed (+ positional embedding, + class embedding on the all-zero row 0 of each frame)
   ARP_TRY(launch_gemm(h, patches, Mcap, h->conv1, h->x, true, ACT_NONE, M, W, h->kp, W, nullptr, nullptr, 0,
                       h->rowtab, h->tokens, st));
-  layernorm_f32_inplace_kernel<768><<<(unsigned)((M + 7) / 8), 256, 0, st>>>(h->x, h->ln_pre_g, h->ln_pre_b, (int)M, 1e-5f);
-  h->launches++;
+  {
+    ProfScope prof(h, PC_LAYERNORM, 0.0, (double)M * 768 * 8, st);
+    layernorm_f32_inplace_kernel<768><<<(unsigned)((M + 7) / 8), 256, 0, st>>>(h->x, h->ln_pre_g, h->ln_pre_b, (int)M, 1e-5f);
+    h->launches++;
+  }
   for (int l = 0; l < c.layers; ++l) {
     const LayerW& L = h->layers[l];
     ARP_TRY(launch_ln_bf16(h, h->x, L.ln1_g, L.ln1_b, h->xn, M, st));
@@ -717,6 +788,7 @@ static int head_chunk(ArpHandle* h, int64_t n, float* reward_out, float* logits_
   const bool need_text = reward_out || logits_out;
   if (need_text && !h->goal && !h->text) return fail(h, ARP_ERR_STATE, "arp_set_text has not been called");
   if (!h->adapter) {
+    ProfScope prof(h, PC_HEAD, 2.0 * (double)n * 768 * 512, (double)n * 768 * 4 + 768.0 * 512 * 4, st);
     clip_head_kernel<768, 512><<<(unsigned)n, 256, 0, st>>>(
         h->x, h->tokens, h->ln_post_g, h->ln_post_b, 1e-5f, h->proj, (need_text && !h->goal) ? h->text : nullptr,
         h->n_text, h->logit_scale, c.reduce, feat_out, c.embed_dim, 0, logits_out, h->goal ? nullptr : reward_out);
@@ -851,6 +923,7 @@ static int scan_launch(ArpHandle* h, const float* reward, int64_t T, const int64
   if (n_eps <= 0 || T <= 0) return ARP_OK;
   if (F < 1 || F > 64) return fail(h, ARP_ERR_INVALID, "num_frames must be in [1,64]");
   if (gs && !rtg) return fail(h, ARP_ERR_INVALID, "rtg_stacked needs an rtg buffer");
+  ProfScope prof(h, PC_SCAN, 0.0, (double)T * (4 + 4 + 2.0 * F * 4), st);
   rtg_scan_stack_kernel<<<n_eps, SCAN_THREADS, 0, st>>>(reward, reinterpret_cast<const long long*>(ep_off), T, F,
                                                        gamma, rtg, rs, gs);
   h->launches++;

@@ -1,0 +1,341 @@
+"""Headline benchmark: reward-labeled frames/s of the ARP labeler hot path on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W]            # this repo's CUDA path
+    python bench.py --impl reference [...]                         # the reference algorithm on host cores
+
+Workload (BASELINE.json configs[1]): CLIP ViT-B/16, model_type="clip", 500 synthetic CoinRun-shaped
+episodes (lengths rng(1).integers(32,256), ~72k frames) of 256x256 uint8 frames, random-init weights.
+A "step" is one pass of the hot path over the whole dataset shard:
+    decode -> ViT-B/16 -> cosine reward -> per-episode return-to-go scan + window stack.
+`value`  : frames/s with the frames already resident in HBM (arp_label on device buffers);
+`e2e`    : frames/s through the host-buffer C-ABI call (arp_label_host): pinned host frames are copied
+           H2D inside the timed region and the four result arrays are copied back;
+`roofline`: the tcgen05 GEMM kernel (all launches of one step), algorithmic FLOPs / CUDA-event time;
+`cpu_baseline`: the oracle port (CPU restatement of the reference) on a bounded sample, rank 0, N=1.
+With N>1 (torchrun) every rank labels its own 500-episode shard (weak scaling) and the per-frame
+reward / return-to-go arrays are gathered to rank 0 with one NCCL collective inside the timed region.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+import torch
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+GFLOP_PER_FRAME_B16 = 35.127
+TEXT = "the goal is to collect the coin."
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--episodes", type=int, default=500)
+    ap.add_argument("--size", type=int, default=256)
+    ap.add_argument("--num-frames", type=int, default=8)
+    ap.add_argument("--max-batch", type=int, default=512)
+    ap.add_argument("--cpu-sample-frames", type=int, default=96)
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def measured_peaks():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        d = json.loads(p.read_text())
+        return {"hbm_gbs": d["hbm_gbs"], "bf16_tflops": d["bf16_tflops"],
+                "bf16_tflops_sustained": d.get("bf16_tflops_sustained", d["bf16_tflops"]), "source": "measured"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "200", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        sm, mx, reasons, pw = [], [], set(), []
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2])); pw.append(float(r[3]))
+            except (ValueError, IndexError):
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        busy = [s for s, p in zip(sm, pw) if p > 300] or sm
+        return {"sm_mhz": float(np.median(busy)) if busy else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def episode_offsets(n_episodes: int, seed: int) -> np.ndarray:
+    lens = np.random.default_rng(seed).integers(32, 256, size=n_episodes)
+    return np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
+
+
+# ---------------------------------------------------------------------------------------------------
+# reference arm: the reference algorithm (oracle port) on the host cores
+# ---------------------------------------------------------------------------------------------------
+def cpu_reference_rate(args, n_frames: int, threads: int | None = None):
+    """Times oracle.port.label_reward_port (torch CPU fp32 + PIL + numpy loops, i.e. the reference's own
+    algorithm) on the first episodes of the same synthetic dataset, >= n_frames frames. Returns
+    (frames/s, frames, cores, rewards, frames_u8, offsets)."""
+    from oracle import port
+    from arp_b200.weights import random_clip_state_dict
+    threads = threads or os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    off = episode_offsets(args.episodes, seed=1)
+    n_eps = int(np.searchsorted(off, n_frames, side="left"))
+    n_eps = max(1, min(n_eps, args.episodes))
+    T = int(off[n_eps])
+    rng = np.random.default_rng(1234)
+    frames = rng.integers(0, 256, size=(T, 1, args.size, args.size, 3), dtype=np.uint8)
+    done = np.zeros((T, args.num_frames), np.float32)
+    done[off[1:n_eps + 1] - 1, -1] = 1.0
+    model = port.clip_shim.build("ViT-B/16", seed=0)
+    sd = random_clip_state_dict("ViT-B/16", seed=0, device="cpu")
+    model.load_state_dict(sd, strict=True)
+    model = model.float().eval()
+    data = {"ob": frames, "done": done}
+    t0 = time.perf_counter()
+    out = port.label_reward_port(data, model=model, model_type="clip", text=TEXT)
+    secs = time.perf_counter() - t0
+    return T / secs, T, threads, out, frames, off[:n_eps + 1], sd
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    rates = []
+    frames = 0
+    for i in range(args.warmup + args.steps):
+        rate, frames, cores, *_ = cpu_reference_rate(args, max(16, args.cpu_sample_frames // 2))
+        if i >= args.warmup:
+            rates.append(rate)
+    v = float(np.mean(rates))
+    sample = f"first episodes of the synthetic dataset, {frames} frames/step, oracle port on {cores} threads"
+    print(json.dumps({
+        "impl": "reference", "metric": "reward-labeled frames/sec", "value": v, "unit": "frames/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * frames / v,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args, frames),
+        "cpu_baseline": {"value": v, "unit": "frames/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": v, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }))
+
+
+def workload_config(args, frames_per_rank: int) -> dict:
+    return {"workload": f"CLIP ViT-B/16 model_type=clip labeling of {args.episodes} synthetic CoinRun-shaped episodes "
+                        f"at {args.size}x{args.size} (BASELINE configs[1]), random-init weights",
+            "episodes_per_gpu": args.episodes, "frames_per_gpu": frames_per_rank, "frame": [args.size, args.size, 3],
+            "num_frames": args.num_frames, "max_batch": args.max_batch, "parallelism": f"episode-sharded x{args.gpus}",
+            "cache": "inputs (14 GB/GPU at the default size) far exceed the 126 MB L2; no flush needed"}
+
+
+# ---------------------------------------------------------------------------------------------------
+# our arm
+# ---------------------------------------------------------------------------------------------------
+def main():
+    args = parse()
+    if args.impl == "reference":
+        return run_reference_arm(args)
+
+    import torch.distributed as dist
+    from arp_b200 import capi
+    from arp_b200.build import build
+    from arp_b200.sharding import gather_rows
+    from arp_b200.text_tower import clip_text_embedding
+    from arp_b200.tokenizer import tokenize
+    from arp_b200.weights import random_clip_state_dict
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        sys.exit("bench.py needs a B200: arp_b200 has no CPU path (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    build()
+
+    F = args.num_frames
+    off_np = episode_offsets(args.episodes, seed=1 + rank)
+    T = int(off_np[-1])
+    eng = capi.Engine(device=local, patch=16, in_h=args.size, in_w=args.size, max_batch=args.max_batch)
+    sd = random_clip_state_dict("ViT-B/16", seed=0, device="cpu")   # CPU generator: same weights as the CPU arm
+    eng.load_state_dict(sd)
+    emb, scale = clip_text_embedding(sd, tokenize([TEXT]), dev)
+    eng.set_text(emb, scale)
+
+    # synthetic frames, generated on the device (de-stacked layout [T,1,H,W,3]: only the scored frame exists)
+    gen = torch.Generator(device=dev).manual_seed(1234 + rank)
+    ob = torch.empty(T, 1, args.size, args.size, 3, dtype=torch.uint8, device=dev)
+    for t0 in range(0, T, 4096):
+        ob[t0:t0 + 4096] = torch.randint(0, 256, ob[t0:t0 + 4096].shape, dtype=torch.uint8, device=dev, generator=gen)
+    off = torch.from_numpy(off_np).to(dev)
+    rows = [int(episode_offsets(args.episodes, seed=1 + r)[-1]) for r in range(world)]
+
+    def step_device():
+        r, g, rs, gs = eng.label(ob, off, F)
+        if world > 1:
+            gather_rows(torch.stack([r, g], dim=1), rows, dst=0)      # the path's only collective
+        return r
+
+    def timed(fn, k):
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(k):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms)
+
+    for _ in range(args.warmup):
+        step_device()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    l0 = eng.launch_count
+    total_ms = timed(step_device, args.steps)
+    launches = eng.launch_count - l0
+    clocks = sampler.stop() if rank == 0 else None
+    ms_per_step = total_ms / args.steps
+    total_frames = sum(rows)
+    value = total_frames / (ms_per_step * 1e-3)
+
+    # ---- roofline of the dominant kernel: one more step with per-launch CUDA events ----
+    eng.profile_begin()
+    step_device()
+    prof = eng.profile_end()
+    peaks = measured_peaks()
+    gemm = prof["gemm"]
+    achieved = gemm["flops"] / (gemm["total_ms"] * 1e-3) / 1e12
+    traffic = None
+    tpath = ROOT / "profiles" / "roofline_traffic.json"
+    if tpath.exists():
+        traffic = json.loads(tpath.read_text())
+    step_kernel_ms = sum(v["total_ms"] for v in prof.values())
+    roofline = {
+        "bound": "tensor", "kernel": "gemm_bf16_tcgen05_kernel (all linear layers of one step)",
+        "achieved": achieved, "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
+        "frac": achieved / peaks["bf16_tflops_sustained"], "peak_source": f"{peaks['source']} (sustained cuBLAS bf16)",
+        "launches_per_step": gemm["launches"], "flops_per_launch_avg": gemm["flops"] / max(gemm["launches"], 1),
+        "avg_launch_ms": gemm["total_ms"] / max(gemm["launches"], 1),
+        "traffic": None if traffic is None else traffic.get("gemm_dram_bytes_per_launch"),
+        "share_of_step": gemm["total_ms"] / step_kernel_ms,
+        "by_class_ms": {k: round(v["total_ms"], 3) for k, v in prof.items() if v["launches"]},
+        "hbm_bound_classes": {k: {"achieved_gbs": v["bytes"] / (v["total_ms"] * 1e-3) / 1e9,
+                                  "frac_of_hbm_peak": v["bytes"] / (v["total_ms"] * 1e-3) / 1e9 / peaks["hbm_gbs"]}
+                              for k, v in prof.items() if k in ("layernorm", "decode", "scan") and v["launches"]},
+        "whole_step_tflops": total_frames / world * GFLOP_PER_FRAME_B16 / (ms_per_step * 1e-3) / 1e3,
+    }
+
+    # ---- end to end through the host-buffer entry point ----
+    e2e = None
+    if not args.no_e2e:
+        try:
+            ob_host = torch.empty(ob.shape, dtype=torch.uint8, pin_memory=True)
+        except RuntimeError:
+            ob_host = torch.empty(ob.shape, dtype=torch.uint8)
+        ob_host.copy_(ob)
+        outs = (np.empty(T, np.float32), np.empty(T, np.float32), np.empty((T, F), np.float32),
+                np.empty((T, F), np.float32))
+        r_dev = step_device().cpu().numpy()
+
+        def step_host():
+            eng.label_host(ob_host, off_np, F, out=outs)
+            if world > 1:
+                both = torch.from_numpy(np.stack([outs[0], outs[1]], axis=1)).to(dev)
+                gather_rows(both, rows, dst=0)
+
+        step_host()
+        assert np.array_equal(outs[0], r_dev), "host and device entry points disagree"
+        t_e2e = []
+        for _ in range(max(1, min(args.steps, 2))):
+            if world > 1:
+                dist.barrier()
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            step_host()
+            torch.cuda.synchronize()
+            t_e2e.append(time.perf_counter() - t0)
+        te = torch.tensor([float(np.mean(t_e2e))], device=dev)
+        if world > 1:
+            dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        frame_bytes = args.size * args.size * 3
+        e2e = {"value": total_frames / float(te), "unit": "frames/s",
+               "h2d_bytes_per_step": int(total_frames * frame_bytes + (args.episodes + 1) * 8 * world),
+               "d2h_bytes_per_step": int(total_frames * 4 * (2 + 2 * F)),
+               "pinned_host": bool(ob_host.is_pinned()), "api": "arp_label_host (C ABI, host buffers)"}
+        del ob_host
+
+    # ---- CPU baseline (reference algorithm on the host cores), rank 0, N=1 only ----
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        rate, n, cores, out, frames, off_s, sd_cpu = cpu_reference_rate(args, args.cpu_sample_frames)
+        # parity on the same sample, same weights (reported, the tests are the gate)
+        r_gpu = eng.compute_reward(torch.from_numpy(frames).to(dev)).cpu().numpy()
+        dcos = float(np.abs(r_gpu - out["reward"]).max() / scale)
+        cpu = {"value": rate, "unit": "frames/s", "cores": cores, "kind": "port",
+               "sample": f"first {len(off_s) - 1} episodes ({n} frames) of the same synthetic workload; "
+                         f"oracle/port.py (torch CPU fp32 + PIL + python scan loops)",
+               "parity_max_abs_dcos_on_sample": dcos}
+
+    if rank == 0:
+        print(json.dumps({
+            "metric": "reward-labeled frames/sec", "value": value, "unit": "frames/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": workload_config(args, T), "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
+            "roofline": roofline, "cpu_baseline": cpu,
+        }))
+    eng.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

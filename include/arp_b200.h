@@ -161,6 +161,20 @@ ARP_API int arp_attention(ArpHandle* h, const void* qkv_dev, void* out_dev, int3
 /* counters: kernels launched by this handle since creation (bench.py's gpu_launches) */
 ARP_API int64_t arp_launch_count(const ArpHandle* h);
 
+/* Optional per-kernel-class timing. Between begin and end every launch is bracketed by CUDA events on the
+ * stream it is launched on; end synchronises the device and fills stats[class] for
+ * class 0 GEMM, 1 attention, 2 LayerNorm, 3 decode, 4 head, 5 scan, 6 other. `flops` / `bytes` are the
+ * ALGORITHMIC work of those launches (2MNK; operand + result bytes), not hardware counters. */
+typedef struct ArpProfileStats {
+  int64_t launches;
+  double total_ms;
+  double flops;
+  double bytes;
+} ArpProfileStats;
+#define ARP_PROFILE_CLASSES 7
+ARP_API int arp_profile_begin(ArpHandle* h);
+ARP_API int arp_profile_end(ArpHandle* h, ArpProfileStats* stats, int32_t n_classes);
+
 #ifdef __cplusplus
 }
 #endif
