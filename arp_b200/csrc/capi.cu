@@ -16,8 +16,10 @@
 
 #include "../../include/arp_b200.h"
 #include "attention.cuh"
+#include "attention_tc.cuh"
 #include "decode.cuh"
 #include "gemm_tcgen05.cuh"
+#include "gemm2_tcgen05.cuh"
 #include "head.cuh"
 #include "layernorm.cuh"
 #include "scan.cuh"
@@ -83,9 +85,10 @@ struct WeightSlot {
 };
 
 struct TmapKey {
-  const void* ptr; uint64_t rows, cols, ld; uint32_t box_rows;
+  const void* ptr; uint64_t rows, cols, ld; uint32_t box_rows, box_cols, elem;
   bool operator<(const TmapKey& o) const {
-    return std::tie(ptr, rows, cols, ld, box_rows) < std::tie(o.ptr, o.rows, o.cols, o.ld, o.box_rows);
+    return std::tie(ptr, rows, cols, ld, box_rows, box_cols, elem) <
+           std::tie(o.ptr, o.rows, o.cols, o.ld, o.box_rows, o.box_cols, o.elem);
   }
 };
 
@@ -93,6 +96,8 @@ struct ArpHandle {
   ArpConfig cfg;
   std::string err;
   int64_t launches = 0;
+  int attn_impl = 2;  // 1 = mma.sync kernel, 2 = tcgen05 kernel (ARP_ATTN_IMPL overrides)
+  int gemm_impl = 3;  // 1 = v1 (register stores), 2 = v2 single-CTA, 3 = v2 CTA pairs (ARP_GEMM_IMPL overrides)
   int tokens = 0, grid = 0, kp = 0;  // 197, 14, 768
   bool adapter = false, goal = false;
   int n_scales = 0, feat_dim = 0;    // 13, 6656 for adapter heads
@@ -453,6 +458,9 @@ extern "C" int arp_create(const ArpConfig* cfg, ArpHandle** out) {
   h->cfg = *cfg;
   auto bail = [&](int code) { g_create_error = h->err; arp_destroy(h); return code; };
   if (cudaSetDevice(cfg->device) != cudaSuccess) { h->err = "cudaSetDevice failed"; return bail(ARP_ERR_CUDA); }
+  if (const char* e = getenv("ARP_GEMM_IMPL")) h->gemm_impl = atoi(e);
+  if (h->gemm_impl < 1 || h->gemm_impl > 3) h->gemm_impl = 3;
+  if (const char* e = getenv("ARP_ATTN_IMPL")) h->attn_impl = atoi(e) == 1 ? 1 : 2;
   h->grid = DEC_OUT / cfg->patch;
   h->tokens = h->grid * h->grid + 1;
   h->kp = 3 * cfg->patch * cfg->patch;
@@ -471,6 +479,8 @@ extern "C" int arp_create(const ArpConfig* cfg, ArpHandle** out) {
   CREATE_TRY(dev_alloc(h, &h->x, M * W));
   CREATE_TRY(dev_alloc(h, &h->xn, M * W));
   CREATE_TRY(dev_alloc(h, &h->qkv, M * 3 * W));
+  // padded key rows of a frame are the next frame's rows: keep every bit pattern in this buffer finite
+  if (cudaMemset(h->qkv, 0, M * 3 * W * sizeof(bf16)) != cudaSuccess) { h->err = "cudaMemset failed"; return bail(ARP_ERR_CUDA); }
   CREATE_TRY(dev_alloc(h, &h->attn, M * W));
   CREATE_TRY(dev_alloc(h, &h->hid, M * std::max<size_t>(4 * W, h->kp)));
   CREATE_TRY(dev_alloc(h, &h->rowtab, (size_t)h->tokens * W));
@@ -499,6 +509,15 @@ extern "C" int arp_create(const ArpConfig* cfg, ArpHandle** out) {
   CREATE_TRY(set_smem(h, gemm_bf16_tcgen05_kernel<float, ACT_NONE>, GEMM_SMEM_BYTES));
   CREATE_TRY(set_smem(h, gemm_bf16_tcgen05_kernel<float, ACT_QUICKGELU>, GEMM_SMEM_BYTES));
   CREATE_TRY(set_smem(h, gemm_bf16_tcgen05_kernel<float, ACT_RELU>, GEMM_SMEM_BYTES));
+#define G2_ATTR(T, A, R)                                                                              \
+  CREATE_TRY(set_smem(h, gemm2_bf16_tcgen05_kernel<T, A, 1, R>, G2Cfg<1>::SMEM_BYTES));               \
+  CREATE_TRY(set_smem(h, gemm2_bf16_tcgen05_kernel<T, A, 2, R>, G2Cfg<2>::SMEM_BYTES));
+  G2_ATTR(bf16, ACT_NONE, false) G2_ATTR(bf16, ACT_QUICKGELU, false) G2_ATTR(bf16, ACT_RELU, false)
+  G2_ATTR(float, ACT_NONE, false) G2_ATTR(float, ACT_QUICKGELU, false) G2_ATTR(float, ACT_RELU, false)
+  G2_ATTR(float, ACT_NONE, true)
+#undef G2_ATTR
+  CREATE_TRY(set_smem(h, attention_tc_kernel<197>, AtcCfg<197>::SMEM_BYTES));
+  CREATE_TRY(set_smem(h, attention_tc_kernel<50>, AtcCfg<50>::SMEM_BYTES));
   CREATE_TRY(set_smem(h, attention_kernel<197>, AttnCfg<197>::SMEM));
   CREATE_TRY(set_smem(h, attention_kernel<50>, AttnCfg<50>::SMEM));
   CREATE_TRY(set_smem(h, decode_kernel, 160 * 1024));
@@ -620,26 +639,89 @@ extern "C" int arp_set_text(ArpHandle* h, const float* text_emb_dev, int32_t n_t
 // ------------------------------------------------------------------------------------------------
 // launch helpers
 // ------------------------------------------------------------------------------------------------
+// 2-D row-major tensor [rows, cols] with row pitch ld (elements of `elem` bytes: 2 = bf16, 4 = fp32),
+// box [box_rows, box_cols] with a 128-byte inner extent and the 128B swizzle.
 static int get_tmap(ArpHandle* h, const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows,
-                    const CUtensorMap** out) {
-  TmapKey key{ptr, rows, cols, ld, box_rows};
+                    const CUtensorMap** out, uint32_t box_cols = GEMM_BK, uint32_t elem = 2) {
+  TmapKey key{ptr, rows, cols, ld, box_rows, box_cols, elem};
   auto it = h->tmaps.find(key);
   if (it == h->tmaps.end()) {
     if (h->tmaps.size() > 4096) h->tmaps.clear();
     CUtensorMap m;
     cuuint64_t gdim[2] = {cols, rows};
-    cuuint64_t gstr[1] = {ld * 2};
-    cuuint32_t box[2] = {GEMM_BK, box_rows};
+    cuuint64_t gstr[1] = {ld * elem};
+    cuuint32_t box[2] = {box_cols, box_rows};
     cuuint32_t estr[2] = {1, 1};
     if ((reinterpret_cast<uintptr_t>(ptr) & 15) || (gstr[0] & 15))
       return fail(h, ARP_ERR_INVALID, "GEMM operand must be 16-byte aligned with a 16-byte multiple row pitch");
-    CUresult r = get_encode_tiled()(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), gdim, gstr, box,
+    CUresult r = get_encode_tiled()(&m, elem == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32,
+                                    2, const_cast<void*>(ptr), gdim, gstr, box,
                                     estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return fail(h, ARP_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d) rows=%llu cols=%llu", (int)r, (unsigned long long)rows, (unsigned long long)cols);
     it = h->tmaps.emplace(key, m).first;
   }
   *out = &it->second;
+  return ARP_OK;
+}
+
+template <typename K>
+static cudaError_t launch_clustered(K kernel, int grid, int cg, int smem, cudaStream_t st, const CUtensorMap& ta,
+                                    const CUtensorMap& tb, const CUtensorMap& to, const GemmArgs& g) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(G2_THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = cg;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, ta, tb, to, g);
+}
+
+// v2 GEMM: TMA-store epilogue, residual by TMA reduce-add, optional CTA pairs (gemm2_tcgen05.cuh)
+static int launch_gemm2(ArpHandle* h, const bf16* a, int64_t a_rows_alloc, const bf16* w, GemmArgs g, bool out_f32,
+                        int act, cudaStream_t st) {
+  const int cg = h->gemm_impl == 3 ? 2 : 1;
+  const CUtensorMap *ta, *tb, *to;
+  ARP_TRY(get_tmap(h, a, (uint64_t)a_rows_alloc, (uint64_t)g.K, (uint64_t)g.K, GEMM_BM, &ta));
+  ARP_TRY(get_tmap(h, w, (uint64_t)g.N, (uint64_t)g.K, (uint64_t)g.K, GEMM_BN / cg, &tb));
+  ARP_TRY(get_tmap(h, g.out, (uint64_t)g.M, (uint64_t)g.N, (uint64_t)g.ldo, 32, &to, out_f32 ? 32 : 64, out_f32 ? 4 : 2));
+  bool reduce = false;
+  if (g.resid) {
+    if (!out_f32 || act != ACT_NONE) return fail(h, ARP_ERR_INVALID, "residual epilogue needs fp32 output and no activation");
+    if (g.resid != g.out)  // out-of-place residual (test hook only): seed the output, then accumulate into it
+      ARP_CUDA(h, cudaMemcpy2DAsync(g.out, (size_t)g.ldo * 4, g.resid, (size_t)g.ldr * 4, (size_t)g.N * 4, (size_t)g.M,
+                                    cudaMemcpyDeviceToDevice, st));
+    reduce = true;
+    g.resid = nullptr;
+  }
+  const int tiles = (int)((g.M + GEMM_BM * cg - 1) / (GEMM_BM * cg)) * (g.N / GEMM_BN);
+  const int grid = std::min(tiles * cg, kNumSMs / cg * cg);
+  const int smem = cg == 2 ? G2Cfg<2>::SMEM_BYTES : G2Cfg<1>::SMEM_BYTES;
+  ProfScope prof(h, PC_GEMM, 2.0 * (double)g.M * g.N * g.K,
+                 (double)g.M * g.K * 2 + (double)g.N * g.K * 2 + (double)g.M * g.N * (out_f32 ? 4 : 2) * (reduce ? 2 : 1), st);
+  cudaError_t e;
+#define G2_LAUNCH(T, A, R)                                                                                         \
+  e = cg == 2 ? launch_clustered(gemm2_bf16_tcgen05_kernel<T, A, 2, R>, grid, 2, smem, st, *ta, *tb, *to, g)       \
+              : launch_clustered(gemm2_bf16_tcgen05_kernel<T, A, 1, R>, grid, 1, smem, st, *ta, *tb, *to, g)
+  if (reduce) G2_LAUNCH(float, ACT_NONE, true);
+  else if (out_f32) {
+    if (act == ACT_NONE) G2_LAUNCH(float, ACT_NONE, false);
+    else if (act == ACT_QUICKGELU) G2_LAUNCH(float, ACT_QUICKGELU, false);
+    else G2_LAUNCH(float, ACT_RELU, false);
+  } else {
+    if (act == ACT_NONE) G2_LAUNCH(bf16, ACT_NONE, false);
+    else if (act == ACT_QUICKGELU) G2_LAUNCH(bf16, ACT_QUICKGELU, false);
+    else G2_LAUNCH(bf16, ACT_RELU, false);
+  }
+#undef G2_LAUNCH
+  h->launches++;
+  if (e != cudaSuccess) return fail(h, ARP_ERR_CUDA, "gemm2 launch failed: %s", cudaGetErrorString(e));
   return ARP_OK;
 }
 
@@ -657,6 +739,7 @@ static int launch_gemm(ArpHandle* h, const bf16* a, int64_t a_rows_alloc, const 
   GemmArgs g;
   g.M = (int)M; g.N = N; g.K = K; g.out = out; g.ldo = ldo; g.bias = bias; g.resid = resid; g.ldr = ldr;
   g.rowtab = rowtab; g.period = period > 0 ? period : 1;
+  if (h->gemm_impl >= 2) return launch_gemm2(h, a, a_rows_alloc, w, g, out_f32, act, st);
   const int tiles = (int)((M + GEMM_BM - 1) / GEMM_BM) * (N / GEMM_BN);
   const int grid = std::min(tiles, kNumSMs);
   ProfScope prof(h, PC_GEMM, 2.0 * (double)M * N * K,
@@ -720,11 +803,29 @@ static int launch_ln_bf16(ArpHandle* h, const float* x, const float* g, const fl
   return ARP_OK;
 }
 
-static int launch_attention(ArpHandle* h, const bf16* qkv, bf16* out, int B, int tokens, cudaStream_t st) {
+static int launch_attention(ArpHandle* h, const bf16* qkv, bf16* out, int B, int tokens, cudaStream_t st,
+                            int64_t rows_alloc = 0) {
   if (B <= 0) return ARP_OK;
   const float scale_log2e = 0.125f * 1.4426950408889634f;
   ProfScope prof(h, PC_ATTENTION, 4.0 * (double)B * h->cfg.heads * tokens * tokens * ATT_DH,
                  (double)B * tokens * h->cfg.width * 2 * 4, st);
+  if (h->attn_impl == 2) {
+    if (tokens != 197 && tokens != 50) return fail(h, ARP_ERR_INVALID, "attention is built for 197 or 50 tokens, got %d", tokens);
+    const int W = h->cfg.width;
+    const uint64_t rows = rows_alloc > 0 ? (uint64_t)rows_alloc : (uint64_t)B * tokens;
+    const int nk = (tokens + 15) / 16 * 16;
+    const CUtensorMap *tq, *tkv;
+    ARP_TRY(get_tmap(h, qkv, rows, 3 * W, 3 * W, 128, &tq));
+    ARP_TRY(get_tmap(h, qkv, rows, 3 * W, 3 * W, nk, &tkv));
+    const int grid = std::min(B * h->cfg.heads, kNumSMs);
+    if (tokens == 197)
+      attention_tc_kernel<197><<<grid, ATC_THREADS, AtcCfg<197>::SMEM_BYTES, st>>>(*tq, *tkv, out, B, h->cfg.heads, W, scale_log2e);
+    else
+      attention_tc_kernel<50><<<grid, ATC_THREADS, AtcCfg<50>::SMEM_BYTES, st>>>(*tq, *tkv, out, B, h->cfg.heads, W, scale_log2e);
+    h->launches++;
+    ARP_CUDA(h, cudaGetLastError());
+    return ARP_OK;
+  }
   for (int b0 = 0; b0 < B; b0 += 32768) {
     const int cnt = std::min(32768, B - b0);
     const bf16* q = qkv + (size_t)b0 * tokens * 3 * h->cfg.width;
@@ -764,7 +865,7 @@ static int encode_chunk(ArpHandle* h, const uint8_t* ob, int64_t n, int64_t stri
     ARP_TRY(launch_ln_bf16(h, h->x, L.ln1_g, L.ln1_b, h->xn, M, st));
     ARP_TRY(launch_gemm(h, h->xn, Mcap, L.w_qkv, h->qkv, false, ACT_NONE, M, 3 * W, W, 3 * W, L.b_qkv, nullptr, 0,
                         nullptr, 0, st));
-    ARP_TRY(launch_attention(h, h->qkv, h->attn, (int)n, h->tokens, st));
+    ARP_TRY(launch_attention(h, h->qkv, h->attn, (int)n, h->tokens, st, Mcap));
     ARP_TRY(launch_gemm(h, h->attn, Mcap, L.w_out, h->x, true, ACT_NONE, M, W, W, W, L.b_out, h->x, W, nullptr, 0, st));
     ARP_TRY(launch_ln_bf16(h, h->x, L.ln2_g, L.ln2_b, h->xn, M, st));
     ARP_TRY(launch_gemm(h, h->xn, Mcap, L.w_fc, h->hid, false, ACT_QUICKGELU, M, 4 * W, W, 4 * W, L.b_fc, nullptr, 0,

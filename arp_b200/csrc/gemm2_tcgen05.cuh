@@ -1,0 +1,262 @@
+// GEMM v2 — same contract as gemm_tcgen05.cuh (C = epilogue(A · W^T), bf16 in, fp32 accumulate in TMEM) with
+//   * an epilogue that never issues an uncoalesced global access: 8 epilogue warps pull 32x128-byte
+//     sub-tiles out of TMEM, apply bias / periodic row table / activation in registers, stage them in
+//     128B-swizzled shared memory (bank-conflict free) and hand them to the TMA unit
+//     (cp.async.bulk.tensor store; rows past M are clipped by the descriptor);
+//   * the fp32 residual stream updated by TMA reduce-add (cp.reduce.async.bulk.tensor .add): x += tile is
+//     performed at L2, so the epilogue never reads the residual — same rounding as fl(x + fl(acc + bias));
+//   * an optional CTA-pair mode (CG = 2): tcgen05.mma.cta_group::2 with M = 256 across two SMs of a cluster,
+//     each CTA staging half of the W tile, which halves shared-memory and L2 traffic for the B operand.
+//
+// Warp roles (320 threads): 0 = TMA producer, 1 = MMA issuer + TMEM owner, 2..9 = epilogue
+// (warp w reads TMEM lane quarter w%4; warps 2-5 take accumulator columns 0-127, warps 6-9 columns 128-255).
+#pragma once
+
+#include "common.cuh"
+#include "gemm_tcgen05.cuh"  // GemmArgs, GemmAct, tile constants
+
+namespace arp {
+
+constexpr int G2_THREADS = 320;
+constexpr int G2_EPI_WARPS = 8;
+constexpr int G2_STAGE_UNIT = 32 * 128;  // one staging buffer: 32 rows x 128 B
+constexpr int G2_STAGING_BYTES = G2_EPI_WARPS * 2 * G2_STAGE_UNIT;  // 64 KB
+
+template <int CG>
+struct G2Cfg {
+  static constexpr int B_ROWS = GEMM_BN / CG;                       // W rows staged per CTA
+  static constexpr int STAGE_BYTES = GEMM_A_BYTES + B_ROWS * GEMM_BK * 2;
+  static constexpr int STAGES = CG == 1 ? 3 : 5;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + G2_STAGING_BYTES + 1024 + 256;
+};
+
+template <typename OutT, int ACT, int CG, bool REDUCE>
+__global__ void __launch_bounds__(G2_THREADS, 1)
+gemm2_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                          const __grid_constant__ CUtensorMap tmap_out, const GemmArgs args) {
+  using Cfg = G2Cfg<CG>;
+  constexpr int STAGES = Cfg::STAGES;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* staging = smem + STAGES * Cfg::STAGE_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(staging + G2_STAGING_BYTES);
+  uint64_t* full_bar = bars;
+  uint64_t* empty_bar = bars + STAGES;
+  uint64_t* tfull_bar = bars + 2 * STAGES;
+  uint64_t* tempty_bar = tfull_bar + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = CG == 2 ? cluster_ctarank() : 0;
+  const int cluster_id = blockIdx.x / CG;
+  const int num_clusters = gridDim.x / CG;
+
+  const int num_m = (args.M + GEMM_BM * CG - 1) / (GEMM_BM * CG);
+  const int num_n = args.N / GEMM_BN;
+  const int num_tiles = num_m * num_n;
+  const int num_kb = args.K / GEMM_BK;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_a);
+    tma_prefetch_desc(&tmap_b);
+    tma_prefetch_desc(&tmap_out);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < STAGES; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tfull_bar[i], 1);
+      mbar_init(&tempty_bar[i], G2_EPI_WARPS * CG);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    if (CG == 1) tmem_alloc<512>(tmem_slot); else tmem_alloc_cg2<512>(tmem_slot);
+  }
+  tc_fence_before();
+  if (CG == 2) cluster_sync_all(); else __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer (every CTA loads its own A rows and its share of W) =====================
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+      const int m_blk = tile / num_n, n_blk = tile % num_n;
+      const int a_row = (m_blk * CG + rank) * GEMM_BM;
+      const int b_row = n_blk * GEMM_BN + rank * Cfg::B_ROWS;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        if (lane == 0) {
+          uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
+          uint8_t* sb = sa + GEMM_A_BYTES;
+          if (CG == 1) {
+            mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
+            tma_load_2d(sa, &tmap_a, &full_bar[stage], kb * GEMM_BK, a_row);
+            tma_load_2d(sb, &tmap_b, &full_bar[stage], kb * GEMM_BK, b_row);
+          } else {
+            // both CTAs' bytes are credited to the leader's barrier, which the leader arms for 2x the bytes
+            if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * Cfg::STAGE_BYTES);
+            const uint32_t leader_bar = mapa_u32(smem_u32(&full_bar[stage]), 0);
+            tma_load_2d_cg2(sa, &tmap_a, leader_bar, kb * GEMM_BK, a_row);
+            tma_load_2d_cg2(sb, &tmap_b, leader_bar, kb * GEMM_BK, b_row);
+          }
+        }
+        __syncwarp();
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (leader CTA of the pair only) =====================
+    if (rank == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(GEMM_BM * CG, GEMM_BN);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+        mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * GEMM_BN;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          if (lane == 0) {
+            const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE_BYTES);
+            const uint64_t da = umma_desc_kmajor_sw128(sa);
+            const uint64_t db = umma_desc_kmajor_sw128(sa + GEMM_A_BYTES);
+#pragma unroll
+            for (int k = 0; k < GEMM_BK / 16; ++k) {
+              if (CG == 1) umma_bf16_ss(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+              else umma_bf16_ss_cg2(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+            }
+            if (CG == 1) {
+              umma_commit(&empty_bar[stage]);
+              if (kb == num_kb - 1) umma_commit(&tfull_bar[acc]);
+            } else {
+              umma_commit_cg2(&empty_bar[stage], 0b11);
+              if (kb == num_kb - 1) umma_commit_cg2(&tfull_bar[acc], 0b11);
+            }
+          }
+          __syncwarp();
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else {
+    // ===================== epilogue (warps 2..9) =====================
+    const int ew = warp - 2;
+    const int quarter = warp & 3;   // TMEM lane quarter this warp may touch
+    const int half = ew >> 2;       // accumulator column half
+    uint8_t* my_stage = staging + ew * 2 * G2_STAGE_UNIT;
+    constexpr int UNIT_COLS = sizeof(OutT) == 4 ? 32 : 64;   // 128 B per row
+    constexpr int UNITS = 128 / UNIT_COLS;
+    const uint32_t tempty_leader0 = CG == 2 ? mapa_u32(smem_u32(&tempty_bar[0]), 0) : 0;
+    const uint32_t tempty_leader1 = CG == 2 ? mapa_u32(smem_u32(&tempty_bar[1]), 0) : 0;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    uint32_t buf = 0;
+    const int sw = lane & 7;
+    for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+      const int m_blk = tile / num_n, n_blk = tile % num_n;
+      mbar_wait(&tfull_bar[acc], acc_phase);
+      tc_fence_after();
+      const int row0 = (m_blk * CG + rank) * GEMM_BM + quarter * 32;
+      const int row = row0 + lane;
+      const uint32_t taddr = tmem_base + acc * GEMM_BN + half * 128 + (static_cast<uint32_t>(quarter * 32) << 16);
+      const float* tab_row =
+          args.rowtab ? args.rowtab + static_cast<size_t>(row % args.period) * args.N : nullptr;
+#pragma unroll 1
+      for (int u = 0; u < UNITS; ++u) {
+        const int n0 = n_blk * GEMM_BN + half * 128 + u * UNIT_COLS;
+        float v[UNIT_COLS];
+        {
+          uint32_t r[32];
+          tmem_ld_32x32(taddr + u * UNIT_COLS, r);
+          if (UNIT_COLS == 64) {
+            uint32_t r2[32];
+            tmem_ld_32x32(taddr + u * UNIT_COLS + 32, r2);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[(UNIT_COLS == 64 ? 32 : 0) + j] = __uint_as_float(r2[j]);
+          } else {
+            tmem_ld_wait();
+          }
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+        }
+        if (u == UNITS - 1) {
+          // all of this warp's accumulator columns are in registers: hand the TMEM stage back to the MMA warp
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) {
+            if (CG == 1) mbar_arrive(&tempty_bar[acc]);
+            else mbar_arrive_cluster(acc ? tempty_leader1 : tempty_leader0);
+          }
+        }
+        if (args.bias) {
+#pragma unroll
+          for (int j = 0; j < UNIT_COLS; j += 4) {
+            const float4 b = __ldg(reinterpret_cast<const float4*>(args.bias + n0 + j));
+            v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
+          }
+        }
+        if (tab_row) {
+#pragma unroll
+          for (int j = 0; j < UNIT_COLS; j += 4) {
+            const float4 b = __ldg(reinterpret_cast<const float4*>(tab_row + n0 + j));
+            v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
+          }
+        }
+        if (ACT == ACT_QUICKGELU) {
+#pragma unroll
+          for (int j = 0; j < UNIT_COLS; ++j) v[j] = __fdividef(v[j], 1.0f + __expf(-1.702f * v[j]));
+        } else if (ACT == ACT_RELU) {
+#pragma unroll
+          for (int j = 0; j < UNIT_COLS; ++j) v[j] = fmaxf(v[j], 0.0f);
+        }
+        // staging buffer `buf` was last read by the TMA store issued two units ago
+        uint8_t* sbuf = my_stage + buf * G2_STAGE_UNIT;
+        if (lane == 0) tma_store_wait_read<1>();
+        __syncwarp();
+        uint4* srow = reinterpret_cast<uint4*>(sbuf + lane * 128);
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          uint4 q;
+          if (sizeof(OutT) == 4) {
+            q = make_uint4(__float_as_uint(v[4 * c]), __float_as_uint(v[4 * c + 1]), __float_as_uint(v[4 * c + 2]),
+                           __float_as_uint(v[4 * c + 3]));
+          } else {
+            q = make_uint4(pack_bf16(v[8 * c], v[8 * c + 1]), pack_bf16(v[8 * c + 2], v[8 * c + 3]),
+                           pack_bf16(v[8 * c + 4], v[8 * c + 5]), pack_bf16(v[8 * c + 6], v[8 * c + 7]));
+          }
+          srow[c ^ sw] = q;   // 128B swizzle: 16-byte chunk index XOR (row & 7)
+        }
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+          if (REDUCE) tma_reduce_add_2d(&tmap_out, sbuf, n0, row0);
+          else tma_store_2d(&tmap_out, sbuf, n0, row0);
+          tma_store_commit();
+        }
+        buf ^= 1;
+      }
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+    if (lane == 0) tma_store_wait_all<0>();
+  }
+
+  tc_fence_before();
+  if (CG == 2) cluster_sync_all(); else __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    if (CG == 1) tmem_dealloc<512>(tmem_base); else tmem_dealloc_cg2<512>(tmem_base);
+  }
+}
+
+}  // namespace arp
