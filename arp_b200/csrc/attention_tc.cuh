@@ -74,7 +74,26 @@ __device__ __forceinline__ uint64_t umma_desc_mnmajor_sw128(uint32_t smem_addr) 
   return d;
 }
 
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+__device__ __forceinline__ void tmem_st_32x16(uint32_t taddr, const uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, "
+      "%15, %16};" ::"r"(taddr),
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+      "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+      : "memory");
+}
+
 // qkv: bf16 [rows, 3*width] (tensor maps: box 64x128 for Q, 64xNK for K/V); out: bf16 [B*L, width]
+//
+// Each query tile of an item is an independent "job" with its own TMEM slot (256 columns) and its own
+// S/P/O barriers, so the MMA warp can run tile 1's Q K^T while tile 0's rows are in softmax, and tile 0's
+// P V while tile 1's rows are in softmax.
 template <int L>
 __global__ void __launch_bounds__(ATC_THREADS, 1)
 attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_kv,
@@ -84,12 +103,12 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 2 * C::BUF_BYTES);
   uint64_t* smem_full = bars;        // [2] TMA -> MMA
-  uint64_t* smem_empty = bars + 2;   // [2] MMA (PV retired) -> TMA
-  uint64_t* s_full = bars + 4;       // MMA -> softmax: S ready
-  uint64_t* p_full = bars + 5;       // softmax -> MMA: P written
-  uint64_t* o_full = bars + 6;       // MMA -> epilogue: O ready
-  uint64_t* tmem_free = bars + 7;    // epilogue -> MMA: O drained, TMEM reusable
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+  uint64_t* smem_empty = bars + 2;   // [2] MMA (all P V of the item retired) -> TMA
+  uint64_t* s_full = bars + 4;       // [2 slots] MMA -> softmax: S ready
+  uint64_t* p_full = bars + 6;       // [2] softmax -> MMA: P written
+  uint64_t* o_full = bars + 8;       // [2] MMA -> epilogue: O ready
+  uint64_t* tmem_free = bars + 10;   // [2] epilogue -> MMA: O drained, slot reusable
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_items = n_frames * heads;
@@ -100,11 +119,14 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
     tma_prefetch_desc(&tmap_kv);
   }
   if (warp == 1 && lane == 0) {
-    for (int i = 0; i < 2; ++i) { mbar_init(&smem_full[i], 1); mbar_init(&smem_empty[i], 1); }
-    mbar_init(s_full, 1);
-    mbar_init(p_full, SM_WARPS);
-    mbar_init(o_full, 1);
-    mbar_init(tmem_free, SM_WARPS);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&smem_full[i], 1);
+      mbar_init(&smem_empty[i], 1);
+      mbar_init(&s_full[i], 1);
+      mbar_init(&p_full[i], 4);
+      mbar_init(&o_full[i], 1);
+      mbar_init(&tmem_free[i], 4);
+    }
     fence_mbar_init();
   }
   if (warp == 1) tmem_alloc<512>(tmem_slot);
@@ -137,43 +159,45 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
     // ===================== MMA issuer =====================
     constexpr uint32_t idesc_s = umma_idesc_bf16(128, C::NK);          // Q K^T: both operands K-major
     constexpr uint32_t idesc_o = umma_idesc_bf16(128, ATC_DH, 0, 1);   // P V: A from TMEM, B = V MN-major
+    auto issue_s = [&](uint32_t sbuf, int t) {
+      const uint64_t dk = umma_desc_kmajor_sw128(sbuf + C::QT * C::Q_BYTES);
+      const uint64_t dq = umma_desc_kmajor_sw128(sbuf + t * C::Q_BYTES);
+#pragma unroll
+      for (int k = 0; k < ATC_DH / 16; ++k)
+        umma_bf16_ss(tmem_base + t * 256, dq + 2 * k, dk + 2 * k, idesc_s, k != 0);
+      umma_commit(&s_full[t]);
+    };
+    auto issue_pv = [&](uint32_t sbuf, int t) {
+      const uint64_t dv = umma_desc_mnmajor_sw128(sbuf + C::QT * C::Q_BYTES + C::KV_PAD);
+#pragma unroll
+      for (int k = 0; k < C::NK / 16; ++k)
+        // 16 keys per MMA: A advances 8 packed columns, V advances 16 rows x 128 B = 2048 B
+        umma_bf16_ts(tmem_base + t * 256 + C::O_COL, tmem_base + t * 256 + k * 8, dv + k * (2048 >> 4), idesc_o, k != 0);
+      umma_commit(&o_full[t]);
+    };
     uint32_t it = 0;
     for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
       const int b = it & 1;
       const uint32_t ph_buf = (it >> 1) & 1, ph = it & 1;
-      mbar_wait(&smem_full[b], ph_buf);
-      mbar_wait(tmem_free, ph ^ 1);
-      tc_fence_after();
       const uint32_t sbuf = smem_u32(smem + b * C::BUF_BYTES);
-      const uint32_t sk = sbuf + C::QT * C::Q_BYTES, sv = sk + C::KV_PAD;
-      if (lane == 0) {
-        const uint64_t dk = umma_desc_kmajor_sw128(sk);
+      mbar_wait(&smem_full[b], ph_buf);
 #pragma unroll
-        for (int t = 0; t < C::QT; ++t) {
-          const uint64_t dq = umma_desc_kmajor_sw128(sbuf + t * C::Q_BYTES);
-#pragma unroll
-          for (int k = 0; k < ATC_DH / 16; ++k)
-            umma_bf16_ss(tmem_base + t * 256, dq + 2 * k, dk + 2 * k, idesc_s, k != 0);
-        }
-        umma_commit(s_full);
+      for (int t = 0; t < C::QT; ++t) {
+        mbar_wait(&tmem_free[t], ph ^ 1);     // previous item's O of this slot has been drained
+        tc_fence_after();
+        if (lane == 0) issue_s(sbuf, t);
+        __syncwarp();
       }
-      __syncwarp();
-      mbar_wait(p_full, ph);
-      tc_fence_after();
-      if (lane == 0) {
-        const uint64_t dv = umma_desc_mnmajor_sw128(sv);
 #pragma unroll
-        for (int t = 0; t < C::QT; ++t) {
-#pragma unroll
-          for (int k = 0; k < C::NK / 16; ++k)
-            // 16 keys per MMA: A advances 8 packed columns, V advances 16 rows x 128 B = 2048 B
-            umma_bf16_ts(tmem_base + t * 256 + C::O_COL, tmem_base + t * 256 + k * 8, dv + k * (2048 >> 4), idesc_o,
-                         k != 0);
+      for (int t = 0; t < C::QT; ++t) {
+        mbar_wait(&p_full[t], ph);
+        tc_fence_after();
+        if (lane == 0) {
+          issue_pv(sbuf, t);
+          if (t == C::QT - 1) umma_commit(&smem_empty[b]);
         }
-        umma_commit(o_full);
-        umma_commit(&smem_empty[b]);
+        __syncwarp();
       }
-      __syncwarp();
     }
   } else if (warp - 2 < SM_WARPS) {
     // ===================== softmax + epilogue: one thread per query row =====================
@@ -181,47 +205,89 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
     const int quarter = warp & 3;
     const int qrow = qt * 128 + quarter * 32 + lane;     // query index inside the frame
     const uint32_t t_s = tmem_base + qt * 256 + (static_cast<uint32_t>(quarter * 32) << 16);
+    constexpr int NFULL = C::NK / 32;                    // full 32-column chunks
+    constexpr int TAIL = C::NK % 32;                     // 16 or 0
     uint32_t it = 0;
     for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
       const uint32_t ph = it & 1;
       const int frame = item / heads, head = item - frame * heads;
-      mbar_wait(s_full, ph);
+      mbar_wait(&s_full[qt], ph);
       tc_fence_after();
-      // pass 1: row maximum over the L real keys
+      // ---- pass 1: row maximum over the L real keys (all loads in flight before the first use) ----
       float m = -INFINITY;
+      {
+        uint32_t a[32], bq[32];
 #pragma unroll 1
-      for (int c0 = 0; c0 < C::NK; c0 += 16) {
-        uint32_t r[16];
-        tmem_ld_32x16(t_s + c0, r);
-        tmem_ld_wait();
+        for (int c = 0; c + 1 < NFULL; c += 2) {
+          tmem_ld_32x32(t_s + c * 32, a);
+          tmem_ld_32x32(t_s + c * 32 + 32, bq);
+          tmem_ld_wait();
 #pragma unroll
-        for (int j = 0; j < 16; ++j)
-          if (c0 + j < L) m = fmaxf(m, __uint_as_float(r[j]));
+          for (int j = 0; j < 32; ++j) {
+            if (c * 32 + j < L) m = fmaxf(m, __uint_as_float(a[j]));
+            if (c * 32 + 32 + j < L) m = fmaxf(m, __uint_as_float(bq[j]));
+          }
+        }
+        if (NFULL & 1) {
+          tmem_ld_32x32(t_s + (NFULL - 1) * 32, a);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if ((NFULL - 1) * 32 + j < L) m = fmaxf(m, __uint_as_float(a[j]));
+        }
+        if (TAIL) {
+          uint32_t r[16];
+          tmem_ld_32x16(t_s + NFULL * 32, r);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 16; ++j)
+            if (NFULL * 32 + j < L) m = fmaxf(m, __uint_as_float(r[j]));
+        }
       }
       const float mo = m * scale_log2e;
-      // pass 2: p = exp2(s * scale - max * scale); P (bf16 pairs) overwrites the S columns it came from
+      // ---- pass 2: p = exp2(s*scale - max*scale); P (bf16 pairs) overwrites the S columns it came from.
+      //      The load of chunk c+1 is issued before chunk c is processed (two register buffers). ----
       float sum = 0.f;
-#pragma unroll 1
-      for (int c0 = 0; c0 < C::NK; c0 += 16) {
-        uint32_t r[16];
-        tmem_ld_32x16(t_s + c0, r);
+      {
+        uint32_t cur[32], nxt[32];
+        tmem_ld_32x32(t_s, cur);
         tmem_ld_wait();
-        uint32_t pk[8];
+#pragma unroll 1
+        for (int c = 0; c < NFULL; ++c) {
+          if (c + 1 < NFULL) tmem_ld_32x32(t_s + (c + 1) * 32, nxt);
+          uint32_t pk[16];
 #pragma unroll
-        for (int j = 0; j < 16; j += 2) {
-          const float p0 = (c0 + j < L) ? exp2f(fmaf(__uint_as_float(r[j]), scale_log2e, -mo)) : 0.f;
-          const float p1 = (c0 + j + 1 < L) ? exp2f(fmaf(__uint_as_float(r[j + 1]), scale_log2e, -mo)) : 0.f;
-          sum += p0 + p1;
-          pk[j >> 1] = pack_bf16(p0, p1);
+          for (int j = 0; j < 32; j += 2) {
+            const float p0 = (c * 32 + j < L) ? ex2_approx(fmaf(__uint_as_float(cur[j]), scale_log2e, -mo)) : 0.f;
+            const float p1 = (c * 32 + j + 1 < L) ? ex2_approx(fmaf(__uint_as_float(cur[j + 1]), scale_log2e, -mo)) : 0.f;
+            sum += p0 + p1;
+            pk[j >> 1] = pack_bf16(p0, p1);
+          }
+          tmem_ld_wait();                       // chunk c+1 has landed: its source columns may now be overwritten
+          tmem_st_32x16(t_s + c * 16, pk);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) cur[j] = nxt[j];
         }
-        tmem_st_32x8(t_s + (c0 >> 1), pk);
+        if (TAIL) {
+          uint32_t r[16], pk[8];
+          tmem_ld_32x16(t_s + NFULL * 32, r);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 16; j += 2) {
+            const float p0 = (NFULL * 32 + j < L) ? ex2_approx(fmaf(__uint_as_float(r[j]), scale_log2e, -mo)) : 0.f;
+            const float p1 = (NFULL * 32 + j + 1 < L) ? ex2_approx(fmaf(__uint_as_float(r[j + 1]), scale_log2e, -mo)) : 0.f;
+            sum += p0 + p1;
+            pk[j >> 1] = pack_bf16(p0, p1);
+          }
+          tmem_st_32x8(t_s + NFULL * 16, pk);
+        }
       }
       tmem_st_wait();
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(p_full);
-      // epilogue: O / rowsum -> bf16 -> HBM (each thread owns one 128-byte output line)
-      mbar_wait(o_full, ph);
+      if (lane == 0) mbar_arrive(&p_full[qt]);
+      // ---- epilogue: O / rowsum -> bf16 -> HBM (each thread owns one 128-byte output line) ----
+      mbar_wait(&o_full[qt], ph);
       tc_fence_after();
       const float inv = 1.0f / sum;
       uint32_t o0[32], o1[32];
@@ -230,7 +296,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
       tmem_ld_wait();
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(tmem_free);
+      if (lane == 0) mbar_arrive(&tmem_free[qt]);
       if (qrow < L) {
         uint4* dst = reinterpret_cast<uint4*>(out + (static_cast<size_t>(frame) * L + qrow) * width + head * ATC_DH);
 #pragma unroll
