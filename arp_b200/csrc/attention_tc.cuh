@@ -121,7 +121,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < 2; ++i) {
       mbar_init(&smem_full[i], 1);
-      mbar_init(&smem_empty[i], 1);
+      mbar_init(&smem_empty[i], C::QT);
       mbar_init(&s_full[i], 1);
       mbar_init(&p_full[i], 4);
       mbar_init(&o_full[i], 1);
@@ -194,7 +194,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
         tc_fence_after();
         if (lane == 0) {
           issue_pv(sbuf, t);
-          if (t == C::QT - 1) umma_commit(&smem_empty[b]);
+          umma_commit(&smem_empty[b]);        // the item's smem is free once BOTH slots' P V have retired (count = QT)
         }
         __syncwarp();
       }
@@ -213,27 +213,38 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
       const int frame = item / heads, head = item - frame * heads;
       mbar_wait(&s_full[qt], ph);
       tc_fence_after();
-      // ---- pass 1: row maximum over the L real keys (all loads in flight before the first use) ----
+      // Only the last (partial or padded) chunk can contain key columns >= L; the others need no masking.
+      constexpr int NCLEAN = (L / 32 < NFULL) ? L / 32 : NFULL;   // full chunks whose 32 columns are all real keys
+      // ---- pass 1: row maximum over the L real keys (two 32-column loads in flight per wait) ----
       float m = -INFINITY;
       {
         uint32_t a[32], bq[32];
 #pragma unroll 1
-        for (int c = 0; c + 1 < NFULL; c += 2) {
+        for (int c = 0; c + 1 < NCLEAN; c += 2) {
           tmem_ld_32x32(t_s + c * 32, a);
           tmem_ld_32x32(t_s + c * 32 + 32, bq);
           tmem_ld_wait();
+          float m0 = m, m1 = -INFINITY;
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            if (c * 32 + j < L) m = fmaxf(m, __uint_as_float(a[j]));
-            if (c * 32 + 32 + j < L) m = fmaxf(m, __uint_as_float(bq[j]));
+          for (int j = 0; j < 32; j += 2) {
+            m0 = fmaxf(m0, fmaxf(__uint_as_float(a[j]), __uint_as_float(a[j + 1])));
+            m1 = fmaxf(m1, fmaxf(__uint_as_float(bq[j]), __uint_as_float(bq[j + 1])));
           }
+          m = fmaxf(m0, m1);
         }
-        if (NFULL & 1) {
-          tmem_ld_32x32(t_s + (NFULL - 1) * 32, a);
+        if (NCLEAN & 1) {
+          tmem_ld_32x32(t_s + (NCLEAN - 1) * 32, a);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; j += 2) m = fmaxf(m, fmaxf(__uint_as_float(a[j]), __uint_as_float(a[j + 1])));
+        }
+#pragma unroll
+        for (int c = NCLEAN; c < NFULL; ++c) {        // masked full chunks (only when L is not past them, e.g. L = 50)
+          tmem_ld_32x32(t_s + c * 32, a);
           tmem_ld_wait();
 #pragma unroll
           for (int j = 0; j < 32; ++j)
-            if ((NFULL - 1) * 32 + j < L) m = fmaxf(m, __uint_as_float(a[j]));
+            if (c * 32 + j < L) m = fmaxf(m, __uint_as_float(a[j]));
         }
         if (TAIL) {
           uint32_t r[16];
@@ -246,28 +257,38 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
       }
       const float mo = m * scale_log2e;
       // ---- pass 2: p = exp2(s*scale - max*scale); P (bf16 pairs) overwrites the S columns it came from.
-      //      The load of chunk c+1 is issued before chunk c is processed (two register buffers). ----
-      float sum = 0.f;
+      //      Two register buffers ping-pong: the load of the next chunk is in flight while this one is processed. ----
+      float sum0 = 0.f, sum1 = 0.f;
+      auto soft_chunk = [&](const uint32_t (&src)[32], int c, bool masked) {
+        uint32_t pk[16];
+#pragma unroll
+        for (int j = 0; j < 32; j += 2) {
+          float p0 = ex2_approx(fmaf(__uint_as_float(src[j]), scale_log2e, -mo));
+          float p1 = ex2_approx(fmaf(__uint_as_float(src[j + 1]), scale_log2e, -mo));
+          if (masked) {
+            if (c * 32 + j >= L) p0 = 0.f;
+            if (c * 32 + j + 1 >= L) p1 = 0.f;
+          }
+          sum0 += p0;
+          sum1 += p1;
+          pk[j >> 1] = pack_bf16(p0, p1);
+        }
+        tmem_st_32x16(t_s + c * 16, pk);
+      };
       {
-        uint32_t cur[32], nxt[32];
-        tmem_ld_32x32(t_s, cur);
+        uint32_t b0[32], b1[32];
+        tmem_ld_32x32(t_s, b0);
         tmem_ld_wait();
 #pragma unroll 1
-        for (int c = 0; c < NFULL; ++c) {
-          if (c + 1 < NFULL) tmem_ld_32x32(t_s + (c + 1) * 32, nxt);
-          uint32_t pk[16];
-#pragma unroll
-          for (int j = 0; j < 32; j += 2) {
-            const float p0 = (c * 32 + j < L) ? ex2_approx(fmaf(__uint_as_float(cur[j]), scale_log2e, -mo)) : 0.f;
-            const float p1 = (c * 32 + j + 1 < L) ? ex2_approx(fmaf(__uint_as_float(cur[j + 1]), scale_log2e, -mo)) : 0.f;
-            sum += p0 + p1;
-            pk[j >> 1] = pack_bf16(p0, p1);
-          }
-          tmem_ld_wait();                       // chunk c+1 has landed: its source columns may now be overwritten
-          tmem_st_32x16(t_s + c * 16, pk);
-#pragma unroll
-          for (int j = 0; j < 32; ++j) cur[j] = nxt[j];
+        for (int c = 0; c + 1 < NFULL; c += 2) {
+          tmem_ld_32x32(t_s + (c + 1) * 32, b1);            // chunk c+1 in flight
+          soft_chunk(b0, c, c >= NCLEAN);
+          tmem_ld_wait();
+          if (c + 2 < NFULL) tmem_ld_32x32(t_s + (c + 2) * 32, b0);   // chunk c+2 in flight
+          soft_chunk(b1, c + 1, c + 1 >= NCLEAN);
+          tmem_ld_wait();
         }
+        if (NFULL & 1) soft_chunk(b0, NFULL - 1, NFULL - 1 >= NCLEAN);
         if (TAIL) {
           uint32_t r[16], pk[8];
           tmem_ld_32x16(t_s + NFULL * 32, r);
@@ -276,12 +297,14 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
           for (int j = 0; j < 16; j += 2) {
             const float p0 = (NFULL * 32 + j < L) ? ex2_approx(fmaf(__uint_as_float(r[j]), scale_log2e, -mo)) : 0.f;
             const float p1 = (NFULL * 32 + j + 1 < L) ? ex2_approx(fmaf(__uint_as_float(r[j + 1]), scale_log2e, -mo)) : 0.f;
-            sum += p0 + p1;
+            sum0 += p0;
+            sum1 += p1;
             pk[j >> 1] = pack_bf16(p0, p1);
           }
           tmem_st_32x8(t_s + NFULL * 16, pk);
         }
       }
+      const float sum = sum0 + sum1;
       tmem_st_wait();
       tc_fence_before();
       __syncwarp();

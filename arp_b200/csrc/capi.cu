@@ -125,12 +125,18 @@ struct ArpHandle {
   float* lut = nullptr;
   int crop_top = 0, crop_left = 0, src_h = 0, src_w = 0;
 
-  // workspace (sized for cfg.max_batch frames)
-  float* x = nullptr;
-  bf16 *xn = nullptr, *qkv = nullptr, *attn = nullptr, *hid = nullptr;
-  bf16 *taps = nullptr, *featb = nullptr, *hid2 = nullptr;
-  float *featf = nullptr, *mlp = nullptr, *feat_clip = nullptr;
-  float* logits_ws = nullptr;
+  // workspaces (each sized for cfg.max_batch frames). Optionally two chunks are in flight on two internal
+  // streams (ARP_PIPES=2), each with its own workspace.
+  struct Work {
+    float* x = nullptr;
+    bf16 *xn = nullptr, *qkv = nullptr, *attn = nullptr, *hid = nullptr;
+    bf16 *taps = nullptr, *featb = nullptr, *hid2 = nullptr;
+    float *featf = nullptr, *mlp = nullptr;
+  } ws[2];
+  int n_pipes = 1;                       // ARP_PIPES=2: two chunks in flight (measured: no gain on B200 — a resident
+                                         // persistent GEMM CTA leaves no room the scheduler will give to another kernel)
+  cudaStream_t pipe_stream[2] = {nullptr, nullptr};
+  cudaEvent_t ev_fork = nullptr, ev_join[2] = {nullptr, nullptr};
 
   // scratch that grows with T (goal heads, host path)
   void* scratch[2] = {nullptr, nullptr};  // [0] label temporaries, [1] device outputs of the host path
@@ -425,7 +431,10 @@ extern "C" void arp_destroy(ArpHandle* h) {
     if (h->stage_dev[i]) cudaFree(h->stage_dev[i]);
     if (h->ev_copied[i]) cudaEventDestroy(h->ev_copied[i]);
     if (h->ev_consumed[i]) cudaEventDestroy(h->ev_consumed[i]);
+    if (h->ev_join[i]) cudaEventDestroy(h->ev_join[i]);
+    if (h->pipe_stream[i]) cudaStreamDestroy(h->pipe_stream[i]);
   }
+  if (h->ev_fork) cudaEventDestroy(h->ev_fork);
   for (auto& r : h->prof) { cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); }
   for (cudaEvent_t e : h->event_pool) cudaEventDestroy(e);
   if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
@@ -476,23 +485,25 @@ extern "C" int arp_create(const ArpConfig* cfg, ArpHandle** out) {
 
   const size_t B = cfg->max_batch, M = B * h->tokens, W = cfg->width;
 #define CREATE_TRY(e) do { int _r = (e); if (_r != ARP_OK) return bail(_r); } while (0)
-  CREATE_TRY(dev_alloc(h, &h->x, M * W));
-  CREATE_TRY(dev_alloc(h, &h->xn, M * W));
-  CREATE_TRY(dev_alloc(h, &h->qkv, M * 3 * W));
-  // padded key rows of a frame are the next frame's rows: keep every bit pattern in this buffer finite
-  if (cudaMemset(h->qkv, 0, M * 3 * W * sizeof(bf16)) != cudaSuccess) { h->err = "cudaMemset failed"; return bail(ARP_ERR_CUDA); }
-  CREATE_TRY(dev_alloc(h, &h->attn, M * W));
-  CREATE_TRY(dev_alloc(h, &h->hid, M * std::max<size_t>(4 * W, h->kp)));
+  if (const char* e = getenv("ARP_PIPES")) h->n_pipes = atoi(e) == 2 ? 2 : 1;
   CREATE_TRY(dev_alloc(h, &h->rowtab, (size_t)h->tokens * W));
-  CREATE_TRY(dev_alloc(h, &h->feat_clip, B * cfg->embed_dim));
-  CREATE_TRY(dev_alloc(h, &h->logits_ws, B * HEAD_MAX_TEXT));
-  if (h->adapter) {
-    const size_t D = h->feat_dim;
-    CREATE_TRY(dev_alloc(h, &h->taps, B * cfg->layers * W));
-    CREATE_TRY(dev_alloc(h, &h->featf, B * D));
-    CREATE_TRY(dev_alloc(h, &h->featb, B * D));
-    CREATE_TRY(dev_alloc(h, &h->hid2, B * 2 * D));
-    CREATE_TRY(dev_alloc(h, &h->mlp, B * D));
+  for (int p = 0; p < h->n_pipes; ++p) {
+    ArpHandle::Work& w = h->ws[p];
+    CREATE_TRY(dev_alloc(h, &w.x, M * W));
+    CREATE_TRY(dev_alloc(h, &w.xn, M * W));
+    CREATE_TRY(dev_alloc(h, &w.qkv, M * 3 * W));
+    // padded key rows of a frame are the next frame's rows: keep every bit pattern in this buffer finite
+    if (cudaMemset(w.qkv, 0, M * 3 * W * sizeof(bf16)) != cudaSuccess) { h->err = "cudaMemset failed"; return bail(ARP_ERR_CUDA); }
+    CREATE_TRY(dev_alloc(h, &w.attn, M * W));
+    CREATE_TRY(dev_alloc(h, &w.hid, M * std::max<size_t>(4 * W, h->kp)));
+    if (h->adapter) {
+      const size_t D = h->feat_dim;
+      CREATE_TRY(dev_alloc(h, &w.taps, B * cfg->layers * W));
+      CREATE_TRY(dev_alloc(h, &w.featf, B * D));
+      CREATE_TRY(dev_alloc(h, &w.featb, B * D));
+      CREATE_TRY(dev_alloc(h, &w.hid2, B * 2 * D));
+      CREATE_TRY(dev_alloc(h, &w.mlp, B * D));
+    }
   }
   // weight buffers
   for (auto& kv : h->slots) {
@@ -529,7 +540,13 @@ extern "C" int arp_create(const ArpConfig* cfg, ArpHandle** out) {
   for (int i = 0; i < 2; ++i) {
     cudaEventCreateWithFlags(&h->ev_copied[i], cudaEventDisableTiming);
     cudaEventCreateWithFlags(&h->ev_consumed[i], cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&h->ev_join[i], cudaEventDisableTiming);
+    if (cudaStreamCreateWithFlags(&h->pipe_stream[i], cudaStreamNonBlocking) != cudaSuccess) {
+      h->err = "cudaStreamCreate failed";
+      return bail(ARP_ERR_CUDA);
+    }
   }
+  cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming);
 #undef CREATE_TRY
   *out = h;
   return ARP_OK;
@@ -845,35 +862,36 @@ static int launch_attention(ArpHandle* h, const bf16* qkv, bf16* out, int B, int
 // ------------------------------------------------------------------------------------------------
 // the encoder: n frames (n <= max_batch) -> residual stream x after the last block (+ CLS taps)
 // ------------------------------------------------------------------------------------------------
-static int encode_chunk(ArpHandle* h, const uint8_t* ob, int64_t n, int64_t stride, cudaStream_t st) {
+static int encode_chunk(ArpHandle* h, int pipe, const uint8_t* ob, int64_t n, int64_t stride, cudaStream_t st) {
   const ArpConfig& c = h->cfg;
+  ArpHandle::Work& ws = h->ws[pipe];
   const int W = c.width;
   const int64_t M = n * h->tokens;
   const int64_t Mcap = (int64_t)c.max_batch * h->tokens;
-  bf16* patches = h->hid;  // aliases the MLP hidden buffer (dead until layer 0's c_fc)
+  bf16* patches = ws.hid;  // aliases the MLP hidden buffer (dead until layer 0's c_fc)
   ARP_TRY(launch_decode(h, ob, n, stride, patches, DEC_OUT_PATCH_BF16, st));
   // patch embed (+ positional embedding, + class embedding on the all-zero row 0 of each frame)
-  ARP_TRY(launch_gemm(h, patches, Mcap, h->conv1, h->x, true, ACT_NONE, M, W, h->kp, W, nullptr, nullptr, 0,
+  ARP_TRY(launch_gemm(h, patches, Mcap, h->conv1, ws.x, true, ACT_NONE, M, W, h->kp, W, nullptr, nullptr, 0,
                       h->rowtab, h->tokens, st));
   {
     ProfScope prof(h, PC_LAYERNORM, 0.0, (double)M * 768 * 8, st);
-    layernorm_f32_inplace_kernel<768><<<(unsigned)((M + 7) / 8), 256, 0, st>>>(h->x, h->ln_pre_g, h->ln_pre_b, (int)M, 1e-5f);
+    layernorm_f32_inplace_kernel<768><<<(unsigned)((M + 7) / 8), 256, 0, st>>>(ws.x, h->ln_pre_g, h->ln_pre_b, (int)M, 1e-5f);
     h->launches++;
   }
   for (int l = 0; l < c.layers; ++l) {
     const LayerW& L = h->layers[l];
-    ARP_TRY(launch_ln_bf16(h, h->x, L.ln1_g, L.ln1_b, h->xn, M, st));
-    ARP_TRY(launch_gemm(h, h->xn, Mcap, L.w_qkv, h->qkv, false, ACT_NONE, M, 3 * W, W, 3 * W, L.b_qkv, nullptr, 0,
+    ARP_TRY(launch_ln_bf16(h, ws.x, L.ln1_g, L.ln1_b, ws.xn, M, st));
+    ARP_TRY(launch_gemm(h, ws.xn, Mcap, L.w_qkv, ws.qkv, false, ACT_NONE, M, 3 * W, W, 3 * W, L.b_qkv, nullptr, 0,
                         nullptr, 0, st));
-    ARP_TRY(launch_attention(h, h->qkv, h->attn, (int)n, h->tokens, st, Mcap));
-    ARP_TRY(launch_gemm(h, h->attn, Mcap, L.w_out, h->x, true, ACT_NONE, M, W, W, W, L.b_out, h->x, W, nullptr, 0, st));
-    ARP_TRY(launch_ln_bf16(h, h->x, L.ln2_g, L.ln2_b, h->xn, M, st));
-    ARP_TRY(launch_gemm(h, h->xn, Mcap, L.w_fc, h->hid, false, ACT_QUICKGELU, M, 4 * W, W, 4 * W, L.b_fc, nullptr, 0,
+    ARP_TRY(launch_attention(h, ws.qkv, ws.attn, (int)n, h->tokens, st, Mcap));
+    ARP_TRY(launch_gemm(h, ws.attn, Mcap, L.w_out, ws.x, true, ACT_NONE, M, W, W, W, L.b_out, ws.x, W, nullptr, 0, st));
+    ARP_TRY(launch_ln_bf16(h, ws.x, L.ln2_g, L.ln2_b, ws.xn, M, st));
+    ARP_TRY(launch_gemm(h, ws.xn, Mcap, L.w_fc, ws.hid, false, ACT_QUICKGELU, M, 4 * W, W, 4 * W, L.b_fc, nullptr, 0,
                         nullptr, 0, st));
-    ARP_TRY(launch_gemm(h, h->hid, Mcap, L.w_proj, h->x, true, ACT_NONE, M, W, 4 * W, W, L.b_proj, h->x, W, nullptr,
+    ARP_TRY(launch_gemm(h, ws.hid, Mcap, L.w_proj, ws.x, true, ACT_NONE, M, W, 4 * W, W, L.b_proj, ws.x, W, nullptr,
                         0, st));
     if (h->adapter) {
-      gather_cls_bf16_kernel<768><<<(unsigned)((n + 7) / 8), 256, 0, st>>>(h->x, h->taps, (int)n, h->tokens,
+      gather_cls_bf16_kernel<768><<<(unsigned)((n + 7) / 8), 256, 0, st>>>(ws.x, ws.taps, (int)n, h->tokens,
                                                                          c.layers * W, l * W);
       h->launches++;
     }
@@ -883,38 +901,39 @@ static int encode_chunk(ArpHandle* h, const uint8_t* ob, int64_t n, int64_t stri
 }
 
 // heads. reward_out [n] / logits_out [n, n_text] / feat_out [n, feat_dim] may each be null.
-static int head_chunk(ArpHandle* h, int64_t n, float* reward_out, float* logits_out, float* feat_out,
+static int head_chunk(ArpHandle* h, int pipe, int64_t n, float* reward_out, float* logits_out, float* feat_out,
                       cudaStream_t st) {
   const ArpConfig& c = h->cfg;
+  ArpHandle::Work& ws = h->ws[pipe];
   const bool need_text = reward_out || logits_out;
   if (need_text && !h->goal && !h->text) return fail(h, ARP_ERR_STATE, "arp_set_text has not been called");
   if (!h->adapter) {
     ProfScope prof(h, PC_HEAD, 2.0 * (double)n * 768 * 512, (double)n * 768 * 4 + 768.0 * 512 * 4, st);
     clip_head_kernel<768, 512><<<(unsigned)n, 256, 0, st>>>(
-        h->x, h->tokens, h->ln_post_g, h->ln_post_b, 1e-5f, h->proj, (need_text && !h->goal) ? h->text : nullptr,
+        ws.x, h->tokens, h->ln_post_g, h->ln_post_b, 1e-5f, h->proj, (need_text && !h->goal) ? h->text : nullptr,
         h->n_text, h->logit_scale, c.reduce, feat_out, c.embed_dim, 0, logits_out, h->goal ? nullptr : reward_out);
     h->launches++;
   } else {
     const int D = h->feat_dim, Dmid = c.layers * c.embed_dim, Din = c.layers * c.width;
     const int64_t B = c.max_batch;
     // final CLIP feature -> last 512 columns of feat (un-normalised, clip_multiscale_adapter.py:136,145)
-    clip_head_kernel<768, 512><<<(unsigned)n, 256, 0, st>>>(h->x, h->tokens, h->ln_post_g, h->ln_post_b, 1e-5f,
-                                                            h->proj, nullptr, 0, 0.f, 0, h->featf, D, Dmid, nullptr,
+    clip_head_kernel<768, 512><<<(unsigned)n, 256, 0, st>>>(ws.x, h->tokens, h->ln_post_g, h->ln_post_b, 1e-5f,
+                                                            h->proj, nullptr, 0, 0.f, 0, ws.featf, D, Dmid, nullptr,
                                                             nullptr);
     h->launches++;
     // image_intermediate_linear (no bias) over the 12 CLS taps -> first 6144 columns (:143-144)
-    ARP_TRY(launch_gemm(h, h->taps, B, h->inter_w, h->featf, true, ACT_NONE, n, Dmid, Din, D, nullptr, nullptr, 0,
+    ARP_TRY(launch_gemm(h, ws.taps, B, h->inter_w, ws.featf, true, ACT_NONE, n, Dmid, Din, D, nullptr, nullptr, 0,
                         nullptr, 0, st));
-    f32_to_bf16_kernel<<<kNumSMs * 4, 256, 0, st>>>(h->featf, h->featb, (size_t)n * D);
+    f32_to_bf16_kernel<<<kNumSMs * 4, 256, 0, st>>>(ws.featf, ws.featb, (size_t)n * D);
     h->launches++;
     // AdapterMLP: Linear -> Identity -> ReLU -> Linear (finetune_module/layers.py:42-49)
-    ARP_TRY(launch_gemm(h, h->featb, B, h->fc1_w, h->hid2, false, ACT_RELU, n, 2 * D, D, 2 * D, h->fc1_b, nullptr, 0,
+    ARP_TRY(launch_gemm(h, ws.featb, B, h->fc1_w, ws.hid2, false, ACT_RELU, n, 2 * D, D, 2 * D, h->fc1_b, nullptr, 0,
                         nullptr, 0, st));
-    ARP_TRY(launch_gemm(h, h->hid2, B, h->fc2_w, h->mlp, true, ACT_NONE, n, D, 2 * D, D, h->fc2_b, nullptr, 0, nullptr,
+    ARP_TRY(launch_gemm(h, ws.hid2, B, h->fc2_w, ws.mlp, true, ACT_NONE, n, D, 2 * D, D, h->fc2_b, nullptr, 0, nullptr,
                         0, st));
     const bool ens = c.head == ARP_HEAD_ADAPTER_ENSEMBLE;
     adapter_head_kernel<13, 512><<<(unsigned)n, 13 * 32, 0, st>>>(
-        h->featf, h->mlp, h->res_sigmoid, (need_text && !h->goal) ? h->text : nullptr,
+        ws.featf, ws.mlp, h->res_sigmoid, (need_text && !h->goal) ? h->text : nullptr,
         (need_text && !h->goal) ? h->n_text : 0, h->logit_scale, ens ? 1 : 0, c.reduce, logits_out,
         h->goal ? nullptr : reward_out, feat_out);
     h->launches++;
@@ -974,6 +993,19 @@ static int carve_label_tmp(ArpHandle* h, int64_t T, LabelTmp* t) {
   return ARP_OK;
 }
 
+// ---- chunk pipelining over the internal streams -------------------------------------------------------
+static int active_pipes(const ArpHandle* h, int64_t nchunks) { return (h->profiling || nchunks < 2) ? 1 : h->n_pipes; }
+static void pipes_fork(ArpHandle* h, cudaStream_t st, int np) {   // pipes start after everything queued on st
+  cudaEventRecord(h->ev_fork, st);
+  for (int p = 0; p < np; ++p) cudaStreamWaitEvent(h->pipe_stream[p], h->ev_fork, 0);
+}
+static void pipes_join(ArpHandle* h, cudaStream_t st, int np) {   // st continues after both pipes drain
+  for (int p = 0; p < np; ++p) {
+    cudaEventRecord(h->ev_join[p], h->pipe_stream[p]);
+    cudaStreamWaitEvent(st, h->ev_join[p], 0);
+  }
+}
+
 static int check_ready(ArpHandle* h, const void* ob, int64_t T, int64_t stride, cudaStream_t st) {
   if (!h) return ARP_ERR_INVALID;
   if (T < 0 || (T > 0 && !ob)) return fail(h, ARP_ERR_INVALID, "bad frame buffer / T");
@@ -991,12 +1023,18 @@ extern "C" int arp_compute_reward(ArpHandle* h, const uint8_t* ob_dev, int64_t T
   ARP_TRY(check_ready(h, ob_dev, T, row_stride_bytes, st));
   if (h->goal) return fail(h, ARP_ERR_INVALID, "goal-conditioned heads need episode boundaries: use arp_label");
   const int64_t B = h->cfg.max_batch;
-  for (int64_t t0 = 0; t0 < T; t0 += B) {
+  const int np = active_pipes(h, (T + B - 1) / B);
+  if (np > 1) pipes_fork(h, st, np);
+  int64_t ci = 0;
+  for (int64_t t0 = 0; t0 < T; t0 += B, ++ci) {
     const int64_t n = std::min(B, T - t0);
-    ARP_TRY(encode_chunk(h, ob_dev + t0 * row_stride_bytes, n, row_stride_bytes, st));
-    ARP_TRY(head_chunk(h, n, reward_dev ? reward_dev + t0 : nullptr,
-                       logits_dev ? logits_dev + t0 * h->n_text : nullptr, nullptr, st));
+    const int p = np > 1 ? (int)(ci % np) : 0;
+    cudaStream_t ps = np > 1 ? h->pipe_stream[p] : st;
+    ARP_TRY(encode_chunk(h, p, ob_dev + t0 * row_stride_bytes, n, row_stride_bytes, ps));
+    ARP_TRY(head_chunk(h, p, n, reward_dev ? reward_dev + t0 : nullptr,
+                       logits_dev ? logits_dev + t0 * h->n_text : nullptr, nullptr, ps));
   }
+  if (np > 1) pipes_join(h, st, np);
   return ARP_OK;
 }
 
@@ -1006,11 +1044,17 @@ extern "C" int arp_encode_image(ArpHandle* h, const uint8_t* ob_dev, int64_t T, 
   ARP_TRY(check_ready(h, ob_dev, T, row_stride_bytes, st));
   if (!feat_dev) return fail(h, ARP_ERR_INVALID, "null output");
   const int64_t B = h->cfg.max_batch;
-  for (int64_t t0 = 0; t0 < T; t0 += B) {
+  const int np = active_pipes(h, (T + B - 1) / B);
+  if (np > 1) pipes_fork(h, st, np);
+  int64_t ci = 0;
+  for (int64_t t0 = 0; t0 < T; t0 += B, ++ci) {
     const int64_t n = std::min(B, T - t0);
-    ARP_TRY(encode_chunk(h, ob_dev + t0 * row_stride_bytes, n, row_stride_bytes, st));
-    ARP_TRY(head_chunk(h, n, nullptr, nullptr, feat_dev + t0 * h->feat_dim, st));
+    const int p = np > 1 ? (int)(ci % np) : 0;
+    cudaStream_t ps = np > 1 ? h->pipe_stream[p] : st;
+    ARP_TRY(encode_chunk(h, p, ob_dev + t0 * row_stride_bytes, n, row_stride_bytes, ps));
+    ARP_TRY(head_chunk(h, p, n, nullptr, nullptr, feat_dev + t0 * h->feat_dim, ps));
   }
+  if (np > 1) pipes_join(h, st, np);
   if (h->adapter && T > 0) {
     l2_normalize_rows_kernel<<<(unsigned)((T + 7) / 8), 256, 0, st>>>(feat_dev, h->feat_dim, T);
     h->launches++;
@@ -1081,12 +1125,18 @@ static int label_device(ArpHandle* h, const uint8_t* ob_dev, int64_t T, int64_t 
   float* r = reward ? reward : tmp.r;
   float* g = rtg ? rtg : tmp.g;
   const int64_t B = h->cfg.max_batch;
-  for (int64_t t0 = 0; t0 < T; t0 += B) {
+  const int np = active_pipes(h, (T + B - 1) / B);
+  if (np > 1) pipes_fork(h, st, np);
+  int64_t ci = 0;
+  for (int64_t t0 = 0; t0 < T; t0 += B, ++ci) {
     const int64_t n = std::min(B, T - t0);
-    ARP_TRY(encode_chunk(h, ob_dev + t0 * stride, n, stride, st));
-    if (!h->goal) ARP_TRY(head_chunk(h, n, r + t0, nullptr, nullptr, st));
-    else ARP_TRY(head_chunk(h, n, nullptr, nullptr, tmp.feats + t0 * h->feat_dim, st));
+    const int p = np > 1 ? (int)(ci % np) : 0;
+    cudaStream_t ps = np > 1 ? h->pipe_stream[p] : st;
+    ARP_TRY(encode_chunk(h, p, ob_dev + t0 * stride, n, stride, ps));
+    if (!h->goal) ARP_TRY(head_chunk(h, p, n, r + t0, nullptr, nullptr, ps));
+    else ARP_TRY(head_chunk(h, p, n, nullptr, nullptr, tmp.feats + t0 * h->feat_dim, ps));
   }
+  if (np > 1) pipes_join(h, st, np);
   if (h->goal) ARP_TRY(goal_rewards(h, tmp, T, ep_off, n_eps, r, st));
   return scan_launch(h, r, T, ep_off, n_eps, F, 1.0f, g, rs, gs, st);
 }
@@ -1125,9 +1175,13 @@ extern "C" int arp_label_host(ArpHandle* h, const uint8_t* ob_host, int64_t T, i
   ARP_CUDA(h, cudaMemcpyAsync(d_off, ep_offsets_host, (size_t)(n_eps + 1) * 8, cudaMemcpyHostToDevice, st));
   // double-buffered: chunk i+1's frames (only the scored image of each row) cross PCIe while chunk i is encoded
   const int64_t nchunks = (T + B - 1) / B;
+  const int np = active_pipes(h, nchunks);
+  if (np > 1) pipes_fork(h, st, np);
   int rc = ARP_OK;
   for (int64_t ci = 0; ci < nchunks && rc == ARP_OK; ++ci) {
     const int buf = (int)(ci & 1);
+    const int p = np > 1 ? buf : 0;
+    cudaStream_t ps = np > 1 ? h->pipe_stream[p] : st;
     const int64_t t0 = ci * B, n = std::min(B, T - t0);
     if (ci >= 2) cudaStreamWaitEvent(h->copy_stream, h->ev_consumed[buf], 0);
     cudaError_t e = cudaMemcpy2DAsync(h->stage_dev[buf], frame_bytes, ob_host + t0 * row_stride_bytes,
@@ -1135,12 +1189,13 @@ extern "C" int arp_label_host(ArpHandle* h, const uint8_t* ob_host, int64_t T, i
                                       h->copy_stream);
     if (e != cudaSuccess) { rc = fail(h, ARP_ERR_CUDA, "H2D frames failed: %s", cudaGetErrorString(e)); break; }
     cudaEventRecord(h->ev_copied[buf], h->copy_stream);
-    cudaStreamWaitEvent(st, h->ev_copied[buf], 0);
-    if ((rc = encode_chunk(h, h->stage_dev[buf], n, (int64_t)frame_bytes, st)) != ARP_OK) break;
-    if (!h->goal) rc = head_chunk(h, n, d_r + t0, nullptr, nullptr, st);
-    else rc = head_chunk(h, n, nullptr, nullptr, tmp.feats + t0 * h->feat_dim, st);
-    cudaEventRecord(h->ev_consumed[buf], st);
+    cudaStreamWaitEvent(ps, h->ev_copied[buf], 0);
+    if ((rc = encode_chunk(h, p, h->stage_dev[buf], n, (int64_t)frame_bytes, ps)) != ARP_OK) break;
+    if (!h->goal) rc = head_chunk(h, p, n, d_r + t0, nullptr, nullptr, ps);
+    else rc = head_chunk(h, p, n, nullptr, nullptr, tmp.feats + t0 * h->feat_dim, ps);
+    cudaEventRecord(h->ev_consumed[buf], ps);
   }
+  if (np > 1) pipes_join(h, st, np);
   if (rc == ARP_OK && h->goal) rc = goal_rewards(h, tmp, T, d_off, n_eps, d_r, st);
   if (rc == ARP_OK) rc = scan_launch(h, d_r, T, d_off, n_eps, F, 1.0f, d_g, d_rs, d_gs, st);
   if (rc == ARP_OK) {
@@ -1152,6 +1207,7 @@ extern "C" int arp_label_host(ArpHandle* h, const uint8_t* ob_host, int64_t T, i
     if (e == cudaSuccess) e = cudaStreamSynchronize(st);
     if (e != cudaSuccess) rc = fail(h, ARP_ERR_CUDA, "label_host tail failed: %s", cudaGetErrorString(e));
   }
+  if (rc != ARP_OK) cudaDeviceSynchronize();   // error path: drain the pipes before the caller frees anything
   cudaStreamSynchronize(h->copy_stream);
   cudaStreamSynchronize(st);
   return rc;
