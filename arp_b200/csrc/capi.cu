@@ -74,9 +74,15 @@ struct LayerW {
   float *ln1_g = nullptr, *ln1_b = nullptr, *ln2_g = nullptr, *ln2_b = nullptr;
   bf16 *w_qkv = nullptr, *w_out = nullptr, *w_fc = nullptr, *w_proj = nullptr;
   float *b_qkv = nullptr, *b_out = nullptr, *b_fc = nullptr, *b_proj = nullptr;
+  // LayerNorm fold: fp32 originals of the two LN-consuming weights, gamma-folded bf16 operands, and the
+  // per-output-column vectors of the algebraic LayerNorm (gemm2 MODE 3)
+  float *w_qkv_f32 = nullptr, *w_fc_f32 = nullptr;
+  bf16 *w_qkv_fold = nullptr, *w_fc_fold = nullptr;
+  float *s_qkv = nullptr, *c_qkv = nullptr, *s_fc = nullptr, *c_fc = nullptr;
 };
 
 struct WeightSlot {
+  void** dst_f32 = nullptr;  // optional extra fp32 copy (weights that get LayerNorm-folded at finalize time)
   void** dst;      // device buffer to fill
   int64_t numel;
   bool as_bf16;    // GEMM operand (bf16) or fp32 parameter
@@ -96,6 +102,11 @@ struct ArpHandle {
   ArpConfig cfg;
   std::string err;
   int64_t launches = 0;
+  // LayerNorm applied inside the GEMM epilogues (ARP_LN_FOLD): 0 = standalone LN kernels (default), 1 = ln_1 folded
+  // (c_proj emits bf16 x + moments, QKV applies them), 2 = ln_1 and ln_2 folded. Measured on B200 (tools/fold_check.py):
+  // numerically equivalent, but the register-path residual epilogue (gemm2 MODE 2) is latency-bound on the x loads
+  // (out_proj 137 -> 236 us), which cancels the 2 x 63 us of LN kernels it removes; kept off until MODE 2 stages x by TMA.
+  int ln_fold = 0;
   int attn_impl = 2;  // 1 = mma.sync kernel, 2 = tcgen05 kernel (ARP_ATTN_IMPL overrides)
   int gemm_impl = 3;  // 1 = v1 (register stores), 2 = v2 single-CTA, 3 = v2 CTA pairs (ARP_GEMM_IMPL overrides)
   int tokens = 0, grid = 0, kp = 0;  // 197, 14, 768
@@ -132,6 +143,7 @@ struct ArpHandle {
     bf16 *xn = nullptr, *qkv = nullptr, *attn = nullptr, *hid = nullptr;
     bf16 *taps = nullptr, *featb = nullptr, *hid2 = nullptr;
     float *featf = nullptr, *mlp = nullptr;
+    float* stats = nullptr;   // [M, 2*W/128] partial LayerNorm moments (LN fold)
   } ws[2];
   int n_pipes = 1;                       // ARP_PIPES=2: two chunks in flight (measured: no gain on B200 — a resident
                                          // persistent GEMM CTA leaves no room the scheduler will give to another kernel)
@@ -311,7 +323,9 @@ static int build_decode_tables(ArpHandle* h) {
 // weights
 // ------------------------------------------------------------------------------------------------
 static void add_slot(ArpHandle* h, const std::string& name, void** dst, int64_t numel, bool as_bf16, bool required) {
-  h->slots[name] = WeightSlot{dst, numel, as_bf16, required, false};
+  WeightSlot s;
+  s.dst = dst; s.numel = numel; s.as_bf16 = as_bf16; s.required = required; s.set = false;
+  h->slots[name] = s;
 }
 
 static void register_slots(ArpHandle* h) {
@@ -341,6 +355,8 @@ static void register_slots(ArpHandle* h) {
     add_slot(h, p + "mlp.c_fc.bias", (void**)&L.b_fc, 4 * W, false, true);
     add_slot(h, p + "mlp.c_proj.weight", (void**)&L.w_proj, (int64_t)4 * W * W, true, true);
     add_slot(h, p + "mlp.c_proj.bias", (void**)&L.b_proj, W, false, true);
+    h->slots[p + "attn.in_proj_weight"].dst_f32 = (void**)&L.w_qkv_f32;
+    h->slots[p + "mlp.c_fc.weight"].dst_f32 = (void**)&L.w_fc_f32;
   }
   if (h->adapter) {
     const int64_t D = h->feat_dim;                       // 13 * 512
@@ -470,6 +486,8 @@ extern "C" int arp_create(const ArpConfig* cfg, ArpHandle** out) {
   if (const char* e = getenv("ARP_GEMM_IMPL")) h->gemm_impl = atoi(e);
   if (h->gemm_impl < 1 || h->gemm_impl > 3) h->gemm_impl = 3;
   if (const char* e = getenv("ARP_ATTN_IMPL")) h->attn_impl = atoi(e) == 1 ? 1 : 2;
+  if (const char* e = getenv("ARP_LN_FOLD")) h->ln_fold = std::max(0, std::min(2, atoi(e)));
+  if (h->gemm_impl < 2) h->ln_fold = 0;   // the fold lives in the v2 epilogue
   h->grid = DEC_OUT / cfg->patch;
   h->tokens = h->grid * h->grid + 1;
   h->kp = 3 * cfg->patch * cfg->patch;
@@ -496,6 +514,7 @@ extern "C" int arp_create(const ArpConfig* cfg, ArpHandle** out) {
     if (cudaMemset(w.qkv, 0, M * 3 * W * sizeof(bf16)) != cudaSuccess) { h->err = "cudaMemset failed"; return bail(ARP_ERR_CUDA); }
     CREATE_TRY(dev_alloc(h, &w.attn, M * W));
     CREATE_TRY(dev_alloc(h, &w.hid, M * std::max<size_t>(4 * W, h->kp)));
+    if (h->ln_fold) CREATE_TRY(dev_alloc(h, &w.stats, M * 2 * (W / 128)));
     if (h->adapter) {
       const size_t D = h->feat_dim;
       CREATE_TRY(dev_alloc(h, &w.taps, B * cfg->layers * W));
@@ -512,6 +531,19 @@ extern "C" int arp_create(const ArpConfig* cfg, ArpHandle** out) {
     if (cudaMalloc(&p, s.numel * (s.as_bf16 ? 2 : 4) + 256) != cudaSuccess) { h->err = "cudaMalloc(weights) failed"; return bail(ARP_ERR_CUDA); }
     h->allocs.push_back(p);
     *s.dst = p;
+    if (s.dst_f32 && h->ln_fold) {
+      float* q = nullptr;
+      if (dev_alloc(h, &q, (size_t)s.numel) != ARP_OK) return bail(ARP_ERR_CUDA);
+      *s.dst_f32 = q;
+    }
+  }
+  if (h->ln_fold) {
+    for (auto& L : h->layers) {
+      if (dev_alloc(h, &L.w_qkv_fold, (size_t)3 * W * W) != ARP_OK || dev_alloc(h, &L.w_fc_fold, (size_t)4 * W * W) != ARP_OK ||
+          dev_alloc(h, &L.s_qkv, (size_t)3 * W) != ARP_OK || dev_alloc(h, &L.c_qkv, (size_t)3 * W) != ARP_OK ||
+          dev_alloc(h, &L.s_fc, (size_t)4 * W) != ARP_OK || dev_alloc(h, &L.c_fc, (size_t)4 * W) != ARP_OK)
+        return bail(ARP_ERR_CUDA);
+    }
   }
   // opt-in shared memory
   CREATE_TRY(set_smem(h, gemm_bf16_tcgen05_kernel<bf16, ACT_NONE>, GEMM_SMEM_BYTES));
@@ -523,9 +555,10 @@ extern "C" int arp_create(const ArpConfig* cfg, ArpHandle** out) {
 #define G2_ATTR(T, A, R)                                                                              \
   CREATE_TRY(set_smem(h, gemm2_bf16_tcgen05_kernel<T, A, 1, R>, G2Cfg<1>::SMEM_BYTES));               \
   CREATE_TRY(set_smem(h, gemm2_bf16_tcgen05_kernel<T, A, 2, R>, G2Cfg<2>::SMEM_BYTES));
-  G2_ATTR(bf16, ACT_NONE, false) G2_ATTR(bf16, ACT_QUICKGELU, false) G2_ATTR(bf16, ACT_RELU, false)
-  G2_ATTR(float, ACT_NONE, false) G2_ATTR(float, ACT_QUICKGELU, false) G2_ATTR(float, ACT_RELU, false)
-  G2_ATTR(float, ACT_NONE, true)
+  G2_ATTR(bf16, ACT_NONE, G2_STORE) G2_ATTR(bf16, ACT_QUICKGELU, G2_STORE) G2_ATTR(bf16, ACT_RELU, G2_STORE)
+  G2_ATTR(float, ACT_NONE, G2_STORE) G2_ATTR(float, ACT_QUICKGELU, G2_STORE) G2_ATTR(float, ACT_RELU, G2_STORE)
+  G2_ATTR(float, ACT_NONE, G2_REDUCE) G2_ATTR(float, ACT_NONE, G2_RESID_LN)
+  G2_ATTR(bf16, ACT_NONE, G2_LNFOLD) G2_ATTR(bf16, ACT_QUICKGELU, G2_LNFOLD)
 #undef G2_ATTR
   CREATE_TRY(set_smem(h, attention_tc_kernel<197>, AtcCfg<197>::SMEM_BYTES));
   CREATE_TRY(set_smem(h, attention_tc_kernel<50>, AtcCfg<50>::SMEM_BYTES));
@@ -595,6 +628,12 @@ extern "C" int arp_set_weight(ArpHandle* h, const char* name, const void* data, 
     else if (dtype == ARP_BF16) launch_convert<bf16, float>(h, data, dst, n, st);
     else return fail(h, ARP_ERR_INVALID, "bad dtype %d", dtype);
   }
+  if (s.dst_f32 && *s.dst_f32) {
+    void* d32 = *s.dst_f32;
+    if (dtype == ARP_F32) ARP_CUDA(h, cudaMemcpyAsync(d32, data, n * 4, cudaMemcpyDeviceToDevice, st));
+    else if (dtype == ARP_F16) launch_convert<__half, float>(h, data, d32, n, st);
+    else launch_convert<bf16, float>(h, data, d32, n, st);
+  }
   ARP_CUDA(h, cudaGetLastError());
   s.set = true;
   h->finalized = false;
@@ -627,6 +666,14 @@ static int finalize_weights(ArpHandle* h, cudaStream_t st) {
   const int n = h->tokens * h->cfg.width;
   build_rowtab_kernel<<<(n + 255) / 256, 256, 0, st>>>(h->pos_emb, h->class_emb, h->rowtab, h->tokens, h->cfg.width);
   h->launches++;
+  if (h->ln_fold) {
+    const int W = h->cfg.width;
+    for (auto& L : h->layers) {
+      fold_ln_weights_kernel<<<(3 * W + 7) / 8, 256, 0, st>>>(L.w_qkv_f32, L.ln1_g, L.ln1_b, L.b_qkv, L.w_qkv_fold, L.s_qkv, L.c_qkv, 3 * W, W);
+      fold_ln_weights_kernel<<<(4 * W + 7) / 8, 256, 0, st>>>(L.w_fc_f32, L.ln2_g, L.ln2_b, L.b_fc, L.w_fc_fold, L.s_fc, L.c_fc, 4 * W, W);
+      h->launches += 2;
+    }
+  }
   if (h->adapter) {
     float w = 0.f;
     ARP_CUDA(h, cudaMemcpyAsync(&w, h->res_w, 4, cudaMemcpyDeviceToHost, st));
@@ -709,7 +756,13 @@ static int launch_gemm2(ArpHandle* h, const bf16* a, int64_t a_rows_alloc, const
   ARP_TRY(get_tmap(h, w, (uint64_t)g.N, (uint64_t)g.K, (uint64_t)g.K, GEMM_BN / cg, &tb));
   ARP_TRY(get_tmap(h, g.out, (uint64_t)g.M, (uint64_t)g.N, (uint64_t)g.ldo, 32, &to, out_f32 ? 32 : 64, out_f32 ? 4 : 2));
   bool reduce = false;
-  if (g.resid) {
+  const bool resid_ln = g.stats_out != nullptr;   // MODE 2: residual + bf16 copy + LN moments (reads the residual itself)
+  const bool lnfold = g.stats_in != nullptr;      // MODE 3: LayerNorm applied algebraically in the epilogue
+  if (resid_ln) {
+    if (!out_f32 || act != ACT_NONE || !g.resid || !g.xb || g.N % 256) return fail(h, ARP_ERR_INVALID, "bad residual+LN-moments GEMM");
+  } else if (lnfold) {
+    if (out_f32 || act == ACT_RELU || !g.svec || !g.cvec || g.K != 128 * g.stats_nh) return fail(h, ARP_ERR_INVALID, "bad LN-folded GEMM");
+  } else if (g.resid) {
     if (!out_f32 || act != ACT_NONE) return fail(h, ARP_ERR_INVALID, "residual epilogue needs fp32 output and no activation");
     if (g.resid != g.out)  // out-of-place residual (test hook only): seed the output, then accumulate into it
       ARP_CUDA(h, cudaMemcpy2DAsync(g.out, (size_t)g.ldo * 4, g.resid, (size_t)g.ldr * 4, (size_t)g.N * 4, (size_t)g.M,
@@ -721,20 +774,25 @@ static int launch_gemm2(ArpHandle* h, const bf16* a, int64_t a_rows_alloc, const
   const int grid = std::min(tiles * cg, kNumSMs / cg * cg);
   const int smem = cg == 2 ? G2Cfg<2>::SMEM_BYTES : G2Cfg<1>::SMEM_BYTES;
   ProfScope prof(h, PC_GEMM, 2.0 * (double)g.M * g.N * g.K,
-                 (double)g.M * g.K * 2 + (double)g.N * g.K * 2 + (double)g.M * g.N * (out_f32 ? 4 : 2) * (reduce ? 2 : 1), st);
+                 (double)g.M * g.K * 2 + (double)g.N * g.K * 2 + (double)g.M * g.N * (out_f32 ? 4 : 2) * (reduce || resid_ln ? 2 : 1) +
+                     (resid_ln ? (double)g.M * g.N * 2 : 0.0), st);
   cudaError_t e;
 #define G2_LAUNCH(T, A, R)                                                                                         \
   e = cg == 2 ? launch_clustered(gemm2_bf16_tcgen05_kernel<T, A, 2, R>, grid, 2, smem, st, *ta, *tb, *to, g)       \
               : launch_clustered(gemm2_bf16_tcgen05_kernel<T, A, 1, R>, grid, 1, smem, st, *ta, *tb, *to, g)
-  if (reduce) G2_LAUNCH(float, ACT_NONE, true);
+  if (resid_ln) G2_LAUNCH(float, ACT_NONE, G2_RESID_LN);
+  else if (lnfold) {
+    if (act == ACT_NONE) G2_LAUNCH(bf16, ACT_NONE, G2_LNFOLD);
+    else G2_LAUNCH(bf16, ACT_QUICKGELU, G2_LNFOLD);
+  } else if (reduce) G2_LAUNCH(float, ACT_NONE, G2_REDUCE);
   else if (out_f32) {
-    if (act == ACT_NONE) G2_LAUNCH(float, ACT_NONE, false);
-    else if (act == ACT_QUICKGELU) G2_LAUNCH(float, ACT_QUICKGELU, false);
-    else G2_LAUNCH(float, ACT_RELU, false);
+    if (act == ACT_NONE) G2_LAUNCH(float, ACT_NONE, G2_STORE);
+    else if (act == ACT_QUICKGELU) G2_LAUNCH(float, ACT_QUICKGELU, G2_STORE);
+    else G2_LAUNCH(float, ACT_RELU, G2_STORE);
   } else {
-    if (act == ACT_NONE) G2_LAUNCH(bf16, ACT_NONE, false);
-    else if (act == ACT_QUICKGELU) G2_LAUNCH(bf16, ACT_QUICKGELU, false);
-    else G2_LAUNCH(bf16, ACT_RELU, false);
+    if (act == ACT_NONE) G2_LAUNCH(bf16, ACT_NONE, G2_STORE);
+    else if (act == ACT_QUICKGELU) G2_LAUNCH(bf16, ACT_QUICKGELU, G2_STORE);
+    else G2_LAUNCH(bf16, ACT_RELU, G2_STORE);
   }
 #undef G2_LAUNCH
   h->launches++;
@@ -744,9 +802,15 @@ static int launch_gemm2(ArpHandle* h, const bf16* a, int64_t a_rows_alloc, const
 
 // a_rows_alloc: rows addressable behind `a` (>= M); the descriptor covers them so that reading a partly
 // filled workspace never depends on M (rows are independent; rows >= M are computed and dropped).
+// LayerNorm-fold extras of one GEMM launch (gemm2 MODE 2 / MODE 3, see GemmArgs)
+struct LnFoldArgs {
+  bf16* xb = nullptr; float* stats_out = nullptr;                                         // MODE 2
+  const float* stats_in = nullptr; const float* svec = nullptr; const float* cvec = nullptr;  // MODE 3
+};
+
 static int launch_gemm(ArpHandle* h, const bf16* a, int64_t a_rows_alloc, const bf16* w, void* out, bool out_f32,
                        int act, int64_t M, int N, int K, int ldo, const float* bias, const float* resid, int ldr,
-                       const float* rowtab, int period, cudaStream_t st) {
+                       const float* rowtab, int period, cudaStream_t st, const LnFoldArgs* fold = nullptr) {
   if (M <= 0) return ARP_OK;
   if (N % GEMM_BN || K % GEMM_BK) return fail(h, ARP_ERR_INVALID, "GEMM needs N %% 256 == 0 and K %% 64 == 0 (N=%d K=%d)", N, K);
   if (M > 0x7fffffff / 2) return fail(h, ARP_ERR_INVALID, "GEMM M too large");
@@ -754,8 +818,15 @@ static int launch_gemm(ArpHandle* h, const bf16* a, int64_t a_rows_alloc, const 
   ARP_TRY(get_tmap(h, a, (uint64_t)a_rows_alloc, (uint64_t)K, (uint64_t)K, GEMM_BM, &ta));
   ARP_TRY(get_tmap(h, w, (uint64_t)N, (uint64_t)K, (uint64_t)K, GEMM_BN, &tb));
   GemmArgs g;
+  memset(&g, 0, sizeof(g));
   g.M = (int)M; g.N = N; g.K = K; g.out = out; g.ldo = ldo; g.bias = bias; g.resid = resid; g.ldr = ldr;
   g.rowtab = rowtab; g.period = period > 0 ? period : 1;
+  g.eps = 1e-5f;
+  if (fold) {
+    if (h->gemm_impl < 2) return fail(h, ARP_ERR_INVALID, "the LayerNorm fold needs the v2 GEMM");
+    g.xb = fold->xb; g.stats_out = fold->stats_out; g.stats_in = fold->stats_in; g.stats_nh = K / 128;
+    g.svec = fold->svec; g.cvec = fold->cvec;
+  }
   if (h->gemm_impl >= 2) return launch_gemm2(h, a, a_rows_alloc, w, g, out_f32, act, st);
   const int tiles = (int)((M + GEMM_BM - 1) / GEMM_BM) * (N / GEMM_BN);
   const int grid = std::min(tiles, kNumSMs);
@@ -873,6 +944,48 @@ static int encode_chunk(ArpHandle* h, int pipe, const uint8_t* ob, int64_t n, in
   // patch embed (+ positional embedding, + class embedding on the all-zero row 0 of each frame)
   ARP_TRY(launch_gemm(h, patches, Mcap, h->conv1, ws.x, true, ACT_NONE, M, W, h->kp, W, nullptr, nullptr, 0,
                       h->rowtab, h->tokens, st));
+  if (h->ln_fold) {
+    // LayerNorm never runs as its own kernel inside the blocks: the residual GEMMs (out_proj, c_proj) emit a bf16
+    // copy of x and per-row moments, and the LN-consuming GEMMs (QKV, c_fc) apply mean / rstd / gamma / beta in
+    // their epilogues on top of gamma-folded weights (GemmArgs, gemm2 MODE 2 / 3).
+    {
+      ProfScope prof(h, PC_LAYERNORM, 0.0, (double)M * 768 * 10, st);
+      layernorm_pre_fold_kernel<768><<<(unsigned)((M + 7) / 8), 256, 0, st>>>(ws.x, h->ln_pre_g, h->ln_pre_b, ws.xn,
+                                                                             ws.stats, (int)M, 1e-5f);
+      h->launches++;
+    }
+    for (int l = 0; l < c.layers; ++l) {
+      const LayerW& L = h->layers[l];
+      LnFoldArgs f_qkv, f_fc, f_res;
+      f_qkv.stats_in = ws.stats; f_qkv.svec = L.s_qkv; f_qkv.cvec = L.c_qkv;
+      f_fc.stats_in = ws.stats; f_fc.svec = L.s_fc; f_fc.cvec = L.c_fc;
+      f_res.xb = ws.xn; f_res.stats_out = ws.stats;
+      ARP_TRY(launch_gemm(h, ws.xn, Mcap, L.w_qkv_fold, ws.qkv, false, ACT_NONE, M, 3 * W, W, 3 * W, nullptr, nullptr, 0,
+                          nullptr, 0, st, &f_qkv));
+      ARP_TRY(launch_attention(h, ws.qkv, ws.attn, (int)n, h->tokens, st, Mcap));
+      if (h->ln_fold >= 2) {
+        ARP_TRY(launch_gemm(h, ws.attn, Mcap, L.w_out, ws.x, true, ACT_NONE, M, W, W, W, L.b_out, ws.x, W, nullptr, 0, st,
+                            &f_res));
+        ARP_TRY(launch_gemm(h, ws.xn, Mcap, L.w_fc_fold, ws.hid, false, ACT_QUICKGELU, M, 4 * W, W, 4 * W, nullptr,
+                            nullptr, 0, nullptr, 0, st, &f_fc));
+      } else {
+        // out_proj (K = N = 768) is HBM-bound: its residual stays a TMA reduce-add and ln_2 a standalone kernel
+        ARP_TRY(launch_gemm(h, ws.attn, Mcap, L.w_out, ws.x, true, ACT_NONE, M, W, W, W, L.b_out, ws.x, W, nullptr, 0, st));
+        ARP_TRY(launch_ln_bf16(h, ws.x, L.ln2_g, L.ln2_b, ws.xn, M, st));
+        ARP_TRY(launch_gemm(h, ws.xn, Mcap, L.w_fc, ws.hid, false, ACT_QUICKGELU, M, 4 * W, W, 4 * W, L.b_fc, nullptr, 0,
+                            nullptr, 0, st));
+      }
+      ARP_TRY(launch_gemm(h, ws.hid, Mcap, L.w_proj, ws.x, true, ACT_NONE, M, W, 4 * W, W, L.b_proj, ws.x, W, nullptr, 0,
+                          st, &f_res));
+      if (h->adapter) {
+        gather_cls_bf16_kernel<768><<<(unsigned)((n + 7) / 8), 256, 0, st>>>(ws.x, ws.taps, (int)n, h->tokens,
+                                                                           c.layers * W, l * W);
+        h->launches++;
+      }
+    }
+    ARP_CUDA(h, cudaGetLastError());
+    return ARP_OK;
+  }
   {
     ProfScope prof(h, PC_LAYERNORM, 0.0, (double)M * 768 * 8, st);
     layernorm_f32_inplace_kernel<768><<<(unsigned)((M + 7) / 8), 256, 0, st>>>(ws.x, h->ln_pre_g, h->ln_pre_b, (int)M, 1e-5f);

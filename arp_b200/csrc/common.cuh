@@ -212,6 +212,15 @@ __device__ __forceinline__ uint32_t mapa_u32(uint32_t local_addr, uint32_t rank)
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
   asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
+// Same arrive without release semantics: no MEMBAR, so the warp's in-flight global loads/stores are not drained
+// first. For barriers that hand back TMEM only (tcgen05.wait::ld + tcgen05.fence::before_thread_sync order the
+// reads); never for barriers that publish generic-proxy memory.
+__device__ __forceinline__ void mbar_arrive_cluster_relaxed(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_relaxed(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.relaxed.cta.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
 // CTA-pair TMA load: data lands in THIS CTA's smem, completion bytes are credited to the barrier at
 // `mbar_cluster_addr` (the leader CTA's barrier).
 __device__ __forceinline__ void tma_load_2d_cg2(void* dst, const CUtensorMap* m, uint32_t mbar_cluster_addr, int c0,

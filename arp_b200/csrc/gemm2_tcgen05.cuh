@@ -39,7 +39,9 @@ struct G2Cfg {
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + G2_STAGING_BYTES + 1024 + 256;
 };
 
-template <typename OutT, int ACT, int CG, bool REDUCE>
+enum G2Mode : int { G2_STORE = 0, G2_REDUCE = 1, G2_RESID_LN = 2, G2_LNFOLD = 3 };
+
+template <typename OutT, int ACT, int CG, int MODE>
 __global__ void __launch_bounds__(G2_THREADS, 1)
 gemm2_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                           const __grid_constant__ CUtensorMap tmap_out, const GemmArgs args) {
@@ -54,6 +56,7 @@ gemm2_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gr
   uint64_t* tfull_bar = bars + 2 * STAGES;
   uint64_t* tempty_bar = tfull_bar + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  static_assert(MODE != G2_RESID_LN || sizeof(OutT) == 4, "the residual stream is fp32");
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -171,18 +174,52 @@ gemm2_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gr
     uint32_t acc_phase = 0;
     uint32_t buf = 0;
     const int sw = lane & 7;
+    float4 xres[2][8];                         // MODE 2: residual values in the coalesced layout, ping-pong over units
+    auto load_resid = [&](float4 (&dst)[8], int r0, int c0) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int gr = r0 + i * 4 + (lane >> 3);
+        dst[i] = gr < args.M ? *reinterpret_cast<const float4*>(args.resid + static_cast<size_t>(gr) * args.ldr + c0 + (lane & 7) * 4)
+                             : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    };
     for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
       const int m_blk = tile / num_n, n_blk = tile % num_n;
+      const int row0 = (m_blk * CG + rank) * GEMM_BM + quarter * 32;
+      // MODE 2: the residual does not depend on the accumulator — its first unit is in flight while the MMAs finish,
+      // and unit u+1 is requested before unit u is processed
+      if (MODE == G2_RESID_LN) load_resid(xres[0], row0, n_blk * GEMM_BN + half * 128);
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
-      const int row0 = (m_blk * CG + rank) * GEMM_BM + quarter * 32;
       const int row = row0 + lane;
       const uint32_t taddr = tmem_base + acc * GEMM_BN + half * 128 + (static_cast<uint32_t>(quarter * 32) << 16);
       const float* tab_row =
           args.rowtab ? args.rowtab + static_cast<size_t>(row % args.period) * args.N : nullptr;
-#pragma unroll 1
+      float ln_rstd = 1.f, ln_rm = 0.f;        // MODE 3: row's 1/std and -mean/std
+      if (MODE == G2_LNFOLD) {
+        const float2* st = reinterpret_cast<const float2*>(args.stats_in) + static_cast<size_t>(row) * args.stats_nh;
+        float S1 = 0.f, S2 = 0.f;
+        if (row < args.M) {
+          for (int hh = 0; hh < args.stats_nh; ++hh) {
+            const float2 p = __ldg(st + hh);
+            S1 += p.x;
+            S2 += p.y;
+          }
+        }
+        const float inv_k = 1.0f / static_cast<float>(128 * args.stats_nh);
+        const float mean = S1 * inv_k;
+        ln_rstd = rsqrtf(fmaxf(S2 * inv_k - mean * mean, 0.f) + args.eps);
+        ln_rm = -ln_rstd * mean;
+      }
+      float rs1[8], rs2[8];                    // MODE 2: moments of the 8 rows this lane touches in the coalesced layout
+      if (MODE == G2_RESID_LN) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) rs1[i] = rs2[i] = 0.f;
+      }
+#pragma unroll(MODE == G2_RESID_LN ? UNITS : 1)
       for (int u = 0; u < UNITS; ++u) {
         const int n0 = n_blk * GEMM_BN + half * 128 + u * UNIT_COLS;
+        if (MODE == G2_RESID_LN && u + 1 < UNITS) load_resid(xres[(u + 1) & 1], row0, n0 + UNIT_COLS);
         float v[UNIT_COLS];
         {
           uint32_t r[32];
@@ -204,11 +241,21 @@ gemm2_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gr
           tc_fence_before();
           __syncwarp();
           if (lane == 0) {
-            if (CG == 1) mbar_arrive(&tempty_bar[acc]);
-            else mbar_arrive_cluster(acc ? tempty_leader1 : tempty_leader0);
+            if (CG == 1) mbar_arrive_relaxed(&tempty_bar[acc]);
+            else mbar_arrive_cluster_relaxed(acc ? tempty_leader1 : tempty_leader0);
           }
         }
-        if (args.bias) {
+        if (MODE == G2_LNFOLD) {
+#pragma unroll
+          for (int j = 0; j < UNIT_COLS; j += 4) {
+            const float4 sv = __ldg(reinterpret_cast<const float4*>(args.svec + n0 + j));
+            const float4 cv = __ldg(reinterpret_cast<const float4*>(args.cvec + n0 + j));
+            v[j] = fmaf(ln_rstd, v[j], fmaf(ln_rm, sv.x, cv.x));
+            v[j + 1] = fmaf(ln_rstd, v[j + 1], fmaf(ln_rm, sv.y, cv.y));
+            v[j + 2] = fmaf(ln_rstd, v[j + 2], fmaf(ln_rm, sv.z, cv.z));
+            v[j + 3] = fmaf(ln_rstd, v[j + 3], fmaf(ln_rm, sv.w, cv.w));
+          }
+        } else if (args.bias) {
 #pragma unroll
           for (int j = 0; j < UNIT_COLS; j += 4) {
             const float4 b = __ldg(reinterpret_cast<const float4*>(args.bias + n0 + j));
@@ -231,7 +278,9 @@ gemm2_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gr
         }
         // staging buffer `buf` was last read by the TMA store issued two units ago
         uint8_t* sbuf = my_stage + buf * G2_STAGE_UNIT;
-        if (lane == 0) tma_store_wait_read<1>();
+        if (MODE != G2_RESID_LN) {
+          if (lane == 0) tma_store_wait_read<1>();
+        }
         __syncwarp();
         uint4* srow = reinterpret_cast<uint4*>(sbuf + lane * 128);
 #pragma unroll
@@ -246,14 +295,54 @@ gemm2_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gr
           }
           srow[c ^ sw] = q;   // 128B swizzle: 16-byte chunk index XOR (row & 7)
         }
-        fence_proxy_async_smem();
-        __syncwarp();
-        if (lane == 0) {
-          if (REDUCE) tma_reduce_add_2d(&tmap_out, sbuf, n0, row0);
-          else tma_store_2d(&tmap_out, sbuf, n0, row0);
-          tma_store_commit();
+        if (MODE == G2_RESID_LN) {
+          // The staged tile is read back transposed: lane -> (row i*4 + lane/8, 16-byte chunk lane%8), so that the
+          // residual read, the fp32 write-back and the bf16 copy are all full-line coalesced accesses.
+          __syncwarp();
+          if (sizeof(OutT) == 4) {
+            float* xo = reinterpret_cast<float*>(args.out);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const int r = i * 4 + (lane >> 3), c = lane & 7;
+              const int gr = row0 + r;
+              const float4 a = *reinterpret_cast<const float4*>(sbuf + r * 128 + ((c ^ (r & 7)) << 4));
+              const float4 xr = xres[u & 1][i];
+              const float4 y = make_float4(a.x + xr.x, a.y + xr.y, a.z + xr.z, a.w + xr.w);
+              if (gr < args.M) {
+                *reinterpret_cast<float4*>(xo + static_cast<size_t>(gr) * args.ldo + n0 + c * 4) = y;
+                *reinterpret_cast<uint2*>(args.xb + static_cast<size_t>(gr) * args.N + n0 + c * 4) =
+                    make_uint2(pack_bf16(y.x, y.y), pack_bf16(y.z, y.w));
+              }
+              rs1[i] += (y.x + y.y) + (y.z + y.w);
+              rs2[i] += (y.x * y.x + y.y * y.y) + (y.z * y.z + y.w * y.w);
+            }
+          }
+        } else {
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            if (MODE == G2_REDUCE) tma_reduce_add_2d(&tmap_out, sbuf, n0, row0);
+            else tma_store_2d(&tmap_out, sbuf, n0, row0);
+            tma_store_commit();
+          }
         }
         buf ^= 1;
+      }
+      if (MODE == G2_RESID_LN) {
+        // moments of this warp's 128 columns: reduce over the 8 lanes that share a row, one writer per row
+        const int nh_out = args.N >> 7;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          float a = rs1[i], b = rs2[i];
+#pragma unroll
+          for (int o = 1; o < 8; o <<= 1) {
+            a += __shfl_xor_sync(0xffffffffu, a, o);
+            b += __shfl_xor_sync(0xffffffffu, b, o);
+          }
+          const int gr = row0 + i * 4 + (lane >> 3);
+          if ((lane & 7) == 0 && gr < args.M)
+            reinterpret_cast<float2*>(args.stats_out)[static_cast<size_t>(gr) * nh_out + n_blk * 2 + half] = make_float2(a, b);
+        }
       }
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }

@@ -29,6 +29,20 @@ struct GemmArgs {
   int ldr;
   const float* rowtab;  // fp32 [period, N] added to row (row % period), or nullptr (pos-emb + cls)
   int period;
+  // ---- LayerNorm fold (gemm2 MODE 2 / 3) ----
+  // MODE 2 (residual + LN statistics): x = resid + acc + bias is written to `out` (fp32, may alias resid), a bf16
+  //   copy to `xb` [M, N], and per-row partial moments (sum, sum of squares over each 128-column span) to
+  //   `stats_out` [M, 2*N/128]. Every partial is written by exactly one warp: no atomics, deterministic.
+  // MODE 3 (LN applied algebraically): A was the RAW bf16 residual stream and W' = W*diag(gamma), so
+  //   LN(x) W^T + bias = rstd_r * (acc - mean_r * svec_n) + cvec_n with svec = W' 1, cvec = W beta + bias;
+  //   mean_r / rstd_r come from `stats_in` [M, 2*stats_nh] (moments over K = 128*stats_nh columns).
+  __nv_bfloat16* xb;
+  float* stats_out;
+  const float* stats_in;
+  int stats_nh;
+  const float* svec;
+  const float* cvec;
+  float eps;
 };
 
 constexpr int GEMM_BM = 128;

@@ -77,6 +77,57 @@ layernorm_f32_inplace_kernel(float* __restrict__ x, const float* __restrict__ ga
   for (int i = 0; i < RowRegs<W>::kVec; ++i) reinterpret_cast<float4*>(xr)[i * 32 + lane] = r.v[i];
 }
 
+// ln_pre for the LayerNorm-folded pipeline: x = LN(x) in place (fp32), plus what the first resblock's folded
+// LN needs — a bf16 copy of the new x and per-row partial moments (sum, sum of squares) over each 128-column
+// span, in the same [M, 2*W/128] layout the residual GEMM epilogue writes (gemm2 MODE 2).
+template <int W>
+__global__ void __launch_bounds__(256)
+layernorm_pre_fold_kernel(float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
+                          __nv_bfloat16* __restrict__ xb, float* __restrict__ stats, int M, float eps) {
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= M) return;
+  const int lane = threadIdx.x & 31;
+  RowRegs<W> r;
+  float* xr = x + static_cast<size_t>(row) * W;
+  ln_row<W>(xr, gamma, beta, eps, r);
+  uint2* ob = reinterpret_cast<uint2*>(xb + static_cast<size_t>(row) * W);
+  float2* st = reinterpret_cast<float2*>(stats) + static_cast<size_t>(row) * (W / 128);
+#pragma unroll
+  for (int i = 0; i < RowRegs<W>::kVec; ++i) {      // float4 i of lane l is column (i*32 + l)*4: span i = columns [128i, 128i+128)
+    reinterpret_cast<float4*>(xr)[i * 32 + lane] = r.v[i];
+    ob[i * 32 + lane] = make_uint2(pack_bf16(r.v[i].x, r.v[i].y), pack_bf16(r.v[i].z, r.v[i].w));
+    const float a = warp_sum((r.v[i].x + r.v[i].y) + (r.v[i].z + r.v[i].w));
+    const float b = warp_sum((r.v[i].x * r.v[i].x + r.v[i].y * r.v[i].y) + (r.v[i].z * r.v[i].z + r.v[i].w * r.v[i].w));
+    if (lane == 0) st[i] = make_float2(a, b);
+  }
+}
+
+// Weight preparation for the folded LayerNorm (run once per weight load), one warp per output row n:
+//   Wf[n,k] = bf16(W[n,k] * gamma[k]);  svec[n] = sum_k float(Wf[n,k]);  cvec[n] = sum_k W[n,k]*beta[k] + bias[n]
+// svec uses the ROUNDED weights so that acc - mean*svec cancels the mean exactly as the tensor core saw it.
+__global__ void __launch_bounds__(256)
+fold_ln_weights_kernel(const float* __restrict__ Wt, const float* __restrict__ gamma, const float* __restrict__ beta,
+                       const float* __restrict__ bias, __nv_bfloat16* __restrict__ Wf, float* __restrict__ svec,
+                       float* __restrict__ cvec, int N, int K) {
+  const int n = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (n >= N) return;
+  const int lane = threadIdx.x & 31;
+  float s = 0.f, c = 0.f;
+  for (int k = lane; k < K; k += 32) {
+    const float w = Wt[static_cast<size_t>(n) * K + k];
+    const __nv_bfloat16 wf = __float2bfloat16_rn(w * gamma[k]);
+    Wf[static_cast<size_t>(n) * K + k] = wf;
+    s += __bfloat162float(wf);
+    c = fmaf(w, beta[k], c);
+  }
+  s = warp_sum(s);
+  c = warp_sum(c);
+  if (lane == 0) {
+    svec[n] = s;
+    cvec[n] = c + bias[n];
+  }
+}
+
 // taps(bf16)[B, ld_taps] columns [layer*W, (layer+1)*W) = x[b*tokens + 0, :]
 // The CLS row of every resblock output; replaces the reference's forward hooks
 // (finetune_module/utils.py:6-18, clip_multiscale_adapter.py:138-143).
