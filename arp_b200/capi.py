@@ -22,6 +22,7 @@ HEAD_CLIP, HEAD_ADAPTER, HEAD_ADAPTER_ENSEMBLE, HEAD_CLIP_GOAL, HEAD_ADAPTER_GOA
 REDUCE_FIRST, REDUCE_MEAN = 0, 1
 DT_F32, DT_BF16, DT_F16 = 0, 1, 2
 ACT_NONE, ACT_QUICKGELU, ACT_RELU = 0, 1, 2
+PREC_BF16, PREC_F32 = 0, 1
 MAX_TEXT = 16
 
 #: every symbol include/arp_b200.h declares (tests check the library exports exactly these)
@@ -41,7 +42,7 @@ class ArpProfileStats(C.Structure):
 class ArpConfig(C.Structure):
     _fields_ = [(n, C.c_int32) for n in (
         "struct_size", "device", "patch", "width", "layers", "heads", "embed_dim", "in_h", "in_w", "use_crop",
-        "preprocess", "head", "reduce", "max_batch")]
+        "preprocess", "head", "reduce", "max_batch", "precision")]
 
 
 class ArpError(RuntimeError):
@@ -113,11 +114,12 @@ class Engine:
 
     def __init__(self, *, device: int = 0, patch: int = 16, in_h: int = 64, in_w: int = 64, use_crop: bool = False,
                  preprocess: int = PRE_PIL_BICUBIC, head: int = HEAD_CLIP, reduce: int = REDUCE_FIRST,
-                 max_batch: int = 256, layers: int = 12, width: int = 768, heads: int = 12, embed_dim: int = 512):
+                 max_batch: int = 256, layers: int = 12, width: int = 768, heads: int = 12, embed_dim: int = 512,
+                 precision: int = PREC_BF16):
         self._lib = load_library()
         self._h = C.c_void_p()
         self.cfg = ArpConfig(C.sizeof(ArpConfig), device, patch, width, layers, heads, embed_dim, in_h, in_w,
-                             int(bool(use_crop)), preprocess, head, reduce, max_batch)
+                             int(bool(use_crop)), preprocess, head, reduce, max_batch, precision)
         rc = self._lib.arp_create(C.byref(self.cfg), C.byref(self._h))
         if rc != ARP_OK:
             raise ArpError(rc, (self._lib.arp_last_error(None) or b"").decode())

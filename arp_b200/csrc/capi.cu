@@ -18,6 +18,7 @@
 #include "attention.cuh"
 #include "attention_tc.cuh"
 #include "decode.cuh"
+#include "fp32_path.cuh"
 #include "gemm_tcgen05.cuh"
 #include "gemm2_tcgen05.cuh"
 #include "head.cuh"
@@ -107,6 +108,7 @@ struct ArpHandle {
   // numerically equivalent, but the register-path residual epilogue (gemm2 MODE 2) is latency-bound on the x loads
   // (out_proj 137 -> 236 us), which cancels the 2 x 63 us of LN kernels it removes; kept off until MODE 2 stages x by TMA.
   int ln_fold = 0;
+  bool f32 = false;   // cfg.precision == ARP_PREC_F32: verification path (fp32_path.cuh); GEMM weights are stored as fp32
   int attn_impl = 2;  // 1 = mma.sync kernel, 2 = tcgen05 kernel (ARP_ATTN_IMPL overrides)
   int gemm_impl = 3;  // 1 = v1 (register stores), 2 = v2 single-CTA, 3 = v2 CTA pairs (ARP_GEMM_IMPL overrides)
   int tokens = 0, grid = 0, kp = 0;  // 197, 14, 768
@@ -144,6 +146,9 @@ struct ArpHandle {
     bf16 *taps = nullptr, *featb = nullptr, *hid2 = nullptr;
     float *featf = nullptr, *mlp = nullptr;
     float* stats = nullptr;   // [M, 2*W/128] partial LayerNorm moments (LN fold)
+    // fp32 verification path
+    float *chw32 = nullptr, *xn32 = nullptr, *qkv32 = nullptr, *attn32 = nullptr, *hid32 = nullptr;
+    float *taps32 = nullptr, *hid2_32 = nullptr;
   } ws[2];
   int n_pipes = 1;                       // ARP_PIPES=2: two chunks in flight (measured: no gain on B200 — a resident
                                          // persistent GEMM CTA leaves no room the scheduler will give to another kernel)
@@ -477,17 +482,20 @@ extern "C" int arp_create(const ArpConfig* cfg, ArpHandle** out) {
     return fail(nullptr, ARP_ERR_INVALID, "bad layers / max_batch / frame size");
   if (cfg->head < 0 || cfg->head > ARP_HEAD_ADAPTER_GOAL || cfg->preprocess < 0 || cfg->preprocess > 1)
     return fail(nullptr, ARP_ERR_INVALID, "bad head / preprocess enum");
+  if (cfg->precision != ARP_PREC_BF16 && cfg->precision != ARP_PREC_F32)
+    return fail(nullptr, ARP_ERR_INVALID, "bad precision enum");
   if (!get_encode_tiled()) return fail(nullptr, ARP_ERR_CUDA, "cuTensorMapEncodeTiled not available from the driver");
 
   ArpHandle* h = new ArpHandle();
   h->cfg = *cfg;
   auto bail = [&](int code) { g_create_error = h->err; arp_destroy(h); return code; };
   if (cudaSetDevice(cfg->device) != cudaSuccess) { h->err = "cudaSetDevice failed"; return bail(ARP_ERR_CUDA); }
+  h->f32 = cfg->precision == ARP_PREC_F32;
   if (const char* e = getenv("ARP_GEMM_IMPL")) h->gemm_impl = atoi(e);
   if (h->gemm_impl < 1 || h->gemm_impl > 3) h->gemm_impl = 3;
   if (const char* e = getenv("ARP_ATTN_IMPL")) h->attn_impl = atoi(e) == 1 ? 1 : 2;
   if (const char* e = getenv("ARP_LN_FOLD")) h->ln_fold = std::max(0, std::min(2, atoi(e)));
-  if (h->gemm_impl < 2) h->ln_fold = 0;   // the fold lives in the v2 epilogue
+  if (h->gemm_impl < 2 || h->f32) h->ln_fold = 0;   // the fold lives in the v2 epilogue
   h->grid = DEC_OUT / cfg->patch;
   h->tokens = h->grid * h->grid + 1;
   h->kp = 3 * cfg->patch * cfg->patch;
@@ -508,6 +516,21 @@ extern "C" int arp_create(const ArpConfig* cfg, ArpHandle** out) {
   for (int p = 0; p < h->n_pipes; ++p) {
     ArpHandle::Work& w = h->ws[p];
     CREATE_TRY(dev_alloc(h, &w.x, M * W));
+    if (h->f32) {
+      CREATE_TRY(dev_alloc(h, &w.chw32, B * 3 * DEC_OUT * DEC_OUT));
+      CREATE_TRY(dev_alloc(h, &w.xn32, M * W));
+      CREATE_TRY(dev_alloc(h, &w.qkv32, M * 3 * W));
+      CREATE_TRY(dev_alloc(h, &w.attn32, M * W));
+      CREATE_TRY(dev_alloc(h, &w.hid32, M * std::max<size_t>(4 * W, h->kp)));
+      if (h->adapter) {
+        const size_t D = h->feat_dim;
+        CREATE_TRY(dev_alloc(h, &w.taps32, B * cfg->layers * W));
+        CREATE_TRY(dev_alloc(h, &w.featf, B * D));
+        CREATE_TRY(dev_alloc(h, &w.hid2_32, B * 2 * D));
+        CREATE_TRY(dev_alloc(h, &w.mlp, B * D));
+      }
+      continue;
+    }
     CREATE_TRY(dev_alloc(h, &w.xn, M * W));
     CREATE_TRY(dev_alloc(h, &w.qkv, M * 3 * W));
     // padded key rows of a frame are the next frame's rows: keep every bit pattern in this buffer finite
@@ -528,6 +551,7 @@ extern "C" int arp_create(const ArpConfig* cfg, ArpHandle** out) {
   for (auto& kv : h->slots) {
     WeightSlot& s = kv.second;
     void* p = nullptr;
+    if (h->f32) s.as_bf16 = false;   // verification path: every tensor is kept in fp32 (LayerW's bf16* then point at floats)
     if (cudaMalloc(&p, s.numel * (s.as_bf16 ? 2 : 4) + 256) != cudaSuccess) { h->err = "cudaMalloc(weights) failed"; return bail(ARP_ERR_CUDA); }
     h->allocs.push_back(p);
     *s.dst = p;
@@ -565,6 +589,7 @@ extern "C" int arp_create(const ArpConfig* cfg, ArpHandle** out) {
   CREATE_TRY(set_smem(h, attention_kernel<197>, AttnCfg<197>::SMEM));
   CREATE_TRY(set_smem(h, attention_kernel<50>, AttnCfg<50>::SMEM));
   CREATE_TRY(set_smem(h, decode_kernel, 160 * 1024));
+  CREATE_TRY(set_smem(h, attention_f32_kernel, attn_f32_smem_bytes(197)));
   if (cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking) != cudaSuccess ||
       cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking) != cudaSuccess) {
     h->err = "cudaStreamCreate failed";
@@ -933,7 +958,10 @@ static int launch_attention(ArpHandle* h, const bf16* qkv, bf16* out, int B, int
 // ------------------------------------------------------------------------------------------------
 // the encoder: n frames (n <= max_batch) -> residual stream x after the last block (+ CLS taps)
 // ------------------------------------------------------------------------------------------------
+static int encode_chunk_f32(ArpHandle* h, int pipe, const uint8_t* ob, int64_t n, int64_t stride, cudaStream_t st);
+
 static int encode_chunk(ArpHandle* h, int pipe, const uint8_t* ob, int64_t n, int64_t stride, cudaStream_t st) {
+  if (h->f32) return encode_chunk_f32(h, pipe, ob, n, stride, st);
   const ArpConfig& c = h->cfg;
   ArpHandle::Work& ws = h->ws[pipe];
   const int W = c.width;
@@ -1013,6 +1041,71 @@ static int encode_chunk(ArpHandle* h, int pipe, const uint8_t* ob, int64_t n, in
   return ARP_OK;
 }
 
+// ------------------------------------------------------------------------------------------------
+// fp32 verification path (fp32_path.cuh): same schedule, FP32 FMA kernels
+// ------------------------------------------------------------------------------------------------
+static int launch_sgemm(ArpHandle* h, const float* a, int lda, const void* w, float* out, int ldo, int act, int64_t M,
+                        int N, int K, const float* bias, const float* resid, int ldr, const float* rowtab, int period,
+                        cudaStream_t st) {
+  if (M <= 0) return ARP_OK;
+  if (N % SG_BN || K % SG_BK) return fail(h, ARP_ERR_INVALID, "fp32 GEMM needs N %% 128 == 0 and K %% 16 == 0 (N=%d K=%d)", N, K);
+  ProfScope prof(h, PC_GEMM, 2.0 * (double)M * N * K, ((double)M * K + (double)N * K + (double)M * N) * 4, st);
+  dim3 grid(N / SG_BN, (unsigned)((M + SG_BM - 1) / SG_BM));
+  sgemm_nt_f32_kernel<<<grid, SG_THREADS, 0, st>>>(a, static_cast<const float*>(w), out, (int)M, N, K, lda, ldo, bias,
+                                                   resid, ldr, rowtab, period > 0 ? period : 1, act);
+  h->launches++;
+  ARP_CUDA(h, cudaGetLastError());
+  return ARP_OK;
+}
+
+static int encode_chunk_f32(ArpHandle* h, int pipe, const uint8_t* ob, int64_t n, int64_t stride, cudaStream_t st) {
+  const ArpConfig& c = h->cfg;
+  ArpHandle::Work& ws = h->ws[pipe];
+  const int W = c.width;
+  const int64_t M = n * h->tokens;
+  if (h->tokens != 197 && h->tokens != 50) return fail(h, ARP_ERR_INVALID, "unsupported token count %d", h->tokens);
+  float* patches = ws.hid32;   // dead until layer 0's c_fc
+  ARP_TRY(launch_decode(h, ob, n, stride, ws.chw32, DEC_OUT_CHW_F32, st));
+  im2col_f32_kernel<<<kNumSMs * 8, 256, 0, st>>>(ws.chw32, patches, (int)n, c.patch, h->grid, h->tokens);
+  h->launches++;
+  ARP_TRY(launch_sgemm(h, patches, h->kp, h->conv1, ws.x, W, F32_ACT_NONE, M, W, h->kp, nullptr, nullptr, 0, h->rowtab,
+                       h->tokens, st));
+  auto ln = [&](const float* x, const float* g, const float* b, float* y) {
+    ProfScope prof(h, PC_LAYERNORM, 0.0, (double)M * W * 8, st);
+    layernorm_f32_f32_kernel<768><<<(unsigned)((M + 7) / 8), 256, 0, st>>>(x, g, b, y, (int)M, 1e-5f);
+    h->launches++;
+  };
+  ln(ws.x, h->ln_pre_g, h->ln_pre_b, ws.x);
+  for (int l = 0; l < c.layers; ++l) {
+    const LayerW& L = h->layers[l];
+    ln(ws.x, L.ln1_g, L.ln1_b, ws.xn32);
+    ARP_TRY(launch_sgemm(h, ws.xn32, W, L.w_qkv, ws.qkv32, 3 * W, F32_ACT_NONE, M, 3 * W, W, L.b_qkv, nullptr, 0, nullptr,
+                         0, st));
+    {
+      ProfScope prof(h, PC_ATTENTION, 4.0 * (double)n * c.heads * h->tokens * h->tokens * 64, (double)M * W * 4 * 4, st);
+      for (int64_t b0 = 0; b0 < n; b0 += 32768) {
+        const int cnt = (int)std::min<int64_t>(32768, n - b0);
+        attention_f32_kernel<<<dim3(c.heads, cnt), A32_THREADS, attn_f32_smem_bytes(h->tokens), st>>>(
+            ws.qkv32 + (size_t)b0 * h->tokens * 3 * W, ws.attn32 + (size_t)b0 * h->tokens * W, h->tokens, W);
+        h->launches++;
+      }
+    }
+    ARP_TRY(launch_sgemm(h, ws.attn32, W, L.w_out, ws.x, W, F32_ACT_NONE, M, W, W, L.b_out, ws.x, W, nullptr, 0, st));
+    ln(ws.x, L.ln2_g, L.ln2_b, ws.xn32);
+    ARP_TRY(launch_sgemm(h, ws.xn32, W, L.w_fc, ws.hid32, 4 * W, F32_ACT_QUICKGELU, M, 4 * W, W, L.b_fc, nullptr, 0,
+                         nullptr, 0, st));
+    ARP_TRY(launch_sgemm(h, ws.hid32, 4 * W, L.w_proj, ws.x, W, F32_ACT_NONE, M, W, 4 * W, L.b_proj, ws.x, W, nullptr, 0,
+                         st));
+    if (h->adapter) {
+      gather_cls_f32_kernel<768><<<(unsigned)((n + 7) / 8), 256, 0, st>>>(ws.x, ws.taps32, (int)n, h->tokens,
+                                                                        c.layers * W, l * W);
+      h->launches++;
+    }
+  }
+  ARP_CUDA(h, cudaGetLastError());
+  return ARP_OK;
+}
+
 // heads. reward_out [n] / logits_out [n, n_text] / feat_out [n, feat_dim] may each be null.
 static int head_chunk(ArpHandle* h, int pipe, int64_t n, float* reward_out, float* logits_out, float* feat_out,
                       cudaStream_t st) {
@@ -1034,6 +1127,14 @@ static int head_chunk(ArpHandle* h, int pipe, int64_t n, float* reward_out, floa
                                                             h->proj, nullptr, 0, 0.f, 0, ws.featf, D, Dmid, nullptr,
                                                             nullptr);
     h->launches++;
+    if (h->f32) {
+      ARP_TRY(launch_sgemm(h, ws.taps32, Din, h->inter_w, ws.featf, D, F32_ACT_NONE, n, Dmid, Din, nullptr, nullptr, 0,
+                           nullptr, 0, st));
+      ARP_TRY(launch_sgemm(h, ws.featf, D, h->fc1_w, ws.hid2_32, 2 * D, F32_ACT_RELU, n, 2 * D, D, h->fc1_b, nullptr, 0,
+                           nullptr, 0, st));
+      ARP_TRY(launch_sgemm(h, ws.hid2_32, 2 * D, h->fc2_w, ws.mlp, D, F32_ACT_NONE, n, D, 2 * D, h->fc2_b, nullptr, 0,
+                           nullptr, 0, st));
+    } else {
     // image_intermediate_linear (no bias) over the 12 CLS taps -> first 6144 columns (:143-144)
     ARP_TRY(launch_gemm(h, ws.taps, B, h->inter_w, ws.featf, true, ACT_NONE, n, Dmid, Din, D, nullptr, nullptr, 0,
                         nullptr, 0, st));
@@ -1044,6 +1145,7 @@ static int head_chunk(ArpHandle* h, int pipe, int64_t n, float* reward_out, floa
                         nullptr, 0, st));
     ARP_TRY(launch_gemm(h, ws.hid2, B, h->fc2_w, ws.mlp, true, ACT_NONE, n, D, 2 * D, D, h->fc2_b, nullptr, 0, nullptr,
                         0, st));
+    }
     const bool ens = c.head == ARP_HEAD_ADAPTER_ENSEMBLE;
     adapter_head_kernel<13, 512><<<(unsigned)n, 13 * 32, 0, st>>>(
         ws.featf, ws.mlp, h->res_sigmoid, (need_text && !h->goal) ? h->text : nullptr,

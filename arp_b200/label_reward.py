@@ -23,6 +23,8 @@ Keyword-only extensions (all optional; defaults reproduce the reference):
     reduce           "first" (reference behaviour) or "mean" (envs/vl_reward.py semantics).
     max_batch        frames per device chunk.      slab_frames  frames per host slab.
     device           CUDA ordinal (default: LOCAL_RANK or 0).
+    precision        "bf16" (tensor-core product path) or "fp32" (verification path: every weight, activation and
+                     contraction in fp32, what the reference's CPU route computes; ~50x slower).
     distributed      shard episodes over torch.distributed ranks (default: on when a process group exists).
 """
 from __future__ import annotations
@@ -112,8 +114,10 @@ class RewardLabeler:
 
     def __init__(self, model_type: str, text, frame_hw: tuple[int, int], *, model_ckpt_dir=None,
                  clip_state_dict=None, arch: str = "ViT-B/16", use_crop: bool = False, reduce: str = "first",
-                 max_batch: int = 512, device: int | None = None):
+                 max_batch: int = 512, device: int | None = None, precision: str = "bf16"):
         head, pre = _head_for(model_type)
+        if precision not in ("bf16", "fp32"):
+            raise ValueError(f"precision must be 'bf16' or 'fp32', got {precision!r}")
         adapter = head in (capi.HEAD_ADAPTER, capi.HEAD_ADAPTER_ENSEMBLE, capi.HEAD_ADAPTER_GOAL)
         if adapter:
             assert model_ckpt_dir is not None, "specify model_ckpt_dir"  # label_reward.py:174
@@ -124,7 +128,8 @@ class RewardLabeler:
         self.engine = capi.Engine(device=device, patch=patch, in_h=frame_hw[0], in_w=frame_hw[1],
                                   use_crop=bool(use_crop), preprocess=pre, head=head,
                                   reduce=capi.REDUCE_MEAN if reduce == "mean" else capi.REDUCE_FIRST,
-                                  max_batch=max_batch)
+                                  max_batch=max_batch,
+                                  precision=capi.PREC_F32 if precision == "fp32" else capi.PREC_BF16)
         dev = self.engine.device
         if adapter:
             sd = load_checkpoint(model_ckpt_dir) if not isinstance(model_ckpt_dir, dict) else model_ckpt_dir
@@ -201,6 +206,7 @@ def label_reward(
     slab_frames=16384,
     device=None,
     distributed=None,
+    precision="bf16",
 ):
     image_keys = image_keys.split(", ")
     if data_path is None:
@@ -228,7 +234,7 @@ def label_reward(
 
         labeler = RewardLabeler(model_type, text, (int(H), int(W)), model_ckpt_dir=model_ckpt_dir,
                                 clip_state_dict=clip_state_dict, arch=arch, use_crop=use_crop, reduce=reduce,
-                                max_batch=max_batch, device=device)
+                                max_batch=max_batch, device=device, precision=precision)
         target_keys = [f"{model_type}_reward", f"{model_type}_pos_rtg"]
         if inst_type != "none":
             target_keys = [f"{x}_{inst_type}" for x in target_keys]
@@ -323,6 +329,7 @@ def main():
     parser.add_argument("--arch", type=str, default="ViT-B/16")
     parser.add_argument("--reduce", type=str, default="first", choices=["first", "mean"])
     parser.add_argument("--max_batch", type=int, default=512)
+    parser.add_argument("--precision", type=str, default="bf16", choices=["bf16", "fp32"])
     args = parser.parse_args()
 
     env_name = f"{args.env_name}" if args.env_type == "none" else f"{args.env_name}_{args.env_type}"
@@ -343,7 +350,7 @@ def main():
         start_level=args.start_level, num_demonstrations=args.num_demonstrations, num_frames=args.num_frames,
         base_path=args.base_path, model_type=args.model_type, model_ckpt_dir=args.model_ckpt_dir,
         use_crop=args.use_crop, inst_type=args.inst_type, arch=args.arch, reduce=args.reduce,
-        max_batch=args.max_batch,
+        max_batch=args.max_batch, precision=args.precision,
     )
 
 

@@ -21,7 +21,7 @@
 extern "C" {
 #endif
 
-#define ARP_B200_ABI_VERSION 1
+#define ARP_B200_ABI_VERSION 2
 
 #if defined(__GNUC__)
 #define ARP_API __attribute__((visibility("default")))
@@ -53,6 +53,11 @@ typedef enum ArpHead {
 typedef enum ArpReduce { ARP_REDUCE_FIRST = 0, ARP_REDUCE_MEAN = 1 } ArpReduce;
 
 typedef enum ArpDType { ARP_F32 = 0, ARP_BF16 = 1, ARP_F16 = 2 } ArpDType;
+/* Arithmetic of the model path. BF16 = tcgen05 tensor cores, bf16 operands, fp32 accumulate and fp32 residual
+ * stream (the product path). F32 = verification path: every weight, activation and contraction in fp32 on the
+ * FMA pipe — what clip.load(...).float() computes on the reference's CPU route (label_reward.py:126-141); used
+ * to check the restated algorithm at the 1e-5 bar, ~50x slower. */
+typedef enum ArpPrecision { ARP_PREC_BF16 = 0, ARP_PREC_F32 = 1 } ArpPrecision;
 
 typedef struct ArpHandle ArpHandle;
 
@@ -70,6 +75,7 @@ typedef struct ArpConfig {
   int32_t head;        /* ArpHead */
   int32_t reduce;      /* ArpReduce */
   int32_t max_batch;   /* frames per internal chunk (workspace is sized for this) */
+  int32_t precision;   /* ArpPrecision */
 } ArpConfig;
 
 /* ------------------------------------------------------------------------------------------------

@@ -21,6 +21,9 @@ TOL_COS_ABS = 5e-4          # absolute error of the cosine similarity, bf16 pipe
 TOL_REWARD_REL_TO_MAX = 2e-2   # max|Δr| / max|r_ref| at random init (reported, loose)
 TOL_REWARD_REL_CORRELATED = 1e-3  # north_star's 1e-3 relative, on the well-conditioned correlated-text case
 LOGIT_SCALE_RANDOM_INIT = 1.0 / 0.07
+# fp32 verification path (precision="fp32") against the fp32 reference — north_star's 1e-5:
+TOL_F32_REL = 1e-5          # max|Δr| / max|r_ref| per golden, and per-frame relative on the correlated-text case
+TOL_F32_COS_ABS = 1e-6      # |Δcos|
 
 
 def golden_names():
