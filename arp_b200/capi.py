@@ -30,7 +30,7 @@ EXPORTS = (
     "arp_create", "arp_destroy", "arp_last_error", "arp_abi_version", "arp_set_weight", "arp_missing_weights",
     "arp_set_text", "arp_label", "arp_label_host", "arp_compute_reward", "arp_encode_image", "arp_decode_only",
     "arp_scan_only", "arp_gemm_bf16", "arp_layernorm_bf16", "arp_attention", "arp_launch_count",
-    "arp_profile_begin", "arp_profile_end",
+    "arp_profile_begin", "arp_profile_end", "arp_online_reward",
 )
 PROFILE_CLASSES = ("gemm", "attention", "layernorm", "decode", "head", "scan", "other")
 
@@ -81,6 +81,7 @@ def load_library() -> C.CDLL:
     lib.arp_label.argtypes = [vp, vp, i64, i64, vp, i32, i32, vp, vp, vp, vp, vp]
     lib.arp_label_host.argtypes = [vp, vp, i64, i64, vp, i32, i32, vp, vp, vp, vp]
     lib.arp_compute_reward.argtypes = [vp, vp, i64, i64, vp, vp, vp]
+    lib.arp_online_reward.argtypes = [vp, vp, i32, vp, vp, vp]
     lib.arp_encode_image.argtypes = [vp, vp, i64, i64, vp, vp]
     lib.arp_decode_only.argtypes = [vp, vp, i64, i64, vp, vp]
     lib.arp_scan_only.argtypes = [vp, vp, i64, vp, i32, i32, f32, vp, vp, vp, vp]
@@ -254,6 +255,26 @@ class Engine:
         self._check(self._lib.arp_compute_reward(self._h, C.c_void_p(p), T, stride, _ptr(r), _ptr(lg),
                                                  _stream_ptr(self.device)))
         return (r, lg) if want_logits else r
+
+    def online_reward(self, frames: np.ndarray, want_logits: bool = False, want_features: bool = False):
+        """Latency mode: host uint8 [n,H,W,3] (or [H,W,3]) -> dict of host arrays (reward [n], logits [n,n_text],
+        features [n,feat_dim]); one CUDA-graph launch per call."""
+        f = np.ascontiguousarray(frames, dtype=np.uint8)
+        if f.ndim == 3:
+            f = f[None]
+        assert f.ndim == 4 and f.shape[1:] == (self.cfg.in_h, self.cfg.in_w, 3), f.shape
+        n = f.shape[0]
+        out = {}
+        r = lg = ft = None
+        if not self.goal:
+            r = out["reward"] = np.empty(n, np.float32)
+            if want_logits:
+                lg = out["logits"] = np.empty((n, self.n_text), np.float32)
+        if want_features or self.goal:
+            ft = out["features"] = np.empty((n, self.feat_dim), np.float32)
+        p = lambda a: None if a is None else C.c_void_p(a.ctypes.data)  # noqa: E731
+        self._check(self._lib.arp_online_reward(self._h, p(f), n, p(r), p(lg), p(ft)))
+        return out
 
     def encode_image(self, ob: torch.Tensor) -> torch.Tensor:
         T, p, stride = self._frames_view(ob)

@@ -166,6 +166,12 @@ struct ArpHandle {
   std::map<TmapKey, CUtensorMap> tmaps;
   std::vector<void*> allocs;
 
+  // latency mode (arp_online_reward): one CUDA graph per batch size n, rebuilt when weights or text change
+  struct OnlineGraph { cudaGraphExec_t exec = nullptr; int64_t launches = 0; uint64_t epoch = 0; };
+  std::map<int, OnlineGraph> online_graphs;
+  uint64_t online_epoch = 1;
+  float* online_out = nullptr;   // device [max_batch * (1 + HEAD_MAX_TEXT + feat_dim)]
+
   // optional per-kernel-class timing (arp_profile_begin/end): CUDA events bracket every launch on its stream
   bool profiling = false;
   struct ProfRec { int cls; double flops; double bytes; cudaEvent_t e0, e1; };
@@ -455,6 +461,7 @@ extern "C" void arp_destroy(ArpHandle* h) {
     if (h->ev_join[i]) cudaEventDestroy(h->ev_join[i]);
     if (h->pipe_stream[i]) cudaStreamDestroy(h->pipe_stream[i]);
   }
+  for (auto& kv : h->online_graphs) if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
   if (h->ev_fork) cudaEventDestroy(h->ev_fork);
   for (auto& r : h->prof) { cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); }
   for (cudaEvent_t e : h->event_pool) cudaEventDestroy(e);
@@ -662,6 +669,7 @@ extern "C" int arp_set_weight(ArpHandle* h, const char* name, const void* data, 
   ARP_CUDA(h, cudaGetLastError());
   s.set = true;
   h->finalized = false;
+  h->online_epoch++;
   return ARP_OK;
 }
 
@@ -722,6 +730,7 @@ extern "C" int arp_set_text(ArpHandle* h, const float* text_emb_dev, int32_t n_t
   h->n_text = n_text;
   h->text_dim = dim;
   h->logit_scale = logit_scale_exp;
+  h->online_epoch++;
   return ARP_OK;
 }
 
@@ -1356,6 +1365,19 @@ static int label_device(ArpHandle* h, const uint8_t* ob_dev, int64_t T, int64_t 
   return scan_launch(h, r, T, ep_off, n_eps, F, 1.0f, g, rs, gs, st);
 }
 
+// two device staging buffers of max_batch frames each (host-buffer entry points)
+static int ensure_stage(ArpHandle* h) {
+  const size_t need = (size_t)h->cfg.in_h * h->cfg.in_w * 3 * h->cfg.max_batch;
+  if (h->stage_bytes >= need) return ARP_OK;
+  for (int i = 0; i < 2; ++i) {
+    if (h->stage_dev[i]) cudaFree(h->stage_dev[i]);
+    h->stage_dev[i] = nullptr;
+    ARP_CUDA(h, cudaMalloc((void**)&h->stage_dev[i], need));
+  }
+  h->stage_bytes = need;
+  return ARP_OK;
+}
+
 extern "C" int arp_label_host(ArpHandle* h, const uint8_t* ob_host, int64_t T, int64_t row_stride_bytes,
                               const int64_t* ep_offsets_host, int32_t n_eps, int32_t num_frames, float* reward_host,
                               float* rtg_host, float* reward_stacked_host, float* rtg_stacked_host) {
@@ -1369,14 +1391,7 @@ extern "C" int arp_label_host(ArpHandle* h, const uint8_t* ob_host, int64_t T, i
   const size_t frame_bytes = (size_t)c.in_h * c.in_w * 3;
   const int64_t B = c.max_batch;
   const int F = num_frames;
-  if (h->stage_bytes < frame_bytes * B) {
-    for (int i = 0; i < 2; ++i) {
-      if (h->stage_dev[i]) cudaFree(h->stage_dev[i]);
-      h->stage_dev[i] = nullptr;
-      ARP_CUDA(h, cudaMalloc((void**)&h->stage_dev[i], frame_bytes * B));
-    }
-    h->stage_bytes = frame_bytes * B;
-  }
+  ARP_TRY(ensure_stage(h));
   // device outputs (scratch slot 1): [ep_off (n_eps+1) i64][reward T][rtg T][reward_stacked T*F][rtg_stacked T*F]
   const size_t off_bytes = (((size_t)(n_eps + 1) * 8) + 255) & ~(size_t)255;
   ARP_TRY(ensure_scratch(h, 1, off_bytes + (size_t)T * 4 * (2 + 2 * F) + 1024));
@@ -1426,6 +1441,67 @@ extern "C" int arp_label_host(ArpHandle* h, const uint8_t* ob_host, int64_t T, i
   cudaStreamSynchronize(h->copy_stream);
   cudaStreamSynchronize(st);
   return rc;
+}
+
+// Latency mode (envs/vl_reward.py: one frame per environment step). The whole kernel sequence for n frames is
+// captured once into a CUDA graph (~100 launches become one submission); per call: H2D of the frames, graph
+// launch, D2H of the results, one synchronisation.
+extern "C" int arp_online_reward(ArpHandle* h, const uint8_t* ob_host, int32_t n, float* reward_host,
+                                 float* logits_host, float* feat_host) {
+  if (!h) return ARP_ERR_INVALID;
+  cudaStream_t st = h->own_stream;
+  const ArpConfig& c = h->cfg;
+  const size_t frame_bytes = (size_t)c.in_h * c.in_w * 3;
+  if (n < 1 || n > c.max_batch) return fail(h, ARP_ERR_INVALID, "n must be in [1, max_batch=%d]", c.max_batch);
+  ARP_TRY(check_ready(h, ob_host, n, (int64_t)frame_bytes, st));
+  const bool text_head = !h->goal;
+  if (text_head && !h->text) return fail(h, ARP_ERR_STATE, "arp_set_text has not been called");
+  if (!text_head && (reward_host || logits_host))
+    return fail(h, ARP_ERR_INVALID, "goal-conditioned heads produce features only (reward = -||f - f_goal||, vl_reward.py:26-41)");
+  ARP_TRY(ensure_stage(h));
+  const size_t per = 1 + HEAD_MAX_TEXT + (size_t)h->feat_dim;
+  if (!h->online_out) ARP_TRY(dev_alloc(h, &h->online_out, per * c.max_batch));
+  float* d_r = h->online_out;
+  float* d_lg = d_r + c.max_batch;
+  float* d_f = d_lg + (size_t)c.max_batch * HEAD_MAX_TEXT;
+  auto run = [&]() -> int {
+    ARP_TRY(encode_chunk(h, 0, h->stage_dev[0], n, (int64_t)frame_bytes, st));
+    ARP_TRY(head_chunk(h, 0, n, text_head ? d_r : nullptr, text_head ? d_lg : nullptr, d_f, st));
+    if (h->adapter) {
+      l2_normalize_rows_kernel<<<(unsigned)((n + 7) / 8), 256, 0, st>>>(d_f, h->feat_dim, n);
+      h->launches++;
+    }
+    return ARP_OK;
+  };
+  ARP_CUDA(h, cudaMemcpyAsync(h->stage_dev[0], ob_host, frame_bytes * n, cudaMemcpyHostToDevice, st));
+  if (h->profiling) {
+    ARP_TRY(run());
+  } else {
+    ArpHandle::OnlineGraph& g = h->online_graphs[n];
+    if (!g.exec || g.epoch != h->online_epoch) {
+      if (g.exec) { cudaGraphExecDestroy(g.exec); g.exec = nullptr; }
+      const int64_t l0 = h->launches;
+      cudaGraph_t graph = nullptr;
+      ARP_CUDA(h, cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+      const int rc = run();
+      const cudaError_t e = cudaStreamEndCapture(st, &graph);
+      if (rc != ARP_OK) { if (graph) cudaGraphDestroy(graph); return rc; }
+      if (e != cudaSuccess) return fail(h, ARP_ERR_CUDA, "graph capture failed: %s", cudaGetErrorString(e));
+      const cudaError_t ei = cudaGraphInstantiate(&g.exec, graph, 0);
+      cudaGraphDestroy(graph);
+      if (ei != cudaSuccess) { g.exec = nullptr; return fail(h, ARP_ERR_CUDA, "cudaGraphInstantiate failed: %s", cudaGetErrorString(ei)); }
+      g.launches = h->launches - l0;
+      g.epoch = h->online_epoch;
+      h->launches = l0;
+    }
+    ARP_CUDA(h, cudaGraphLaunch(g.exec, st));
+    h->launches += g.launches;
+  }
+  if (reward_host) ARP_CUDA(h, cudaMemcpyAsync(reward_host, d_r, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
+  if (logits_host) ARP_CUDA(h, cudaMemcpyAsync(logits_host, d_lg, (size_t)n * h->n_text * 4, cudaMemcpyDeviceToHost, st));
+  if (feat_host) ARP_CUDA(h, cudaMemcpyAsync(feat_host, d_f, (size_t)n * h->feat_dim * 4, cudaMemcpyDeviceToHost, st));
+  ARP_CUDA(h, cudaStreamSynchronize(st));
+  return ARP_OK;
 }
 
 // ------------------------------------------------------------------------------------------------

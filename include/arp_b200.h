@@ -133,6 +133,16 @@ ARP_API int arp_label_host(ArpHandle* h, const uint8_t* ob_host, int64_t T, int6
                    const int64_t* ep_offsets_host, int32_t n_eps, int32_t num_frames, float* reward_host,
                    float* rtg_host, float* reward_stacked_host, float* rtg_stacked_host);
 
+/* Latency mode — the online reward of a rollout (arp_dt/envs/vl_reward.py:11-23 get_torch_clip_reward, :44-59
+ * get_torch_clip_adapter_reward, and the two encode_image calls of the goal-conditioned variants :26-41, :62-77;
+ * called once per environment step from envs/rollout_procgen.py:133-150). Scores n (1..max_batch) HOST frames
+ * uint8 [n,H,W,3] and returns, each optional: reward [n] (row 0 or the mean over texts, per ArpConfig.reduce),
+ * logits [n, n_text], features [n, feat_dim] (CLIP: un-normalised encode_image; adapter heads: normalised).
+ * The kernel sequence is captured into a CUDA graph on first use per n; the call synchronises. Goal heads give
+ * features only (the caller takes -||f_obs - f_goal||). */
+ARP_API int arp_online_reward(ArpHandle* h, const uint8_t* ob_host, int32_t n, float* reward_host, float* logits_host,
+                      float* feat_host);
+
 /* compute_reward only (label_reward.py:132-146 / :200-230): per-frame rewards, optional [T,n_text] logits. */
 ARP_API int arp_compute_reward(ArpHandle* h, const uint8_t* ob_dev, int64_t T, int64_t row_stride_bytes, float* reward_dev,
                        float* logits_dev, void* stream);

@@ -294,6 +294,60 @@ class AdapterOracle:
 
 
 # ---------------------------------------------------------------------------------------------------
+# (f)1: online reward of a rollout                    arp_dt/envs/vl_reward.py:11-77, rollout_procgen.py:133-150
+# ---------------------------------------------------------------------------------------------------
+def _online_image(obs: np.ndarray) -> torch.Tensor:
+    """preprocess(Image.fromarray(obs)).unsqueeze(0) with clip.load's preprocess (= _transform(224))."""
+    return transform_pil(False)(np.asarray(obs)).unsqueeze(0)
+
+
+def _online_crop(obs: np.ndarray) -> np.ndarray:
+    """center_crop(obs[None], (obs.shape[0] // 2, obs.shape[0] // 2))[0]                      (vl_reward.py:13-14)"""
+    return center_crop_np(obs[None, ...], (obs.shape[0] // 2, obs.shape[0] // 2))[0]
+
+
+@torch.no_grad()
+def online_clip_reward(model, obs: np.ndarray, pos_text, use_crop: bool = False) -> np.ndarray:
+    """get_torch_clip_reward (vl_reward.py:11-23): list text -> mean over texts, str -> row 0; float32 [1]."""
+    if use_crop:
+        obs = _online_crop(obs)
+    tokens = clip_shim.tokenize(pos_text)
+    _, logits_per_text = model(_online_image(obs), tokens)
+    r = logits_per_text.mean(axis=0) if isinstance(pos_text, list) else logits_per_text[0]
+    return r.float().cpu().numpy()
+
+
+@torch.no_grad()
+def online_goal_reward(encode_image, obs: np.ndarray, goal_image: np.ndarray, use_crop: bool = False) -> float:
+    """get_torch_clip_goal_conditioned_reward / ..._adapter_goal_conditioned_reward (vl_reward.py:26-41, :62-77).
+    Quirk kept: with use_crop the goal is cropped with the ALREADY CROPPED obs' size, i.e. to H/4 (:29-30)."""
+    if use_crop:
+        obs = _online_crop(obs)
+        goal_image = center_crop_np(goal_image[None, ...], (obs.shape[0] // 2, obs.shape[0] // 2))[0]
+    f, g = encode_image(_online_image(obs)), encode_image(_online_image(goal_image))
+    return -1 * torch.norm(f - g).item()
+
+
+@torch.no_grad()
+def online_adapter_reward(adapter: "AdapterOracle", obs: np.ndarray, pos_text, use_crop: bool = False) -> np.ndarray:
+    """get_torch_clip_adapter_reward (vl_reward.py:44-59): CLIP's PIL preprocess, the adapter's encoders."""
+    if use_crop:
+        obs = _online_crop(obs)
+    tokens = clip_shim.tokenize(pos_text)
+    fi, ft = adapter.encode_image(_online_image(obs)), adapter.encode_text(tokens)
+    logit = (adapter.logit_scale.exp() * (fi @ ft.T)).t()
+    r = logit.mean(axis=0) if isinstance(pos_text, list) else logit[0]
+    return r.float().cpu().numpy()
+
+
+def update_rtg(rtg: float, clip_reward, scale: float, reward_min: float = 0.0, use_normalize: bool = False):
+    """rollout_procgen.py:147-150: the return-to-go token the policy is conditioned on at the next step."""
+    if use_normalize:
+        return rtg - (clip_reward - reward_min) / scale
+    return rtg - clip_reward / scale
+
+
+# ---------------------------------------------------------------------------------------------------
 # the whole labeler                                                          label_reward.py:44-291
 # ---------------------------------------------------------------------------------------------------
 def label_reward_port(data: dict, *, model=None, adapter: AdapterOracle | None = None, model_type: str = "clip",

@@ -28,7 +28,8 @@ def test_library_exports_every_declared_symbol(built_lib):
     out = subprocess.run(["nm", "-D", "--defined-only", str(built_lib)], capture_output=True, text=True).stdout
     exported = set(re.findall(r" T (\w+)", out))
     assert exported == set(declared_symbols()), "library must export exactly the declared C ABI"
-    assert lib.arp_abi_version() == 1
+    header = (Path(__file__).resolve().parents[1] / "include" / "arp_b200.h").read_text()
+    assert lib.arp_abi_version() == int(re.search(r"#define ARP_B200_ABI_VERSION (\d+)", header).group(1))
 
 
 def test_sass_is_blackwell_native(built_lib):
