@@ -30,7 +30,8 @@ EXPORTS = (
     "arp_create", "arp_destroy", "arp_last_error", "arp_abi_version", "arp_set_weight", "arp_missing_weights",
     "arp_set_text", "arp_label", "arp_label_host", "arp_compute_reward", "arp_encode_image", "arp_decode_only",
     "arp_scan_only", "arp_gemm_bf16", "arp_layernorm_bf16", "arp_attention", "arp_launch_count",
-    "arp_profile_begin", "arp_profile_end", "arp_online_reward",
+    "arp_profile_begin", "arp_profile_end", "arp_online_reward", "arp_preprocess_rtgs",
+    "arp_quantile_f32",
 )
 PROFILE_CLASSES = ("gemm", "attention", "layernorm", "decode", "head", "scan", "other")
 
@@ -82,6 +83,8 @@ def load_library() -> C.CDLL:
     lib.arp_label_host.argtypes = [vp, vp, i64, i64, vp, i32, i32, vp, vp, vp, vp]
     lib.arp_compute_reward.argtypes = [vp, vp, i64, i64, vp, vp, vp]
     lib.arp_online_reward.argtypes = [vp, vp, i32, vp, vp, vp]
+    lib.arp_preprocess_rtgs.argtypes = [vp, vp, i64, vp, i32, i32, i32, vp, vp, vp, vp, vp]
+    lib.arp_quantile_f32.argtypes = [vp, vp, i64, i64, i64, vp, vp]
     lib.arp_encode_image.argtypes = [vp, vp, i64, i64, vp, vp]
     lib.arp_decode_only.argtypes = [vp, vp, i64, i64, vp, vp]
     lib.arp_scan_only.argtypes = [vp, vp, i64, vp, i32, i32, f32, vp, vp, vp, vp]
@@ -274,6 +277,29 @@ class Engine:
             ft = out["features"] = np.empty((n, self.feat_dim), np.float32)
         p = lambda a: None if a is None else C.c_void_p(a.ctypes.data)  # noqa: E731
         self._check(self._lib.arp_online_reward(self._h, p(f), n, p(r), p(lg), p(ft)))
+        return out
+
+    def preprocess_rtgs(self, reward: torch.Tensor, ep_offsets: torch.Tensor, num_frames: int, use_normalize: bool):
+        """data_procgen.py:142-168 on the device: returns (rtg_stacked [T,F] device tensor, rtg [T],
+        (reward_min, reward_max, rtg_min, rtg_max) as np.float32)."""
+        r = reward.to(self.device, torch.float32).contiguous()
+        off = ep_offsets.to(self.device, torch.int64).contiguous()
+        T = r.numel()
+        g = torch.zeros(T, device=self.device, dtype=torch.float32)
+        gs = torch.zeros(T, num_frames, device=self.device, dtype=torch.float32)
+        shifted = torch.empty(T, device=self.device, dtype=torch.float32) if use_normalize else None
+        stats = np.zeros(4, np.float32)
+        self._check(self._lib.arp_preprocess_rtgs(self._h, _ptr(r), T, _ptr(off), off.numel() - 1, num_frames,
+                                                  int(bool(use_normalize)), _ptr(shifted), _ptr(g), _ptr(gs),
+                                                  C.c_void_p(stats.ctypes.data), _stream_ptr(self.device)))
+        return gs, g, stats
+
+    def order_statistics(self, x: torch.Tensor, k_lo: int, k_hi: int) -> np.ndarray:
+        """The k_lo-th and k_hi-th smallest values (0-based) of a device float32 tensor, exactly."""
+        x = x.to(self.device, torch.float32).contiguous().view(-1)
+        out = np.zeros(2, np.float32)
+        self._check(self._lib.arp_quantile_f32(self._h, _ptr(x), x.numel(), int(k_lo), int(k_hi),
+                                               C.c_void_p(out.ctypes.data), _stream_ptr(self.device)))
         return out
 
     def encode_image(self, ob: torch.Tensor) -> torch.Tensor:

@@ -23,6 +23,7 @@
 #include "gemm2_tcgen05.cuh"
 #include "head.cuh"
 #include "layernorm.cuh"
+#include "rtgstats.cuh"
 #include "scan.cuh"
 
 using namespace arp;
@@ -171,6 +172,7 @@ struct ArpHandle {
   std::map<int, OnlineGraph> online_graphs;
   uint64_t online_epoch = 1;
   float* online_out = nullptr;   // device [max_batch * (1 + HEAD_MAX_TEXT + feat_dim)]
+  void* stats_dev = nullptr;     // RadixSelectState + min/max keys + 8 result floats (consumer-side statistics)
 
   // optional per-kernel-class timing (arp_profile_begin/end): CUDA events bracket every launch on its stream
   bool profiling = false;
@@ -1441,6 +1443,96 @@ extern "C" int arp_label_host(ArpHandle* h, const uint8_t* ob_host, int64_t T, i
   cudaStreamSynchronize(h->copy_stream);
   cudaStreamSynchronize(st);
   return rc;
+}
+
+// ------------------------------------------------------------------------------------------------
+// C ABI: consumer side (ProcgenDataset.preprocess_rtgs, data_procgen.py:132-174)
+// ------------------------------------------------------------------------------------------------
+struct StatsDev {
+  RadixSelectState sel;
+  uint32_t mm[2];
+  float res[8];   // [0] min [1] max | [2] rtg min [3] rtg max | [4] q_lo [5] q_hi
+};
+
+static int ensure_stats(ArpHandle* h) {
+  if (h->stats_dev) return ARP_OK;
+  uint8_t* p = nullptr;
+  ARP_TRY(dev_alloc(h, &p, sizeof(StatsDev)));
+  h->stats_dev = p;
+  return ARP_OK;
+}
+
+static int launch_minmax(ArpHandle* h, const float* x, int64_t n, float* res2, cudaStream_t st) {
+  StatsDev* sd = static_cast<StatsDev*>(h->stats_dev);
+  const uint32_t init[2] = {0xffffffffu, 0u};
+  ARP_CUDA(h, cudaMemcpyAsync(sd->mm, init, sizeof(init), cudaMemcpyHostToDevice, st));
+  const int blocks = (int)std::min<int64_t>((n + 255) / 256, kNumSMs * 8);
+  minmax_f32_kernel<<<blocks, 256, 0, st>>>(x, n, sd->mm);
+  minmax_finish_kernel<<<1, 1, 0, st>>>(sd->mm, res2);
+  h->launches += 2;
+  return ARP_OK;
+}
+
+static int launch_select(ArpHandle* h, const float* x, int64_t n, uint64_t k0, uint64_t k1, float* res2, cudaStream_t st) {
+  StatsDev* sd = static_cast<StatsDev*>(h->stats_dev);
+  const int blocks = (int)std::min<int64_t>((n + 255) / 256, kNumSMs * 8);
+  radix_select_init_kernel<<<1, 256, 0, st>>>(&sd->sel, k0, k1);
+  h->launches++;
+  for (int pass = 0; pass < 4; ++pass) {
+    radix_select_hist_kernel<<<blocks, 256, 0, st>>>(x, n, &sd->sel, pass);
+    radix_select_pick_kernel<<<1, 256, 0, st>>>(&sd->sel, pass, res2);
+    h->launches += 2;
+  }
+  ARP_CUDA(h, cudaGetLastError());
+  return ARP_OK;
+}
+
+extern "C" int arp_quantile_f32(ArpHandle* h, const float* x_dev, int64_t n, int64_t k_lo, int64_t k_hi,
+                                float* lo_hi_host, void* stream) {
+  if (!h || !x_dev || !lo_hi_host) return fail(h, ARP_ERR_INVALID, "null argument");
+  if (n < 1 || k_lo < 0 || k_hi < 0 || k_lo >= n || k_hi >= n) return fail(h, ARP_ERR_INVALID, "ranks must be in [0, n)");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  ARP_CUDA(h, cudaSetDevice(h->cfg.device));
+  ARP_TRY(ensure_stats(h));
+  StatsDev* sd = static_cast<StatsDev*>(h->stats_dev);
+  ProfScope prof(h, PC_SCAN, 0.0, (double)n * 4 * 4, st);
+  ARP_TRY(launch_select(h, x_dev, n, (uint64_t)k_lo, (uint64_t)k_hi, sd->res + 4, st));
+  ARP_CUDA(h, cudaMemcpyAsync(lo_hi_host, sd->res + 4, 8, cudaMemcpyDeviceToHost, st));
+  ARP_CUDA(h, cudaStreamSynchronize(st));
+  return ARP_OK;
+}
+
+extern "C" int arp_preprocess_rtgs(ArpHandle* h, const float* reward_dev, int64_t T, const int64_t* ep_offsets_dev,
+                                   int32_t n_eps, int32_t num_frames, int32_t use_normalize, float* shifted_dev,
+                                   float* rtg_dev, float* rtg_stacked_dev, float* stats_host, void* stream) {
+  if (!h || !reward_dev || !ep_offsets_dev || !rtg_dev || !rtg_stacked_dev || !stats_host)
+    return fail(h, ARP_ERR_INVALID, "null argument");
+  if (T < 1 || n_eps < 1) return fail(h, ARP_ERR_INVALID, "empty dataset");
+  if (use_normalize && !shifted_dev) return fail(h, ARP_ERR_INVALID, "use_normalize needs a [T] scratch buffer");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  ARP_CUDA(h, cudaSetDevice(h->cfg.device));
+  ARP_TRY(ensure_stats(h));
+  StatsDev* sd = static_cast<StatsDev*>(h->stats_dev);
+  ARP_TRY(launch_minmax(h, reward_dev, T, sd->res, st));                      // data_procgen.py:147-148: over ALL rows
+  const float* r = reward_dev;
+  if (use_normalize) {                                                        // :150-151
+    sub_scalar_f32_kernel<<<(int)std::min<int64_t>((T + 255) / 256, kNumSMs * 8), 256, 0, st>>>(reward_dev, sd->res,
+                                                                                              shifted_dev, T);
+    h->launches++;
+    r = shifted_dev;
+  }
+  // :155-168 — discount_cumsum(gamma=1.0) and the deque window, identical to the labeler's scan + stack
+  ARP_TRY(scan_launch(h, r, T, ep_offsets_dev, n_eps, num_frames, 1.0f, rtg_dev, nullptr, rtg_stacked_dev, st));
+  // the stacked values are a gather of rtg: min / max over the labeled rows of rtg = over the stacked array (:171)
+  int64_t off_last = 0;
+  ARP_CUDA(h, cudaMemcpyAsync(&off_last, ep_offsets_dev + n_eps, 8, cudaMemcpyDeviceToHost, st));
+  ARP_CUDA(h, cudaStreamSynchronize(st));
+  const int64_t rows = std::min<int64_t>(off_last, T);
+  if (rows < 1) return fail(h, ARP_ERR_INVALID, "no labeled rows");
+  ARP_TRY(launch_minmax(h, rtg_dev, rows, sd->res + 2, st));
+  ARP_CUDA(h, cudaMemcpyAsync(stats_host, sd->res, 16, cudaMemcpyDeviceToHost, st));
+  ARP_CUDA(h, cudaStreamSynchronize(st));
+  return ARP_OK;
 }
 
 // Latency mode (envs/vl_reward.py: one frame per environment step). The whole kernel sequence for n frames is

@@ -143,6 +143,22 @@ ARP_API int arp_label_host(ArpHandle* h, const uint8_t* ob_host, int64_t T, int6
 ARP_API int arp_online_reward(ArpHandle* h, const uint8_t* ob_host, int32_t n, float* reward_host, float* logits_host,
                       float* feat_host);
 
+/* Consumer side — ProcgenDataset.preprocess_rtgs (arp_dt/data_procgen.py:132-174), which turns the labeler's
+ * per-frame rewards into the return-to-go tokens and the conditioning statistic of DT training:
+ *   reward_dev [T] fp32 (column -1 of the "<key>_<vl_type>_pos_reward" dataset, :142-146)
+ *   stats_host[0..1] = min, max of the rewards over all T rows (:147-148)
+ *   use_normalize: shifted_dev [T] = reward - min (:150-151), and the scan runs on it
+ *   rtg_dev [T], rtg_stacked_dev [T, num_frames]: per-episode discount_cumsum(gamma=1) + window stack (:155-168)
+ *   stats_host[2..3] = min, max over the stacked return-to-go values (:171, CoinRun's return_to_go before //100*100)
+ * Synchronises. The 0.9-quantile branch (:173) takes its two order statistics from arp_quantile_f32. */
+ARP_API int arp_preprocess_rtgs(ArpHandle* h, const float* reward_dev, int64_t T, const int64_t* ep_offsets_dev,
+                        int32_t n_eps, int32_t num_frames, int32_t use_normalize, float* shifted_dev, float* rtg_dev,
+                        float* rtg_stacked_dev, float* stats_host, void* stream);
+/* Exact order statistics of n device floats: lo_hi_host[0] = k_lo-th smallest, [1] = k_hi-th smallest (0-based),
+ * by MSB-first radix select. np.quantile(x, q) (data_procgen.py:173) interpolates between the two. Synchronises. */
+ARP_API int arp_quantile_f32(ArpHandle* h, const float* x_dev, int64_t n, int64_t k_lo, int64_t k_hi, float* lo_hi_host,
+                     void* stream);
+
 /* compute_reward only (label_reward.py:132-146 / :200-230): per-frame rewards, optional [T,n_text] logits. */
 ARP_API int arp_compute_reward(ArpHandle* h, const uint8_t* ob_dev, int64_t T, int64_t row_stride_bytes, float* reward_dev,
                        float* logits_dev, void* stream);

@@ -348,6 +348,48 @@ def update_rtg(rtg: float, clip_reward, scale: float, reward_min: float = 0.0, u
 
 
 # ---------------------------------------------------------------------------------------------------
+# (f)2: consumer side                       arp_dt/data_procgen.py:132-174 (preprocess_rtgs), utils.py:453-463
+# ---------------------------------------------------------------------------------------------------
+def compute_scale(return_to_go):
+    """arp_dt/utils.py:453-463."""
+    if return_to_go >= 0:
+        max_digit = int(str(int(return_to_go))[0])
+    else:
+        max_digit = int(str(int(return_to_go))[1])
+    if return_to_go >= 0:
+        n = len(str(int(return_to_go))) - 1 if max_digit < 5 else len(str(int(return_to_go)))
+    else:
+        n = len(str(int(return_to_go))) - 2 if max_digit < 5 else len(str(int(return_to_go))) - 1
+    return pow(10, n)
+
+
+def preprocess_rtgs(rewards: dict, traj_idx, num_frames: int, env_name: str, use_normalize: bool) -> dict:
+    """ProcgenDataset.preprocess_rtgs (data_procgen.py:132-174) with the h5 reads factored out:
+    rewards[image_key] = h5_file[f"{image_key}_{vl_type}_pos_reward"][:, -1].astype(np.float32) (:142-146)."""
+    reward_min = {k: np.min(r) for k, r in rewards.items()}                              # :147
+    reward_max = {k: np.max(r) for k, r in rewards.items()}                              # :148
+    modified = {k: (r - reward_min[k]) for k, r in rewards.items()} if use_normalize else rewards   # :150-153
+    out = {k: [] for k in rewards}
+    for k in out:                                                                         # :155-168
+        for idx in range(len(traj_idx) - 1):
+            stack = deque([], maxlen=num_frames)
+            ids = list(range(traj_idx[idx], traj_idx[idx + 1]))
+            cs = discount_cumsum(modified[k][ids], gamma=1.0)
+            for i in range(len(ids)):
+                if i == 0:
+                    stack.extend([cs[i]] * num_frames)
+                else:
+                    stack.append(cs[i])
+                out[k].append(np.stack(stack))
+    if "coinrun" in env_name:                                                             # :171-174
+        rtg = np.max(list(out.values())) // 100 * 100
+    else:
+        rtg = np.quantile(list(out.values()), 0.9) // 100 * 100
+    return {"rtgs": {k: np.asarray(v) for k, v in out.items()}, "reward_min": reward_min, "reward_max": reward_max,
+            "return_to_go": rtg, "scale": compute_scale(rtg)}
+
+
+# ---------------------------------------------------------------------------------------------------
 # the whole labeler                                                          label_reward.py:44-291
 # ---------------------------------------------------------------------------------------------------
 def label_reward_port(data: dict, *, model=None, adapter: AdapterOracle | None = None, model_type: str = "clip",
