@@ -13,7 +13,7 @@ import numpy as np
 import torch
 
 _PKG = Path(__file__).resolve().parent
-_LIB_PATH = _PKG / "_lib" / "libarp_b200.so"
+_LIB_PATH = Path(os.environ.get("ARP_B200_LIB") or _PKG / "_lib" / "libarp_b200.so")   # env override: dev builds only
 
 ARP_OK = 0
 ARP_ERR_INVALID, ARP_ERR_CUDA, ARP_ERR_STATE, ARP_ERR_NO_DEVICE, ARP_ERR_UNKNOWN_KEY = -1, -2, -3, -4, -5

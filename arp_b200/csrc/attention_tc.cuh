@@ -97,7 +97,8 @@ __device__ __forceinline__ void tmem_st_32x16(uint32_t taddr, const uint32_t (&r
 template <int L>
 __global__ void __launch_bounds__(ATC_THREADS, 1)
 attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_kv,
-                    __nv_bfloat16* __restrict__ out, int n_frames, int heads, int width, float scale_log2e) {
+                    __nv_bfloat16* __restrict__ out, int n_frames, int heads, int width, float scale_log2e,
+                    int reverse) {
   using C = AtcCfg<L>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -143,7 +144,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
       const uint32_t ph = (it >> 1) & 1;
       mbar_wait(&smem_empty[b], ph ^ 1);
       if (lane == 0) {
-        const int frame = item / heads, head = item - frame * heads;
+        const int item_o = reverse ? n_items - 1 - item : item;   // snake order across kernels (L2 reuse)
+        const int frame = item_o / heads, head = item_o - frame * heads;
         uint8_t* buf = smem + b * C::BUF_BYTES;
         const int row = frame * L;
         mbar_arrive_expect_tx(&smem_full[b], C::TX_BYTES);
@@ -210,7 +212,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
     uint32_t it = 0;
     for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
       const uint32_t ph = it & 1;
-      const int frame = item / heads, head = item - frame * heads;
+      const int item_o = reverse ? n_items - 1 - item : item;
+      const int frame = item_o / heads, head = item_o - frame * heads;
       mbar_wait(&s_full[qt], ph);
       tc_fence_after();
       // Only the last (partial or padded) chunk can contain key columns >= L; the others need no masking.

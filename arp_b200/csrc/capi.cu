@@ -109,6 +109,10 @@ struct ArpHandle {
   // numerically equivalent, but the register-path residual epilogue (gemm2 MODE 2) is latency-bound on the x loads
   // (out_proj 137 -> 236 us), which cancels the 2 x 63 us of LN kernels it removes; kept off until MODE 2 stages x by TMA.
   int ln_fold = 0;
+  // Snake order: consecutive kernels of a chunk walk the rows in opposite directions, so each starts on what its
+  // predecessor wrote last (the tail of a 150-600 MB activation is still in the 126 MB L2). ARP_SNAKE=0 disables.
+  bool snake = true;
+  int dir = 0;
   bool f32 = false;   // cfg.precision == ARP_PREC_F32: verification path (fp32_path.cuh); GEMM weights are stored as fp32
   int attn_impl = 2;  // 1 = mma.sync kernel, 2 = tcgen05 kernel (ARP_ATTN_IMPL overrides)
   int gemm_impl = 3;  // 1 = v1 (register stores), 2 = v2 single-CTA, 3 = v2 CTA pairs (ARP_GEMM_IMPL overrides)
@@ -503,6 +507,7 @@ extern "C" int arp_create(const ArpConfig* cfg, ArpHandle** out) {
   if (const char* e = getenv("ARP_GEMM_IMPL")) h->gemm_impl = atoi(e);
   if (h->gemm_impl < 1 || h->gemm_impl > 3) h->gemm_impl = 3;
   if (const char* e = getenv("ARP_ATTN_IMPL")) h->attn_impl = atoi(e) == 1 ? 1 : 2;
+  if (const char* e = getenv("ARP_SNAKE")) h->snake = atoi(e) != 0;
   if (const char* e = getenv("ARP_LN_FOLD")) h->ln_fold = std::max(0, std::min(2, atoi(e)));
   if (h->gemm_impl < 2 || h->f32) h->ln_fold = 0;   // the fold lives in the v2 epilogue
   h->grid = DEC_OUT / cfg->patch;
@@ -858,6 +863,7 @@ static int launch_gemm(ArpHandle* h, const bf16* a, int64_t a_rows_alloc, const 
   g.M = (int)M; g.N = N; g.K = K; g.out = out; g.ldo = ldo; g.bias = bias; g.resid = resid; g.ldr = ldr;
   g.rowtab = rowtab; g.period = period > 0 ? period : 1;
   g.eps = 1e-5f;
+  g.reverse = h->snake ? (h->dir ^= 1) : 0;
   if (fold) {
     if (h->gemm_impl < 2) return fail(h, ARP_ERR_INVALID, "the LayerNorm fold needs the v2 GEMM");
     g.xb = fold->xb; g.stats_out = fold->stats_out; g.stats_in = fold->stats_in; g.stats_nh = K / 128;
@@ -921,7 +927,8 @@ static int launch_ln_bf16(ArpHandle* h, const float* x, const float* g, const fl
                           cudaStream_t st) {
   if (M <= 0) return ARP_OK;
   ProfScope prof(h, PC_LAYERNORM, 0.0, (double)M * 768 * 6, st);
-  layernorm_f32_bf16_kernel<768><<<(unsigned)((M + 7) / 8), 256, 0, st>>>(x, g, b, y, (int)M, 1e-5f);
+  layernorm_f32_bf16_kernel<768><<<(unsigned)((M + 7) / 8), 256, 0, st>>>(x, g, b, y, (int)M, 1e-5f,
+                                                                         h->snake ? (h->dir ^= 1) : 0);
   h->launches++;
   ARP_CUDA(h, cudaGetLastError());
   return ARP_OK;
@@ -942,10 +949,11 @@ static int launch_attention(ArpHandle* h, const bf16* qkv, bf16* out, int B, int
     ARP_TRY(get_tmap(h, qkv, rows, 3 * W, 3 * W, 128, &tq));
     ARP_TRY(get_tmap(h, qkv, rows, 3 * W, 3 * W, nk, &tkv));
     const int grid = std::min(B * h->cfg.heads, kNumSMs);
+    const int rev = h->snake ? (h->dir ^= 1) : 0;
     if (tokens == 197)
-      attention_tc_kernel<197><<<grid, ATC_THREADS, AtcCfg<197>::SMEM_BYTES, st>>>(*tq, *tkv, out, B, h->cfg.heads, W, scale_log2e);
+      attention_tc_kernel<197><<<grid, ATC_THREADS, AtcCfg<197>::SMEM_BYTES, st>>>(*tq, *tkv, out, B, h->cfg.heads, W, scale_log2e, rev);
     else
-      attention_tc_kernel<50><<<grid, ATC_THREADS, AtcCfg<50>::SMEM_BYTES, st>>>(*tq, *tkv, out, B, h->cfg.heads, W, scale_log2e);
+      attention_tc_kernel<50><<<grid, ATC_THREADS, AtcCfg<50>::SMEM_BYTES, st>>>(*tq, *tkv, out, B, h->cfg.heads, W, scale_log2e, rev);
     h->launches++;
     ARP_CUDA(h, cudaGetLastError());
     return ARP_OK;

@@ -29,13 +29,16 @@ __device__ __forceinline__ float quick_gelu(float x) {
 constexpr int G2_THREADS = 320;
 constexpr int G2_EPI_WARPS = 8;
 constexpr int G2_STAGE_UNIT = 32 * 128;  // one staging buffer: 32 rows x 128 B
-constexpr int G2_STAGING_BYTES = G2_EPI_WARPS * 2 * G2_STAGE_UNIT;  // 64 KB
+#ifndef G2_STAGE_BUFS
+#define G2_STAGE_BUFS 1                  // staging buffers per epilogue warp (1 frees 32 KB for a 6th pipeline stage)
+#endif
+constexpr int G2_STAGING_BYTES = G2_EPI_WARPS * G2_STAGE_BUFS * G2_STAGE_UNIT;
 
 template <int CG>
 struct G2Cfg {
   static constexpr int B_ROWS = GEMM_BN / CG;                       // W rows staged per CTA
   static constexpr int STAGE_BYTES = GEMM_A_BYTES + B_ROWS * GEMM_BK * 2;
-  static constexpr int STAGES = CG == 1 ? 3 : 5;
+  static constexpr int STAGES = CG == 1 ? 3 : (G2_STAGE_BUFS == 1 ? 6 : 5);
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + G2_STAGING_BYTES + 1024 + 256;
 };
 
@@ -98,7 +101,8 @@ gemm2_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gr
     int stage = 0;
     uint32_t phase = 0;
     for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
-      const int m_blk = tile / num_n, n_blk = tile % num_n;
+      const int tile_o = args.reverse ? num_tiles - 1 - tile : tile;
+      const int m_blk = tile_o / num_n, n_blk = tile_o % num_n;
       const int a_row = (m_blk * CG + rank) * GEMM_BM;
       const int b_row = n_blk * GEMM_BN + rank * Cfg::B_ROWS;
       for (int kb = 0; kb < num_kb; ++kb) {
@@ -165,7 +169,7 @@ gemm2_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gr
     const int ew = warp - 2;
     const int quarter = warp & 3;   // TMEM lane quarter this warp may touch
     const int half = ew >> 2;       // accumulator column half
-    uint8_t* my_stage = staging + ew * 2 * G2_STAGE_UNIT;
+    uint8_t* my_stage = staging + ew * G2_STAGE_BUFS * G2_STAGE_UNIT;
     constexpr int UNIT_COLS = sizeof(OutT) == 4 ? 32 : 64;   // 128 B per row
     constexpr int UNITS = 128 / UNIT_COLS;
     const uint32_t tempty_leader0 = CG == 2 ? mapa_u32(smem_u32(&tempty_bar[0]), 0) : 0;
@@ -184,7 +188,8 @@ gemm2_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gr
       }
     };
     for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
-      const int m_blk = tile / num_n, n_blk = tile % num_n;
+      const int tile_o = args.reverse ? num_tiles - 1 - tile : tile;
+      const int m_blk = tile_o / num_n, n_blk = tile_o % num_n;
       const int row0 = (m_blk * CG + rank) * GEMM_BM + quarter * 32;
       // MODE 2: the residual does not depend on the accumulator — its first unit is in flight while the MMAs finish,
       // and unit u+1 is requested before unit u is processed
@@ -279,7 +284,7 @@ gemm2_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gr
         // staging buffer `buf` was last read by the TMA store issued two units ago
         uint8_t* sbuf = my_stage + buf * G2_STAGE_UNIT;
         if (MODE != G2_RESID_LN) {
-          if (lane == 0) tma_store_wait_read<1>();
+          if (lane == 0) tma_store_wait_read<G2_STAGE_BUFS - 1>();
         }
         __syncwarp();
         uint4* srow = reinterpret_cast<uint4*>(sbuf + lane * 128);
@@ -326,7 +331,7 @@ gemm2_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gr
             tma_store_commit();
           }
         }
-        buf ^= 1;
+        buf ^= (G2_STAGE_BUFS - 1);
       }
       if (MODE == G2_RESID_LN) {
         // moments of this warp's 128 columns: reduce over the 8 lanes that share a row, one writer per row

@@ -29,6 +29,8 @@ struct GemmArgs {
   int ldr;
   const float* rowtab;  // fp32 [period, N] added to row (row % period), or nullptr (pos-emb + cls)
   int period;
+  int reverse;          // gemm2: walk the tiles from the last row block to the first (snake order across kernels,
+                        // so a kernel starts on the rows its predecessor wrote last — still in L2)
   // ---- LayerNorm fold (gemm2 MODE 2 / 3) ----
   // MODE 2 (residual + LN statistics): x = resid + acc + bias is written to `out` (fp32, may alias resid), a bf16
   //   copy to `xb` [M, N], and per-row partial moments (sum, sum of squares over each 128-column span) to

@@ -50,9 +50,11 @@ __device__ __forceinline__ void ln_row(const float* __restrict__ x, const float*
 template <int W>
 __global__ void __launch_bounds__(256)
 layernorm_f32_bf16_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
-                          const float* __restrict__ beta, __nv_bfloat16* __restrict__ y, int M, float eps) {
-  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+                          const float* __restrict__ beta, __nv_bfloat16* __restrict__ y, int M, float eps,
+                          int reverse) {
+  int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= M) return;
+  if (reverse) row = M - 1 - row;   // snake order across kernels: start on the rows the previous kernel wrote last
   const int lane = threadIdx.x & 31;
   RowRegs<W> r;
   ln_row<W>(x + static_cast<size_t>(row) * W, gamma, beta, eps, r);
