@@ -10,8 +10,21 @@
 //   MMA #2   O[128 x 64] = P V        A operand straight from TMEM, B = V from smem as an MN-major operand
 //   epilogue tcgen05.ld O, scale by 1/rowsum, bf16, one full 128-byte line per thread to HBM
 // TMEM map per query tile t (base = 256 t): S fp32 [base, base+208) -> P bf16x2 [base, base+104); O fp32 [base+128, base+192).
-// Warp roles (320 threads): 0 = TMA producer, 1 = MMA issuer + TMEM owner, 2..9 = softmax/epilogue
+// Warp roles (320 threads): 0 = TMA producer, 1 = TMEM owner (alloc / dealloc only), 2..9 = softmax / MMA issue / epilogue
 // (warps 2-5 own query tile 0, warps 6-9 query tile 1; a warp may only touch TMEM lanes 32*(warp%4)..+31).
+//
+// Scheduling (measured with the ARP_ATTN_TRACE timeline, tools/attn_trace.py; MUFU.EX2 = 8 clk per warp
+// instruction per SMSP, tools/micro/):
+//   * no MMA warp: the LAST softmax warp of a slot to finish its P rows issues P V, the last one to drain O issues
+//     the slot's next Q K^T (smem arrival counters). A dedicated MMA warp shares its SMSP with two softmax warps
+//     and took ~400 cycles to notice a barrier plus ~1000 to issue 13 MMAs;
+//   * everything the MMA issue needs is derived from a shuffled (provably warp-uniform) warp index, so the
+//     descriptors live in uniform registers: back-to-back UTCHMMA instead of an ELECT / R2UR.BROADCAST loop
+//     (75 cycles per MMA) in front of every one;
+//   * the exp2 pass is taken in turns per SMSP (xu_turn): the two slots' MUFU-bound passes never overlap, which
+//     keeps the slots half a period apart — one slot's row-max / P V / epilogue / Q K^T hide under the other's exp2;
+//   * the exp2 pass uses packed fp32x2 FMA/ADD and an integer round-and-merge for the bf16 pairs (F2FP would
+//     issue on the XU pipe, the one MUFU.EX2 needs).
 #pragma once
 
 #include "common.cuh"
@@ -74,6 +87,35 @@ __device__ __forceinline__ uint64_t umma_desc_mnmajor_sw128(uint32_t smem_addr) 
   return d;
 }
 
+// Packed fp32x2 arithmetic (sm_100): one issue slot for two elements. A lone warp issues at most every other cycle,
+// and the exp2 pass is issue-bound once its F2FP conversions are off the XU pipe — halving the FFMA / FADD count
+// is what lets the pass run at the MUFU rate (8 clk per warp instruction).
+__device__ __forceinline__ uint64_t f32x2_pack(float lo, float hi) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void f32x2_unpack(uint64_t v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ uint64_t f32x2_fma(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ uint64_t f32x2_add(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+// Two fp32 -> packed bf16 pair WITHOUT F2FP (which issues on the XU pipe, the same pipe as MUFU.EX2): adding 0x8000
+// to the bit pattern rounds the magnitude to nearest (ties away from zero; finite inputs), then the two high halves
+// are merged with a shift and a LOP3 on the ALU pipe.
+__device__ __forceinline__ uint32_t pack_bf16_int(float lo, float hi) {
+  const uint32_t a = __float_as_uint(lo) + 0x8000u, b = __float_as_uint(hi) + 0x8000u;
+  return (a >> 16) | (b & 0xffff0000u);
+}
+
 __device__ __forceinline__ float ex2_approx(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
@@ -89,6 +131,20 @@ __device__ __forceinline__ void tmem_st_32x16(uint32_t taddr, const uint32_t (&r
       : "memory");
 }
 
+#ifdef ARP_ATTN_TRACE
+// dev-only timeline of block 0: clock64 stamps kept in shared memory (a plain st.shared per event), dumped at exit.
+// events: 0 S_issue 1 PV_issue 2 S_ready 3 pass1_done 4 turn_acquired 5 P_arrive 6 O_ready 7 epilogue_done
+constexpr int ATC_TR_ITEMS = 10, ATC_TR_EVENTS = 10;
+__device__ long long g_attn_trace[2 * ATC_TR_ITEMS * ATC_TR_EVENTS];
+#define ATC_TRACE(ev, slot, item)                                                                              \
+  do {                                                                                                         \
+    if (blockIdx.x == 0 && (threadIdx.x & 31) == 0 && (item) < ATC_TR_ITEMS)                                   \
+      atc_tr[((slot) * ATC_TR_ITEMS + (item)) * ATC_TR_EVENTS + (ev)] = clock64();                             \
+  } while (0)
+#else
+#define ATC_TRACE(ev, slot, item)
+#endif
+
 // qkv: bf16 [rows, 3*width] (tensor maps: box 64x128 for Q, 64xNK for K/V); out: bf16 [B*L, width]
 //
 // Each query tile of an item is an independent "job" with its own TMEM slot (256 columns) and its own
@@ -103,16 +159,27 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 2 * C::BUF_BYTES);
-  uint64_t* smem_full = bars;        // [2] TMA -> MMA
-  uint64_t* smem_empty = bars + 2;   // [2] MMA (all P V of the item retired) -> TMA
-  uint64_t* s_full = bars + 4;       // [2 slots] MMA -> softmax: S ready
-  uint64_t* p_full = bars + 6;       // [2] softmax -> MMA: P written
-  uint64_t* o_full = bars + 8;       // [2] MMA -> epilogue: O ready
-  uint64_t* tmem_free = bars + 10;   // [2] epilogue -> MMA: O drained, slot reusable
+  uint64_t* smem_full = bars;        // [2] TMA -> Q K^T issuer: the item's Q/K/V have landed
+  uint64_t* smem_empty = bars + 2;   // [2] tensor core (all P V of the item retired) -> TMA
+  uint64_t* s_full = bars + 4;       // [2 slots] tensor core -> softmax warps: S ready
+  uint64_t* o_full = bars + 8;       // [2] tensor core -> epilogue: O ready
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
+  // exp2 turn per TMEM lane quarter (= per SMSP): the two softmax warps that share an SMSP take their MUFU-bound
+  // pass strictly in (item, slot) order, never both at once
+  volatile int* xu_turn = reinterpret_cast<volatile int*>(bars + 13);
+  // arrival counters per slot: the LAST softmax warp to finish its P rows issues P V itself, the last one to drain O
+  // issues the next item's Q K^T — no hand-off to a separate MMA warp (which, sharing an SMSP with a warp in its
+  // exp2 pass, took ~400 cycles to notice a barrier and ~1000 to get 13 MMA instructions issued)
+  int* cnt_p = reinterpret_cast<int*>(bars + 15);   // [2]
+  int* cnt_e = cnt_p + 2;                            // [2]
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // warp index through a shuffle: provably warp-uniform for the compiler, so everything derived from it (slot,
+  // TMEM addresses, descriptors) lives in uniform registers and an MMA issue is not an ELECT / R2UR.BROADCAST loop
+  const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
   const int n_items = n_frames * heads;
+#ifdef ARP_ATTN_TRACE
+  __shared__ long long atc_tr[2 * ATC_TR_ITEMS * ATC_TR_EVENTS];
+#endif
   constexpr int SM_WARPS = 4 * C::QT;   // softmax warps that actually own rows
 
   if (warp == 0 && lane == 0) {
@@ -124,17 +191,36 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
       mbar_init(&smem_full[i], 1);
       mbar_init(&smem_empty[i], C::QT);
       mbar_init(&s_full[i], 1);
-      mbar_init(&p_full[i], 4);
       mbar_init(&o_full[i], 1);
-      mbar_init(&tmem_free[i], 4);
     }
     fence_mbar_init();
   }
+  if (warp == 1 && lane < 4) { xu_turn[lane] = 0; cnt_p[lane] = 0; }   // cnt_p[0..1], cnt_e[0..1] are contiguous
   if (warp == 1) tmem_alloc<512>(tmem_slot);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
+
+  // ---- MMA issue (one elected thread of a softmax warp) ----
+  constexpr uint32_t idesc_s = umma_idesc_bf16(128, C::NK);          // Q K^T: both operands K-major
+  constexpr uint32_t idesc_o = umma_idesc_bf16(128, ATC_DH, 0, 1);   // P V: A from TMEM, B = V MN-major
+  auto issue_s = [&](uint32_t sbuf, int t) {
+    const uint64_t dk = umma_desc_kmajor_sw128(sbuf + C::QT * C::Q_BYTES);
+    const uint64_t dq = umma_desc_kmajor_sw128(sbuf + t * C::Q_BYTES);
+#pragma unroll
+    for (int k = 0; k < ATC_DH / 16; ++k)
+      umma_bf16_ss(tmem_base + t * 256, dq + 2 * k, dk + 2 * k, idesc_s, k != 0);
+    umma_commit(&s_full[t]);
+  };
+  auto issue_pv = [&](uint32_t sbuf, int t) {
+    const uint64_t dv = umma_desc_mnmajor_sw128(sbuf + C::QT * C::Q_BYTES + C::KV_PAD);
+#pragma unroll
+    for (int k = 0; k < C::NK / 16; ++k)
+      // 16 keys per MMA: A advances 8 packed columns, V advances 16 rows x 128 B = 2048 B
+      umma_bf16_ts(tmem_base + t * 256 + C::O_COL, tmem_base + t * 256 + k * 8, dv + k * (2048 >> 4), idesc_o, k != 0);
+    umma_commit(&o_full[t]);
+  };
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -157,51 +243,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
       }
       __syncwarp();
     }
-  } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    constexpr uint32_t idesc_s = umma_idesc_bf16(128, C::NK);          // Q K^T: both operands K-major
-    constexpr uint32_t idesc_o = umma_idesc_bf16(128, ATC_DH, 0, 1);   // P V: A from TMEM, B = V MN-major
-    auto issue_s = [&](uint32_t sbuf, int t) {
-      const uint64_t dk = umma_desc_kmajor_sw128(sbuf + C::QT * C::Q_BYTES);
-      const uint64_t dq = umma_desc_kmajor_sw128(sbuf + t * C::Q_BYTES);
-#pragma unroll
-      for (int k = 0; k < ATC_DH / 16; ++k)
-        umma_bf16_ss(tmem_base + t * 256, dq + 2 * k, dk + 2 * k, idesc_s, k != 0);
-      umma_commit(&s_full[t]);
-    };
-    auto issue_pv = [&](uint32_t sbuf, int t) {
-      const uint64_t dv = umma_desc_mnmajor_sw128(sbuf + C::QT * C::Q_BYTES + C::KV_PAD);
-#pragma unroll
-      for (int k = 0; k < C::NK / 16; ++k)
-        // 16 keys per MMA: A advances 8 packed columns, V advances 16 rows x 128 B = 2048 B
-        umma_bf16_ts(tmem_base + t * 256 + C::O_COL, tmem_base + t * 256 + k * 8, dv + k * (2048 >> 4), idesc_o, k != 0);
-      umma_commit(&o_full[t]);
-    };
-    uint32_t it = 0;
-    for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
-      const int b = it & 1;
-      const uint32_t ph_buf = (it >> 1) & 1, ph = it & 1;
-      const uint32_t sbuf = smem_u32(smem + b * C::BUF_BYTES);
-      mbar_wait(&smem_full[b], ph_buf);
-#pragma unroll
-      for (int t = 0; t < C::QT; ++t) {
-        mbar_wait(&tmem_free[t], ph ^ 1);     // previous item's O of this slot has been drained
-        tc_fence_after();
-        if (lane == 0) issue_s(sbuf, t);
-        __syncwarp();
-      }
-#pragma unroll
-      for (int t = 0; t < C::QT; ++t) {
-        mbar_wait(&p_full[t], ph);
-        tc_fence_after();
-        if (lane == 0) {
-          issue_pv(sbuf, t);
-          umma_commit(&smem_empty[b]);        // the item's smem is free once BOTH slots' P V have retired (count = QT)
-        }
-        __syncwarp();
-      }
-    }
-  } else if (warp - 2 < SM_WARPS) {
+  } else if (warp >= 2 && warp - 2 < SM_WARPS) {
     // ===================== softmax + epilogue: one thread per query row =====================
     const int qt = (warp - 2) >> 2;
     const int quarter = warp & 3;
@@ -209,6 +251,14 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
     const uint32_t t_s = tmem_base + qt * 256 + (static_cast<uint32_t>(quarter * 32) << 16);
     constexpr int NFULL = C::NK / 32;                    // full 32-column chunks
     constexpr int TAIL = C::NK % 32;                     // 16 or 0
+    const int n_mine = n_items > static_cast<int>(blockIdx.x) ? (n_items - 1 - static_cast<int>(blockIdx.x)) / static_cast<int>(gridDim.x) + 1 : 0;
+    if (quarter == 0 && n_mine > 0) {      // the slot's first Q K^T
+      mbar_wait(&smem_full[0], 0);
+      tc_fence_after();
+      if (elect_one()) issue_s(smem_u32(smem), qt);
+      ATC_TRACE(0, qt, 0);
+      __syncwarp();
+    }
     uint32_t it = 0;
     for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
       const uint32_t ph = it & 1;
@@ -216,6 +266,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
       const int frame = item_o / heads, head = item_o - frame * heads;
       mbar_wait(&s_full[qt], ph);
       tc_fence_after();
+      if (quarter == 0) ATC_TRACE(2, qt, it);
       // Only the last (partial or padded) chunk can contain key columns >= L; the others need no masking.
       constexpr int NCLEAN = (L / 32 < NFULL) ? L / 32 : NFULL;   // full chunks whose 32 columns are all real keys
       // ---- pass 1: row maximum over the L real keys (two 32-column loads in flight per wait) ----
@@ -259,22 +310,36 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
         }
       }
       const float mo = m * scale_log2e;
+      if (quarter == 0) ATC_TRACE(3, qt, it);
+      if (C::QT == 2) {     // wait for this warp's exp2 turn
+        const int my_turn = 2 * static_cast<int>(it) + qt;
+        if (xu_turn[quarter] != my_turn) {
+          const long long t0 = clock64();
+          while (xu_turn[quarter] != my_turn) {
+            if (clock64() - t0 > ARP_WATCHDOG_CYCLES) __trap();
+          }
+        }
+      }
       // ---- pass 2: p = exp2(s*scale - max*scale); P (bf16 pairs) overwrites the S columns it came from.
       //      Two register buffers ping-pong: the load of the next chunk is in flight while this one is processed. ----
+      if (quarter == 0) ATC_TRACE(4, qt, it);
       float sum0 = 0.f, sum1 = 0.f;
+      uint64_t sumA = f32x2_pack(0.f, 0.f), sumB = sumA;      // four partial row sums (two packed accumulators)
+      const uint64_t scale2 = f32x2_pack(scale_log2e, scale_log2e), nmo2 = f32x2_pack(-mo, -mo);
       auto soft_chunk = [&](const uint32_t (&src)[32], int c, bool masked) {
         uint32_t pk[16];
 #pragma unroll
         for (int j = 0; j < 32; j += 2) {
-          float p0 = ex2_approx(fmaf(__uint_as_float(src[j]), scale_log2e, -mo));
-          float p1 = ex2_approx(fmaf(__uint_as_float(src[j + 1]), scale_log2e, -mo));
+          float x0, x1;
+          f32x2_unpack(f32x2_fma(f32x2_pack(__uint_as_float(src[j]), __uint_as_float(src[j + 1])), scale2, nmo2), x0, x1);
+          float p0 = ex2_approx(x0), p1 = ex2_approx(x1);
           if (masked) {
             if (c * 32 + j >= L) p0 = 0.f;
             if (c * 32 + j + 1 >= L) p1 = 0.f;
           }
-          sum0 += p0;
-          sum1 += p1;
-          pk[j >> 1] = pack_bf16(p0, p1);
+          if (j & 2) sumB = f32x2_add(sumB, f32x2_pack(p0, p1));
+          else sumA = f32x2_add(sumA, f32x2_pack(p0, p1));
+          pk[j >> 1] = pack_bf16_int(p0, p1);
         }
         tmem_st_32x16(t_s + c * 16, pk);
       };
@@ -302,19 +367,50 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
             const float p1 = (NFULL * 32 + j + 1 < L) ? ex2_approx(fmaf(__uint_as_float(r[j + 1]), scale_log2e, -mo)) : 0.f;
             sum0 += p0;
             sum1 += p1;
-            pk[j >> 1] = pack_bf16(p0, p1);
+            pk[j >> 1] = pack_bf16_int(p0, p1);
           }
           tmem_st_32x8(t_s + NFULL * 16, pk);
         }
       }
+      {
+        float a0, a1, b0, b1;
+        f32x2_unpack(sumA, a0, a1);
+        f32x2_unpack(sumB, b0, b1);
+        sum0 += a0 + b0;
+        sum1 += a1 + b1;
+      }
       const float sum = sum0 + sum1;
+      if (C::QT == 2) {     // hand the exp2 turn to the other slot's warp of this quarter
+        __syncwarp();
+        if (lane == 0) xu_turn[quarter] = 2 * static_cast<int>(it) + qt + 1;
+      }
       tmem_st_wait();
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&p_full[qt]);
+      {
+        // the last of the slot's four warps to get here issues P V (its P rows and everyone else's are in TMEM)
+        int last = 0;
+        if (lane == 0) {
+          __threadfence_block();
+          last = (atomicAdd(&cnt_p[qt], 1) & 3) == 3;
+          __threadfence_block();
+        }
+        last = __shfl_sync(0xffffffffu, last, 0);
+        if (last) {
+          tc_fence_after();
+          if (elect_one()) {
+            issue_pv(smem_u32(smem + (it & 1) * C::BUF_BYTES), qt);
+            umma_commit(&smem_empty[it & 1]);   // the item's smem is free once BOTH slots' P V have retired (count = QT)
+          }
+          ATC_TRACE(1, qt, it);
+          __syncwarp();
+        }
+      }
+      if (quarter == 0) ATC_TRACE(5, qt, it);
       // ---- epilogue: O / rowsum -> bf16 -> HBM (each thread owns one 128-byte output line) ----
       mbar_wait(&o_full[qt], ph);
       tc_fence_after();
+      if (quarter == 0) ATC_TRACE(6, qt, it);
       const float inv = 1.0f / sum;
       uint32_t o0[32], o1[32];
       tmem_ld_32x32(t_s + C::O_COL, o0);
@@ -322,7 +418,25 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
       tmem_ld_wait();
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tmem_free[qt]);
+      {
+        // the last warp to have drained its O rows issues the slot's next Q K^T (S overwrites the P / O columns)
+        int last = 0;
+        if (lane == 0) {
+          __threadfence_block();
+          last = (atomicAdd(&cnt_e[qt], 1) & 3) == 3;
+          __threadfence_block();
+        }
+        last = __shfl_sync(0xffffffffu, last, 0);
+        if (last && static_cast<int>(it) + 1 < n_mine) {
+          const uint32_t nx = it + 1;
+          mbar_wait(&smem_full[nx & 1], (nx >> 1) & 1);
+          tc_fence_after();
+          if (elect_one()) issue_s(smem_u32(smem + (nx & 1) * C::BUF_BYTES), qt);
+          ATC_TRACE(0, qt, nx);
+          __syncwarp();
+        }
+      }
+      if (quarter == 0) ATC_TRACE(7, qt, it);
       if (qrow < L) {
         uint4* dst = reinterpret_cast<uint4*>(out + (static_cast<size_t>(frame) * L + qrow) * width + head * ATC_DH);
 #pragma unroll
@@ -343,6 +457,10 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
 
   tc_fence_before();
   __syncthreads();
+#ifdef ARP_ATTN_TRACE
+  if (blockIdx.x == 0)
+    for (int i = threadIdx.x; i < 2 * ATC_TR_ITEMS * ATC_TR_EVENTS; i += blockDim.x) g_attn_trace[i] = atc_tr[i];
+#endif
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc<512>(tmem_base);

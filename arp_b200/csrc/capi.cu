@@ -1639,3 +1639,14 @@ extern "C" int arp_attention(ArpHandle* h, const void* qkv_dev, void* out_dev, i
   return launch_attention(h, static_cast<const bf16*>(qkv_dev), static_cast<bf16*>(out_dev), B, tokens,
                           static_cast<cudaStream_t>(stream));
 }
+
+#ifdef ARP_ATTN_TRACE
+// dev-only (never part of the shipped ABI): the attention timeline of block 0 (last launch)
+extern "C" __attribute__((visibility("default"))) int arp_debug_attn_trace(long long* out, int cap) {
+  const int n = 2 * ATC_TR_ITEMS * ATC_TR_EVENTS;
+  cudaDeviceSynchronize();
+  if (cap < n) return -1;
+  cudaMemcpyFromSymbol(out, g_attn_trace, (size_t)n * sizeof(long long));
+  return n;
+}
+#endif
