@@ -61,7 +61,9 @@ gemm2_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gr
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
   static_assert(MODE != G2_RESID_LN || sizeof(OutT) == 4, "the residual stream is fp32");
 
-  const int warp = threadIdx.x >> 5;
+  // warp index through a shuffle: provably warp-uniform, so the MMA / TMA issue paths keep their descriptors in
+  // uniform registers (back-to-back UTCHMMA instead of an ELECT / R2UR.BROADCAST loop before every instruction)
+  const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0);
   const int lane = threadIdx.x & 31;
   const uint32_t rank = CG == 2 ? cluster_ctarank() : 0;
   const int cluster_id = blockIdx.x / CG;
@@ -94,7 +96,7 @@ gemm2_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gr
   tc_fence_before();
   if (CG == 2) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
 
   if (warp == 0) {
     // ===================== TMA producer (every CTA loads its own A rows and its share of W) =====================
