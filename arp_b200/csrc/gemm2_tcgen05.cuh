@@ -100,6 +100,9 @@ gemm2_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gr
 
   if (warp == 0) {
     // ===================== TMA producer (every CTA loads its own A rows and its share of W) =====================
+    // One elected thread runs the whole loop (no per-iteration ELECT / __syncwarp; the other lanes park at the final
+    // barrier and cost no issue slots).
+    if (elect_one()) {
     int stage = 0;
     uint32_t phase = 0;
     for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
@@ -109,7 +112,7 @@ gemm2_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gr
       const int b_row = n_blk * GEMM_BN + rank * Cfg::B_ROWS;
       for (int kb = 0; kb < num_kb; ++kb) {
         mbar_wait(&empty_bar[stage], phase ^ 1);
-        if (lane == 0) {
+        {
           uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
           uint8_t* sb = sa + GEMM_A_BYTES;
           if (CG == 1) {
@@ -124,13 +127,13 @@ gemm2_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gr
             tma_load_2d_cg2(sb, &tmap_b, leader_bar, kb * GEMM_BK, b_row);
           }
         }
-        __syncwarp();
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
     }
+    }
   } else if (warp == 1) {
     // ===================== MMA issuer (leader CTA of the pair only) =====================
-    if (rank == 0) {
+    if (rank == 0 && elect_one()) {   // a single thread waits, issues and commits
       constexpr uint32_t idesc = umma_idesc_bf16(GEMM_BM * CG, GEMM_BN);
       int stage = 0;
       uint32_t phase = 0;
@@ -143,7 +146,7 @@ gemm2_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gr
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
-          if (lane == 0) {
+          {
             const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE_BYTES);
             const uint64_t da = umma_desc_kmajor_sw128(sa);
             const uint64_t db = umma_desc_kmajor_sw128(sa + GEMM_A_BYTES);
@@ -160,7 +163,6 @@ gemm2_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gr
               if (kb == num_kb - 1) umma_commit_cg2(&tfull_bar[acc], 0b11);
             }
           }
-          __syncwarp();
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
