@@ -9,7 +9,8 @@
 //            and write P back INTO the same TMEM columns as packed bf16 (tcgen05.st)
 //   MMA #2   O[128 x 64] = P V        A operand straight from TMEM, B = V from smem as an MN-major operand
 //   epilogue tcgen05.ld O, scale by 1/rowsum, bf16, one full 128-byte line per thread to HBM
-// TMEM map per query tile t (base = 256 t): S fp32 [base, base+208) -> P bf16x2 [base, base+104); O fp32 [base+128, base+192).
+// TMEM map per query tile t (base = 256 t): S fp32 [base, base+208) -> P bf16x2 [base, base+104); O fp32 [base+128, base+208)
+// (64 head dims + 16 copies of the row sum: V's operand has a second, all-ones N block).
 // Warp roles (320 threads): 0 = TMA producer, 1 = TMEM owner (alloc / dealloc only), 2..9 = softmax / MMA issue / epilogue
 // (warps 2-5 own query tile 0, warps 6-9 query tile 1; a warp may only touch TMEM lanes 32*(warp%4)..+31).
 //
@@ -43,8 +44,10 @@ struct AtcCfg {
   static constexpr int KV_PAD = (KV_BYTES + 1023) / 1024 * 1024;
   static constexpr int BUF_BYTES = QT * Q_BYTES + 2 * KV_PAD;
   static constexpr int TX_BYTES = QT * Q_BYTES + 2 * KV_BYTES;
-  static constexpr int SMEM_BYTES = 2 * BUF_BYTES + 1024 + 256;
+  static constexpr int ONES_BYTES = KV_PAD;            // a second 64-wide N block of "V" that is all 1.0 (row sums)
+  static constexpr int SMEM_BYTES = 2 * BUF_BYTES + ONES_BYTES + 1024 + 256;
   static constexpr int O_COL = 128;                    // O accumulator column offset inside a tile's TMEM region
+  static constexpr int O_N = ATC_DH + 16;              // P V output width: 64 head dims + 16 copies of the row sum
 };
 
 __device__ __forceinline__ void umma_bf16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc,
@@ -77,10 +80,11 @@ __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.
 
 // MN-major shared-memory operand, 128B swizzle: rows (the K index of the MMA) are 128 B = 64 elements of the
 // MN index; groups of 8 rows are 1024 B apart (SBO). One 64-wide MN span -> LBO unused.
-__device__ __forceinline__ uint64_t umma_desc_mnmajor_sw128(uint32_t smem_addr) {
+// lbo_bytes: distance to the next 64-element block along MN (only read when the instruction's N exceeds 64).
+__device__ __forceinline__ uint64_t umma_desc_mnmajor_sw128(uint32_t smem_addr, uint32_t lbo_bytes = 16) {
   uint64_t d = 0;
   d |= static_cast<uint64_t>((smem_addr & 0x3FFFF) >> 4);
-  d |= static_cast<uint64_t>(1) << 16;
+  d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3FFF) << 16;
   d |= static_cast<uint64_t>(1024 >> 4) << 32;
   d |= static_cast<uint64_t>(1) << 46;
   d |= static_cast<uint64_t>(2) << 61;
@@ -114,6 +118,13 @@ __device__ __forceinline__ uint64_t f32x2_add(uint64_t a, uint64_t b) {
 __device__ __forceinline__ uint32_t pack_bf16_int(float lo, float hi) {
   const uint32_t a = __float_as_uint(lo) + 0x8000u, b = __float_as_uint(hi) + 0x8000u;
   return (a >> 16) | (b & 0xffff0000u);
+}
+
+// bf16 pair by TRUNCATION (two ALU ops, no rounding adds): the weights P are normalised by the tensor core's own sum of
+// the truncated values (ones block), so the one-sided error cancels in the mean and what remains has the spread of
+// round-to-nearest.
+__device__ __forceinline__ uint32_t pack_bf16_trunc(float lo, float hi) {
+  return (__float_as_uint(lo) >> 16) | (__float_as_uint(hi) & 0xffff0000u);
 }
 
 __device__ __forceinline__ float ex2_approx(float x) {
@@ -158,7 +169,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
   using C = AtcCfg<L>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 2 * C::BUF_BYTES);
+  uint8_t* ones = smem + 2 * C::BUF_BYTES;     // [NK rows x 128 B] of bf16 1.0: N block 1 of the P V operand
+  uint64_t* bars = reinterpret_cast<uint64_t*>(ones + C::ONES_BYTES);
   uint64_t* smem_full = bars;        // [2] TMA -> Q K^T issuer: the item's Q/K/V have landed
   uint64_t* smem_empty = bars + 2;   // [2] tensor core (all P V of the item retired) -> TMA
   uint64_t* s_full = bars + 4;       // [2 slots] tensor core -> softmax warps: S ready
@@ -196,6 +208,9 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
     fence_mbar_init();
   }
   if (warp == 1 && lane < 4) { xu_turn[lane] = 0; cnt_p[lane] = 0; }   // cnt_p[0..1], cnt_e[0..1] are contiguous
+  for (int i = threadIdx.x; i < C::ONES_BYTES / 16; i += ATC_THREADS)      // swizzle-invariant: every element is 1.0
+    reinterpret_cast<uint4*>(ones)[i] = make_uint4(0x3f803f80u, 0x3f803f80u, 0x3f803f80u, 0x3f803f80u);
+  fence_proxy_async_smem();                                                // generic-proxy writes -> tensor-core reads
   if (warp == 1) tmem_alloc<512>(tmem_slot);
   tc_fence_before();
   __syncthreads();
@@ -204,7 +219,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
 
   // ---- MMA issue (one elected thread of a softmax warp) ----
   constexpr uint32_t idesc_s = umma_idesc_bf16(128, C::NK);          // Q K^T: both operands K-major
-  constexpr uint32_t idesc_o = umma_idesc_bf16(128, ATC_DH, 0, 1);   // P V: A from TMEM, B = V MN-major
+  constexpr uint32_t idesc_o = umma_idesc_bf16(128, C::O_N, 0, 1);    // P [V | 1]: A from TMEM, B MN-major, N = 80
   auto issue_s = [&](uint32_t sbuf, int t) {
     const uint64_t dk = umma_desc_kmajor_sw128(sbuf + C::QT * C::Q_BYTES);
     const uint64_t dq = umma_desc_kmajor_sw128(sbuf + t * C::Q_BYTES);
@@ -214,7 +229,10 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
     umma_commit(&s_full[t]);
   };
   auto issue_pv = [&](uint32_t sbuf, int t) {
-    const uint64_t dv = umma_desc_mnmajor_sw128(sbuf + C::QT * C::Q_BYTES + C::KV_PAD);
+    // N block 0 = the item's V tile, N block 1 (LBO away) = the shared all-ones tile: O[:, 64..79] = sum_k P[:, k],
+    // the softmax denominator of exactly the bf16 weights the tensor core used
+    const uint32_t v_addr = sbuf + C::QT * C::Q_BYTES + C::KV_PAD;
+    const uint64_t dv = umma_desc_mnmajor_sw128(v_addr, smem_u32(ones) - v_addr);
 #pragma unroll
     for (int k = 0; k < C::NK / 16; ++k)
       // 16 keys per MMA: A advances 8 packed columns, V advances 16 rows x 128 B = 2048 B
@@ -323,8 +341,6 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
       // ---- pass 2: p = exp2(s*scale - max*scale); P (bf16 pairs) overwrites the S columns it came from.
       //      Two register buffers ping-pong: the load of the next chunk is in flight while this one is processed. ----
       if (quarter == 0) ATC_TRACE(4, qt, it);
-      float sum0 = 0.f, sum1 = 0.f;
-      uint64_t sumA = f32x2_pack(0.f, 0.f), sumB = sumA;      // four partial row sums (two packed accumulators)
       const uint64_t scale2 = f32x2_pack(scale_log2e, scale_log2e), nmo2 = f32x2_pack(-mo, -mo);
       auto soft_chunk = [&](const uint32_t (&src)[32], int c, bool masked) {
         uint32_t pk[16];
@@ -337,9 +353,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
             if (c * 32 + j >= L) p0 = 0.f;
             if (c * 32 + j + 1 >= L) p1 = 0.f;
           }
-          if (j & 2) sumB = f32x2_add(sumB, f32x2_pack(p0, p1));
-          else sumA = f32x2_add(sumA, f32x2_pack(p0, p1));
-          pk[j >> 1] = pack_bf16_int(p0, p1);
+          pk[j >> 1] = pack_bf16_trunc(p0, p1);
         }
         tmem_st_32x16(t_s + c * 16, pk);
       };
@@ -365,21 +379,11 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
           for (int j = 0; j < 16; j += 2) {
             const float p0 = (NFULL * 32 + j < L) ? ex2_approx(fmaf(__uint_as_float(r[j]), scale_log2e, -mo)) : 0.f;
             const float p1 = (NFULL * 32 + j + 1 < L) ? ex2_approx(fmaf(__uint_as_float(r[j + 1]), scale_log2e, -mo)) : 0.f;
-            sum0 += p0;
-            sum1 += p1;
-            pk[j >> 1] = pack_bf16_int(p0, p1);
+            pk[j >> 1] = pack_bf16_trunc(p0, p1);
           }
           tmem_st_32x8(t_s + NFULL * 16, pk);
         }
       }
-      {
-        float a0, a1, b0, b1;
-        f32x2_unpack(sumA, a0, a1);
-        f32x2_unpack(sumB, b0, b1);
-        sum0 += a0 + b0;
-        sum1 += a1 + b1;
-      }
-      const float sum = sum0 + sum1;
       if (C::QT == 2) {     // hand the exp2 turn to the other slot's warp of this quarter
         __syncwarp();
         if (lane == 0) xu_turn[quarter] = 2 * static_cast<int>(it) + qt + 1;
@@ -411,11 +415,12 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
       mbar_wait(&o_full[qt], ph);
       tc_fence_after();
       if (quarter == 0) ATC_TRACE(6, qt, it);
-      const float inv = 1.0f / sum;
-      uint32_t o0[32], o1[32];
+      uint32_t o0[32], o1[32], osum[16];
       tmem_ld_32x32(t_s + C::O_COL, o0);
       tmem_ld_32x32(t_s + C::O_COL + 32, o1);
+      tmem_ld_32x16(t_s + C::O_COL + ATC_DH, osum);      // 16 copies of the row sum (the ones block of the operand)
       tmem_ld_wait();
+      const float inv = 1.0f / __uint_as_float(osum[0]);
       tc_fence_before();
       __syncwarp();
       {
