@@ -289,7 +289,10 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
       constexpr int NCLEAN = (L / 32 < NFULL) ? L / 32 : NFULL;   // full chunks whose 32 columns are all real keys
       // ---- pass 1: row maximum over the L real keys (two 32-column loads in flight per wait) ----
       float m = -INFINITY;
-      {
+      // a warp whose 32 rows are all padding (tile 1, rows 224..255 when L = 197) keeps the barrier / turn protocol but
+      // does no softmax: whatever sits in its P rows only reaches O rows that are never stored
+      const bool warp_live = qt * 128 + quarter * 32 < L;
+      if (warp_live) {
         uint32_t a[32], bq[32];
 #pragma unroll 1
         for (int c = 0; c + 1 < NCLEAN; c += 2) {
@@ -357,7 +360,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
         }
         tmem_st_32x16(t_s + c * 16, pk);
       };
-      {
+      if (warp_live) {
         uint32_t b0[32], b1[32];
         tmem_ld_32x32(t_s, b0);
         tmem_ld_wait();
