@@ -33,82 +33,107 @@ __device__ __forceinline__ float block_sum(float v, float* scratch) {
   return t;
 }
 
-// One CTA (256 threads) per frame.
+// One CTA (256 threads) per FR consecutive frames: the 768x512 projection is streamed once per CTA and applied to all
+// FR class-token rows (with one frame per CTA the 1.5 MB matrix was re-read from L2 by every CTA).
 //   x        fp32 [B*tokens, W]   residual stream after the last block (row b*tokens = class token)
 //   proj     fp32 [W, E]
 //   text     fp32 [n_text, E] unit rows (may be null when only features are wanted)
 //   feat_out fp32 [B, ld_feat] : un-normalised f written at column feat_col0 (adapter / goal modes) or null
 //   logits   fp32 [B, n_text] or null ; reward fp32 [B] or null
+constexpr int HEAD_FR = 4;
+
 template <int W, int E>
 __global__ void __launch_bounds__(256)
 clip_head_kernel(const float* __restrict__ x, int tokens, const float* __restrict__ ln_g,
                  const float* __restrict__ ln_b, float eps, const float* __restrict__ proj,
                  const float* __restrict__ text, int n_text, float scale, int reduce,
                  float* __restrict__ feat_out, int ld_feat, int feat_col0, float* __restrict__ logits,
-                 float* __restrict__ reward) {
+                 float* __restrict__ reward, int n_frames) {
   static_assert(W % 256 == 0 && E % 256 == 0, "head widths must be multiples of the CTA size");
-  __shared__ float s_f[W];
-  __shared__ float s_y[E];
+  __shared__ float s_f[HEAD_FR][W];
+  __shared__ float s_y[HEAD_FR][E];
   __shared__ float s_red[8];
-  const int b = blockIdx.x, tid = threadIdx.x;
-  const float* xr = x + static_cast<size_t>(b) * tokens * W;
+  __shared__ float s_inv[HEAD_FR];
+  __shared__ float s_logit[HEAD_FR][HEAD_MAX_TEXT];
+  const int b0 = blockIdx.x * HEAD_FR, tid = threadIdx.x;
+  const int nf = min(HEAD_FR, n_frames - b0);
 
-  float v[W / 256];
-  float s = 0.f;
+  for (int f = 0; f < HEAD_FR; ++f) {        // ln_post of each class-token row (zeros for frames past the end)
+    float v[W / 256];
+    float s = 0.f;
+    if (f < nf) {
+      const float* xr = x + static_cast<size_t>(b0 + f) * tokens * W;
 #pragma unroll
-  for (int i = 0; i < W / 256; ++i) { v[i] = xr[tid + i * 256]; s += v[i]; }
-  const float mean = block_sum<256>(s, s_red) * (1.0f / W);
-  float q = 0.f;
+      for (int i = 0; i < W / 256; ++i) { v[i] = xr[tid + i * 256]; s += v[i]; }
+    } else {
 #pragma unroll
-  for (int i = 0; i < W / 256; ++i) { const float d = v[i] - mean; q += d * d; }
-  const float rstd = rsqrtf(block_sum<256>(q, s_red) * (1.0f / W) + eps);
+      for (int i = 0; i < W / 256; ++i) v[i] = 0.f;
+    }
+    const float mean = block_sum<256>(s, s_red) * (1.0f / W);
+    float q = 0.f;
 #pragma unroll
-  for (int i = 0; i < W / 256; ++i) {
-    const int c = tid + i * 256;
-    s_f[c] = (v[i] - mean) * rstd * ln_g[c] + ln_b[c];
+    for (int i = 0; i < W / 256; ++i) { const float d = v[i] - mean; q += d * d; }
+    const float rstd = rsqrtf(block_sum<256>(q, s_red) * (1.0f / W) + eps);
+#pragma unroll
+    for (int i = 0; i < W / 256; ++i) {
+      const int c = tid + i * 256;
+      s_f[f][c] = f < nf ? (v[i] - mean) * rstd * ln_g[c] + ln_b[c] : 0.f;
+    }
   }
   __syncthreads();
 
-  float y[E / 256];
+  float y[HEAD_FR][E / 256];
 #pragma unroll
-  for (int j = 0; j < E / 256; ++j) y[j] = 0.f;
+  for (int f = 0; f < HEAD_FR; ++f)
+#pragma unroll
+    for (int j = 0; j < E / 256; ++j) y[f][j] = 0.f;
 #pragma unroll 4
   for (int k = 0; k < W; ++k) {
-    const float fk = s_f[k];
+    float pk[E / 256];
 #pragma unroll
-    for (int j = 0; j < E / 256; ++j) y[j] = fmaf(fk, __ldg(proj + static_cast<size_t>(k) * E + tid + j * 256), y[j]);
-  }
-  float n2 = 0.f;
+    for (int j = 0; j < E / 256; ++j) pk[j] = __ldg(proj + static_cast<size_t>(k) * E + tid + j * 256);
 #pragma unroll
-  for (int j = 0; j < E / 256; ++j) {
-    s_y[tid + j * 256] = y[j];
-    n2 += y[j] * y[j];
-    if (feat_out) feat_out[static_cast<size_t>(b) * ld_feat + feat_col0 + tid + j * 256] = y[j];
+    for (int f = 0; f < HEAD_FR; ++f) {
+      const float fk = s_f[f][k];
+#pragma unroll
+      for (int j = 0; j < E / 256; ++j) y[f][j] = fmaf(fk, pk[j], y[f][j]);
+    }
   }
-  const float inv_norm = 1.0f / sqrtf(block_sum<256>(n2, s_red));
+  for (int f = 0; f < HEAD_FR; ++f) {
+    float n2 = 0.f;
+#pragma unroll
+    for (int j = 0; j < E / 256; ++j) {
+      s_y[f][tid + j * 256] = y[f][j];
+      n2 += y[f][j] * y[f][j];
+      if (feat_out && f < nf) feat_out[static_cast<size_t>(b0 + f) * ld_feat + feat_col0 + tid + j * 256] = y[f][j];
+    }
+    const float tot = block_sum<256>(n2, s_red);
+    if (tid == 0) s_inv[f] = 1.0f / sqrtf(tot);
+  }
   if (text == nullptr) return;
+  __syncthreads();
 
-  // cosines: warp w handles texts w, w+8, ...
-  __shared__ float s_logit[HEAD_MAX_TEXT];
+  // cosines: warp w handles (frame, text) pairs w, w+8, ...
   const int warp = tid >> 5, lane = tid & 31;
-  for (int t = warp; t < n_text; t += 8) {
+  for (int p = warp; p < nf * n_text; p += 8) {
+    const int f = p / n_text, t = p - f * n_text;
     float d = 0.f;
-    for (int k = lane; k < E; k += 32) d = fmaf(s_y[k], __ldg(text + static_cast<size_t>(t) * E + k), d);
+    for (int k = lane; k < E; k += 32) d = fmaf(s_y[f][k], __ldg(text + static_cast<size_t>(t) * E + k), d);
     d = warp_sum(d);
     if (lane == 0) {
-      const float lg = scale * (d * inv_norm);
-      s_logit[t] = lg;
-      if (logits) logits[static_cast<size_t>(b) * n_text + t] = lg;
+      const float lg = scale * (d * s_inv[f]);
+      s_logit[f][t] = lg;
+      if (logits) logits[static_cast<size_t>(b0 + f) * n_text + t] = lg;
     }
   }
   __syncthreads();
-  if (tid == 0 && reward) {
-    float r = s_logit[0];
+  if (tid < nf && reward) {
+    float r = s_logit[tid][0];
     if (reduce == REDUCE_MEAN) {
-      for (int t = 1; t < n_text; ++t) r += s_logit[t];
+      for (int t = 1; t < n_text; ++t) r += s_logit[tid][t];
       r /= static_cast<float>(n_text);
     }
-    reward[b] = r;
+    reward[b0 + tid] = r;
   }
 }
 

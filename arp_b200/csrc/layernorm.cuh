@@ -149,6 +149,82 @@ gather_cls_bf16_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ 
   }
 }
 
+// xcls fp32 [B, W] = x[b*tokens, :]  — the class-token rows of the residual stream, compacted (last-layer pruning)
+template <int W>
+__global__ void __launch_bounds__(256)
+gather_cls_rows_f32_kernel(const float* __restrict__ x, float* __restrict__ xcls, int B, int tokens) {
+  const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (b >= B) return;
+  const int lane = threadIdx.x & 31;
+  const float4* src = reinterpret_cast<const float4*>(x + static_cast<size_t>(b) * tokens * W);
+  float4* dst = reinterpret_cast<float4*>(xcls + static_cast<size_t>(b) * W);
+#pragma unroll
+  for (int i = 0; i < W / 128; ++i) dst[i * 32 + lane] = src[i * 32 + lane];
+}
+
+// Attention for the CLASS-TOKEN query only (last resblock): one warp per (frame, head).
+//   q     bf16 [B, W]           projected class-token queries (head h at columns h*64)
+//   qkv   bf16 [B*L, 3W]        K at columns W + h*64, V at 2W + h*64 (the Q third is not read)
+//   out   bf16 [B, W]
+// Lanes own keys for the scores (fp32 dot products, fp32 softmax with the true max), then own 2 head dims for P V.
+template <int L>
+__global__ void __launch_bounds__(256)
+cls_attention_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __restrict__ qkv,
+                     __nv_bfloat16* __restrict__ out, int B, int heads, int width, float scale) {
+  __shared__ float s_p[8][L + 3];
+  __shared__ float s_q[8][64];
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int item = blockIdx.x * 8 + w;
+  if (item >= B * heads) return;
+  const int frame = item / heads, head = item - frame * heads;
+  {
+    const __nv_bfloat162 v = reinterpret_cast<const __nv_bfloat162*>(q + static_cast<size_t>(frame) * width + head * 64)[lane];
+    s_q[w][2 * lane] = __bfloat162float(v.x) * scale;      // torch scales q by 1/sqrt(d) before q k^T
+    s_q[w][2 * lane + 1] = __bfloat162float(v.y) * scale;
+  }
+  __syncwarp();
+  const __nv_bfloat16* kbase = qkv + static_cast<size_t>(frame) * L * 3 * width + width + head * 64;
+  const __nv_bfloat16* vbase = kbase + width;
+  float m = -INFINITY;
+#pragma unroll 2
+  for (int j = lane; j < L; j += 32) {
+    const uint4* kr = reinterpret_cast<const uint4*>(kbase + static_cast<size_t>(j) * 3 * width);
+    float s = 0.f;
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      const uint4 u = __ldg(kr + c);
+      const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        s = fmaf(s_q[w][c * 8 + 2 * e], __bfloat162float(h2[e].x), s);
+        s = fmaf(s_q[w][c * 8 + 2 * e + 1], __bfloat162float(h2[e].y), s);
+      }
+    }
+    s_p[w][j] = s;
+    m = fmaxf(m, s);
+  }
+  m = warp_max(m);
+  float sum = 0.f;
+  for (int j = lane; j < L; j += 32) {
+    const float e = __expf(s_p[w][j] - m);
+    s_p[w][j] = e;
+    sum += e;
+  }
+  sum = warp_sum(sum);
+  __syncwarp();
+  float o0 = 0.f, o1 = 0.f;
+#pragma unroll 16      // 16 independent 128-byte row loads in flight per warp: the loop is pure load latency otherwise
+  for (int j = 0; j < L; ++j) {
+    const __nv_bfloat162 v = __ldg(reinterpret_cast<const __nv_bfloat162*>(vbase + static_cast<size_t>(j) * 3 * width) + lane);
+    const float pj = s_p[w][j];
+    o0 = fmaf(pj, __bfloat162float(v.x), o0);
+    o1 = fmaf(pj, __bfloat162float(v.y), o1);
+  }
+  const float inv = 1.0f / sum;
+  reinterpret_cast<__nv_bfloat162*>(out + static_cast<size_t>(frame) * width + head * 64)[lane] =
+      __floats2bfloat162_rn(o0 * inv, o1 * inv);
+}
+
 // fp32 -> bf16 conversion of a contiguous buffer (weights at load time, adapter features).
 __global__ void __launch_bounds__(256)
 f32_to_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, size_t n) {
