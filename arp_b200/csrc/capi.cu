@@ -616,6 +616,7 @@ extern "C" int arp_create(const ArpConfig* cfg, ArpHandle** out) {
   CREATE_TRY(set_smem(h, attention_kernel<197>, AttnCfg<197>::SMEM));
   CREATE_TRY(set_smem(h, attention_kernel<50>, AttnCfg<50>::SMEM));
   CREATE_TRY(set_smem(h, decode_kernel, 160 * 1024));
+  CREATE_TRY(set_smem(h, clip_head_kernel<768, 512>, HEAD_SMEM_BYTES));
   CREATE_TRY(set_smem(h, attention_f32_kernel, attn_f32_smem_bytes(197)));
   if (cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking) != cudaSuccess ||
       cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking) != cudaSuccess) {
@@ -1188,7 +1189,7 @@ static int head_chunk(ArpHandle* h, int pipe, int64_t n, float* reward_out, floa
   const int xtok = ws.pruned ? 1 : h->tokens;
   if (!h->adapter) {
     ProfScope prof(h, PC_HEAD, 2.0 * (double)n * 768 * 512, (double)n * 768 * 4 + 768.0 * 512 * 4, st);
-    clip_head_kernel<768, 512><<<(unsigned)((n + HEAD_FR - 1) / HEAD_FR), 256, 0, st>>>(
+    clip_head_kernel<768, 512><<<(unsigned)((n + HEAD_FR - 1) / HEAD_FR), 256, HEAD_SMEM_BYTES, st>>>(
         xsrc, xtok, h->ln_post_g, h->ln_post_b, 1e-5f, h->proj, (need_text && !h->goal) ? h->text : nullptr,
         h->n_text, h->logit_scale, c.reduce, feat_out, c.embed_dim, 0, logits_out, h->goal ? nullptr : reward_out, (int)n);
     h->launches++;
@@ -1196,7 +1197,7 @@ static int head_chunk(ArpHandle* h, int pipe, int64_t n, float* reward_out, floa
     const int D = h->feat_dim, Dmid = c.layers * c.embed_dim, Din = c.layers * c.width;
     const int64_t B = c.max_batch;
     // final CLIP feature -> last 512 columns of feat (un-normalised, clip_multiscale_adapter.py:136,145)
-    clip_head_kernel<768, 512><<<(unsigned)((n + HEAD_FR - 1) / HEAD_FR), 256, 0, st>>>(
+    clip_head_kernel<768, 512><<<(unsigned)((n + HEAD_FR - 1) / HEAD_FR), 256, HEAD_SMEM_BYTES, st>>>(
         xsrc, xtok, h->ln_post_g, h->ln_post_b, 1e-5f, h->proj, nullptr, 0, 0.f, 0, ws.featf, D, Dmid, nullptr, nullptr,
         (int)n);
     h->launches++;

@@ -41,6 +41,7 @@ __device__ __forceinline__ float block_sum(float v, float* scratch) {
 //   feat_out fp32 [B, ld_feat] : un-normalised f written at column feat_col0 (adapter / goal modes) or null
 //   logits   fp32 [B, n_text] or null ; reward fp32 [B] or null
 constexpr int HEAD_FR = 4;
+constexpr int HEAD_SMEM_BYTES = 8 * HEAD_FR * 512 * 4;   // dynamic: the per-warp partial outputs of clip_head_kernel
 
 template <int W, int E>
 __global__ void __launch_bounds__(256)
@@ -82,30 +83,56 @@ clip_head_kernel(const float* __restrict__ x, int tokens, const float* __restric
   }
   __syncthreads();
 
-  float y[HEAD_FR][E / 256];
+  // projection, split over k across the 8 warps: a warp streams whole 2 KB rows of proj (4 x LDG.128 per lane, 16 loads
+  // in flight) for its 96 values of k and keeps FR x 16 partial outputs per lane; the partials meet in shared memory.
+  // (One output pair per thread over all 768 k was a chain of 192 dependent L2 round trips: ~100 us per CTA.)
+  static_assert(E == 512 && W % 8 == 0, "lane -> column mapping below assumes 512 outputs");
+  extern __shared__ float s_part[];            // [8 warps][HEAD_FR][E]
+  {
+    const int warp = tid >> 5, lane = tid & 31;
+    constexpr int KW = W / 8;
+    float acc[HEAD_FR][16];
 #pragma unroll
-  for (int f = 0; f < HEAD_FR; ++f)
+    for (int f = 0; f < HEAD_FR; ++f)
 #pragma unroll
-    for (int j = 0; j < E / 256; ++j) y[f][j] = 0.f;
+      for (int j = 0; j < 16; ++j) acc[f][j] = 0.f;
+    const float4* prow = reinterpret_cast<const float4*>(proj) + static_cast<size_t>(warp) * KW * (E / 4) + lane;
 #pragma unroll 4
-  for (int k = 0; k < W; ++k) {
-    float pk[E / 256];
+    for (int kk = 0; kk < KW; ++kk) {
+      float4 pv[4];
 #pragma unroll
-    for (int j = 0; j < E / 256; ++j) pk[j] = __ldg(proj + static_cast<size_t>(k) * E + tid + j * 256);
+      for (int g = 0; g < 4; ++g) pv[g] = __ldg(prow + static_cast<size_t>(kk) * (E / 4) + g * 32);
 #pragma unroll
-    for (int f = 0; f < HEAD_FR; ++f) {
-      const float fk = s_f[f][k];
+      for (int f = 0; f < HEAD_FR; ++f) {
+        const float fk = s_f[f][warp * KW + kk];
 #pragma unroll
-      for (int j = 0; j < E / 256; ++j) y[f][j] = fmaf(fk, pk[j], y[f][j]);
+        for (int g = 0; g < 4; ++g) {
+          acc[f][4 * g] = fmaf(fk, pv[g].x, acc[f][4 * g]);
+          acc[f][4 * g + 1] = fmaf(fk, pv[g].y, acc[f][4 * g + 1]);
+          acc[f][4 * g + 2] = fmaf(fk, pv[g].z, acc[f][4 * g + 2]);
+          acc[f][4 * g + 3] = fmaf(fk, pv[g].w, acc[f][4 * g + 3]);
+        }
+      }
     }
+#pragma unroll
+    for (int f = 0; f < HEAD_FR; ++f)
+#pragma unroll
+      for (int g = 0; g < 4; ++g)
+        reinterpret_cast<float4*>(s_part + (static_cast<size_t>(warp) * HEAD_FR + f) * E)[g * 32 + lane] =
+            make_float4(acc[f][4 * g], acc[f][4 * g + 1], acc[f][4 * g + 2], acc[f][4 * g + 3]);
   }
+  __syncthreads();
   for (int f = 0; f < HEAD_FR; ++f) {
     float n2 = 0.f;
 #pragma unroll
     for (int j = 0; j < E / 256; ++j) {
-      s_y[f][tid + j * 256] = y[f][j];
-      n2 += y[f][j] * y[f][j];
-      if (feat_out && f < nf) feat_out[static_cast<size_t>(b0 + f) * ld_feat + feat_col0 + tid + j * 256] = y[f][j];
+      const int col = tid + j * 256;
+      float yv = 0.f;
+#pragma unroll
+      for (int w8 = 0; w8 < 8; ++w8) yv += s_part[(static_cast<size_t>(w8) * HEAD_FR + f) * E + col];
+      s_y[f][col] = yv;
+      n2 += yv * yv;
+      if (feat_out && f < nf) feat_out[static_cast<size_t>(b0 + f) * ld_feat + feat_col0 + col] = yv;
     }
     const float tot = block_sum<256>(n2, s_red);
     if (tid == 0) s_inv[f] = 1.0f / sqrtf(tot);

@@ -185,24 +185,33 @@ cls_attention_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* _
   __syncwarp();
   const __nv_bfloat16* kbase = qkv + static_cast<size_t>(frame) * L * 3 * width + width + head * 64;
   const __nv_bfloat16* vbase = kbase + width;
+  // scores: lane -> (key lane/8 of a group of 4, 16-byte chunk lane%8): every load instruction covers four whole 128-byte
+  // K rows; the 8 partial dot products of a key are combined with 3 shuffles
   float m = -INFINITY;
-#pragma unroll 2
-  for (int j = lane; j < L; j += 32) {
-    const uint4* kr = reinterpret_cast<const uint4*>(kbase + static_cast<size_t>(j) * 3 * width);
-    float s = 0.f;
+  const int kq = lane >> 3, kc = lane & 7;
+  float qv[8];
 #pragma unroll
-    for (int c = 0; c < 8; ++c) {
-      const uint4 u = __ldg(kr + c);
+  for (int e = 0; e < 8; ++e) qv[e] = s_q[w][kc * 8 + e];
+#pragma unroll 4
+  for (int j0 = 0; j0 < L; j0 += 4) {
+    const int j = j0 + kq;
+    float s = 0.f;
+    if (j < L) {
+      const uint4 u = __ldg(reinterpret_cast<const uint4*>(kbase + static_cast<size_t>(j) * 3 * width) + kc);
       const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&u);
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
-        s = fmaf(s_q[w][c * 8 + 2 * e], __bfloat162float(h2[e].x), s);
-        s = fmaf(s_q[w][c * 8 + 2 * e + 1], __bfloat162float(h2[e].y), s);
+        s = fmaf(qv[2 * e], __bfloat162float(h2[e].x), s);
+        s = fmaf(qv[2 * e + 1], __bfloat162float(h2[e].y), s);
       }
     }
-    s_p[w][j] = s;
-    m = fmaxf(m, s);
+    s += __shfl_xor_sync(0xffffffffu, s, 1);
+    s += __shfl_xor_sync(0xffffffffu, s, 2);
+    s += __shfl_xor_sync(0xffffffffu, s, 4);
+    if (kc == 0 && j < L) s_p[w][j] = s;
   }
+  __syncwarp();
+  for (int j = lane; j < L; j += 32) m = fmaxf(m, s_p[w][j]);
   m = warp_max(m);
   float sum = 0.f;
   for (int j = lane; j < L; j += 32) {
