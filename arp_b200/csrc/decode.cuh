@@ -53,9 +53,14 @@ struct DecodeArgs {
 __host__ __device__ inline int dec_out_bytes(int out_kind) {
   return DEC_BAND * DEC_OUT * 3 * (out_kind == DEC_OUT_PATCH_BF16 ? 2 : 4);
 }
+// Staged input rows and the horizontally resampled rows. Both carry slack that is never written: the fast path applies
+// all KS taps of every output pixel (coefficients past a pixel's tap count are 0), so it reads a few bytes past the
+// last staged row / up to KS-1 rows past the last resampled row; the slack keeps those reads off memory other threads write.
+__host__ __device__ inline int dec_in_bytes(int src_w, int max_rows) { return (max_rows * src_w * 3 + 32 + 15) / 16 * 16; }
+__host__ __device__ inline int dec_tmp_bytes(int max_rows) { return ((max_rows + 8) * DEC_OUT * 3 + 15) / 16 * 16; }
 __host__ __device__ inline int dec_smem_bytes(int src_w, int max_rows, int h_ksize, int v_ksize, int out_kind) {
-  int in_b = (max_rows * src_w * 3 + 15) / 16 * 16;
-  int tmp_b = (max_rows * DEC_OUT * 3 + 15) / 16 * 16;
+  int in_b = dec_in_bytes(src_w, max_rows);
+  int tmp_b = dec_tmp_bytes(max_rows);
   int out_b = dec_out_bytes(out_kind);
   int tab_b = (DEC_OUT * 2 + DEC_OUT * h_ksize + DEC_BAND * 2 + DEC_BAND * v_ksize) * 4;
   return in_b + tmp_b + out_b + tab_b + 64;
@@ -119,8 +124,8 @@ decode_kernel(const DecodeArgs a) {
   const int y0 = band * DEC_BAND;
   const int tid = threadIdx.x;
 
-  const int in_bytes = (a.max_rows * a.src_w * 3 + 15) / 16 * 16;
-  const int tmp_bytes = (a.max_rows * DEC_OUT * 3 + 15) / 16 * 16;
+  const int in_bytes = dec_in_bytes(a.src_w, a.max_rows);
+  const int tmp_bytes = dec_tmp_bytes(a.max_rows);
   uint8_t* s_in = dsm;
   uint8_t* s_tmp = s_in + in_bytes;
   uint8_t* s_out = s_tmp + tmp_bytes;
