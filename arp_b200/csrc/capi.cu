@@ -117,6 +117,13 @@ struct ArpHandle {
   // adapter taps = CLS rows), so that block computes K/V for all tokens but Q, attention, out_proj and the MLP for
   // the class-token row only — same result, 2.4 of 35.1 GFLOP per frame less. ARP_PRUNE_LAST=0 disables.
   bool prune_last = true;
+  // LayerNorm fused behind the residual GEMMs (GemmArgs::ln_cnt, gemm2 MODE 4): out_proj emits ln_2(x), c_proj the next
+  // block's ln_1(x), by the CTA that completes a 128-row block. Correct (all parity tests pass with ARP_LN_FUSE=1) but
+  // measured slower on B200 and therefore OFF: by the time the last column tile of a row block lands, c_proj's 620 MB
+  // A stream has evicted the block's x rows from L2 (ncu: DRAM reads 0.94 -> 1.67 GB, L2 hit 52 %), the gpu-scope
+  // fence of the hand-off invalidates L1 every tile, and 8 epilogue warps per SM hide HBM latency far worse than the
+  // standalone kernel's 64 (c_proj 320 -> 505 us, out_proj 125 -> 394 us vs 2 x 63 us of LayerNorm kernels saved).
+  bool ln_fuse = false;
   bool f32 = false;   // cfg.precision == ARP_PREC_F32: verification path (fp32_path.cuh); GEMM weights are stored as fp32
   int attn_impl = 2;  // 1 = mma.sync kernel, 2 = tcgen05 kernel (ARP_ATTN_IMPL overrides)
   int gemm_impl = 3;  // 1 = v1 (register stores), 2 = v2 single-CTA, 3 = v2 CTA pairs (ARP_GEMM_IMPL overrides)
@@ -155,6 +162,7 @@ struct ArpHandle {
     bf16 *taps = nullptr, *featb = nullptr, *hid2 = nullptr;
     float *featf = nullptr, *mlp = nullptr;
     float* stats = nullptr;   // [M, 2*W/128] partial LayerNorm moments (LN fold)
+    int* ln_cnt = nullptr;                                       // [ceil(M/128)] row-block arrival counters (fused LayerNorm)
     bool pruned = false;                                         // the heads read xcls (stride 1) instead of x (stride tokens)
     float* xcls = nullptr;                                       // [B, W] class-token residual rows (last-layer pruning)
     bf16 *xncls = nullptr, *qcls = nullptr, *acls = nullptr, *hcls = nullptr;   // [B,W] x3, [B,4W]
@@ -516,8 +524,10 @@ extern "C" int arp_create(const ArpConfig* cfg, ArpHandle** out) {
   if (const char* e = getenv("ARP_ATTN_IMPL")) h->attn_impl = atoi(e) == 1 ? 1 : 2;
   if (const char* e = getenv("ARP_SNAKE")) h->snake = atoi(e) != 0;
   if (const char* e = getenv("ARP_PRUNE_LAST")) h->prune_last = atoi(e) != 0;
+  if (const char* e = getenv("ARP_LN_FUSE")) h->ln_fuse = atoi(e) != 0;
   if (const char* e = getenv("ARP_LN_FOLD")) h->ln_fold = std::max(0, std::min(2, atoi(e)));
   if (h->gemm_impl < 2 || h->f32) h->ln_fold = 0;   // the fold lives in the v2 epilogue
+  if (h->gemm_impl < 2 || h->f32) h->ln_fuse = false;
   h->grid = DEC_OUT / cfg->patch;
   h->tokens = h->grid * h->grid + 1;
   h->kp = 3 * cfg->patch * cfg->patch;
@@ -560,6 +570,7 @@ extern "C" int arp_create(const ArpConfig* cfg, ArpHandle** out) {
     CREATE_TRY(dev_alloc(h, &w.attn, M * W));
     CREATE_TRY(dev_alloc(h, &w.hid, M * std::max<size_t>(4 * W, h->kp)));
     if (h->ln_fold) CREATE_TRY(dev_alloc(h, &w.stats, M * 2 * (W / 128)));
+    CREATE_TRY(dev_alloc(h, &w.ln_cnt, M / 128 + 2));
     CREATE_TRY(dev_alloc(h, &w.xcls, B * W));
     CREATE_TRY(dev_alloc(h, &w.xncls, B * W));
     CREATE_TRY(dev_alloc(h, &w.qcls, B * W));
@@ -608,7 +619,7 @@ extern "C" int arp_create(const ArpConfig* cfg, ArpHandle** out) {
   CREATE_TRY(set_smem(h, gemm2_bf16_tcgen05_kernel<T, A, 2, R>, G2Cfg<2>::SMEM_BYTES));
   G2_ATTR(bf16, ACT_NONE, G2_STORE) G2_ATTR(bf16, ACT_QUICKGELU, G2_STORE) G2_ATTR(bf16, ACT_RELU, G2_STORE)
   G2_ATTR(float, ACT_NONE, G2_STORE) G2_ATTR(float, ACT_QUICKGELU, G2_STORE) G2_ATTR(float, ACT_RELU, G2_STORE)
-  G2_ATTR(float, ACT_NONE, G2_REDUCE) G2_ATTR(float, ACT_NONE, G2_RESID_LN)
+  G2_ATTR(float, ACT_NONE, G2_REDUCE) G2_ATTR(float, ACT_NONE, G2_RESID_LN) G2_ATTR(float, ACT_NONE, G2_REDUCE_LN)
   G2_ATTR(bf16, ACT_NONE, G2_LNFOLD) G2_ATTR(bf16, ACT_QUICKGELU, G2_LNFOLD)
 #undef G2_ATTR
   CREATE_TRY(set_smem(h, attention_tc_kernel<197>, AtcCfg<197>::SMEM_BYTES));
@@ -839,7 +850,8 @@ static int launch_gemm2(ArpHandle* h, const bf16* a, int64_t a_rows_alloc, const
   else if (lnfold) {
     if (act == ACT_NONE) G2_LAUNCH(bf16, ACT_NONE, G2_LNFOLD);
     else G2_LAUNCH(bf16, ACT_QUICKGELU, G2_LNFOLD);
-  } else if (reduce) G2_LAUNCH(float, ACT_NONE, G2_REDUCE);
+  } else if (reduce && g.ln_out) G2_LAUNCH(float, ACT_NONE, G2_REDUCE_LN);
+  else if (reduce) G2_LAUNCH(float, ACT_NONE, G2_REDUCE);
   else if (out_f32) {
     if (act == ACT_NONE) G2_LAUNCH(float, ACT_NONE, G2_STORE);
     else if (act == ACT_QUICKGELU) G2_LAUNCH(float, ACT_QUICKGELU, G2_STORE);
@@ -863,9 +875,13 @@ struct LnFoldArgs {
   const float* stats_in = nullptr; const float* svec = nullptr; const float* cvec = nullptr;  // MODE 3
 };
 
+// LayerNorm fused behind a residual GEMM (GemmArgs::ln_*)
+struct LnFuseArgs { const float* gamma; const float* beta; bf16* out; int* cnt; };
+
 static int launch_gemm(ArpHandle* h, const bf16* a, int64_t a_rows_alloc, const bf16* w, void* out, bool out_f32,
                        int act, int64_t M, int N, int K, int ldo, const float* bias, const float* resid, int ldr,
-                       const float* rowtab, int period, cudaStream_t st, const LnFoldArgs* fold = nullptr) {
+                       const float* rowtab, int period, cudaStream_t st, const LnFoldArgs* fold = nullptr,
+                       const LnFuseArgs* fuse = nullptr) {
   if (M <= 0) return ARP_OK;
   if (N % GEMM_BN || K % GEMM_BK) return fail(h, ARP_ERR_INVALID, "GEMM needs N %% 256 == 0 and K %% 64 == 0 (N=%d K=%d)", N, K);
   if (M > 0x7fffffff / 2) return fail(h, ARP_ERR_INVALID, "GEMM M too large");
@@ -882,6 +898,12 @@ static int launch_gemm(ArpHandle* h, const bf16* a, int64_t a_rows_alloc, const 
     if (h->gemm_impl < 2) return fail(h, ARP_ERR_INVALID, "the LayerNorm fold needs the v2 GEMM");
     g.xb = fold->xb; g.stats_out = fold->stats_out; g.stats_in = fold->stats_in; g.stats_nh = K / 128;
     g.svec = fold->svec; g.cvec = fold->cvec;
+  }
+  if (fuse) {
+    if (h->gemm_impl < 2 || !out_f32 || act != ACT_NONE || !resid || resid != out || N != 768 || ldo != 768)
+      return fail(h, ARP_ERR_INVALID, "fused LayerNorm needs the in-place fp32 residual GEMM with N = 768");
+    g.ln_gamma = fuse->gamma; g.ln_beta = fuse->beta; g.ln_out = fuse->out; g.ln_cnt = fuse->cnt;
+    ARP_CUDA(h, cudaMemsetAsync(fuse->cnt, 0, (size_t)((M + 127) / 128) * sizeof(int), st));
   }
   if (h->gemm_impl >= 2) return launch_gemm2(h, a, a_rows_alloc, w, g, out_f32, act, st);
   const int tiles = (int)((M + GEMM_BM - 1) / GEMM_BM) * (N / GEMM_BN);
@@ -1054,9 +1076,11 @@ static int encode_chunk(ArpHandle* h, int pipe, const uint8_t* ob, int64_t n, in
     h->launches++;
   }
   ws.pruned = false;
+  bool xn_ready = false;   // ws.xn already holds this block's ln_1(x): fused behind the previous block's c_proj
   for (int l = 0; l < c.layers; ++l) {
     const LayerW& L = h->layers[l];
-    ARP_TRY(launch_ln_bf16(h, ws.x, L.ln1_g, L.ln1_b, ws.xn, M, st));
+    if (!xn_ready) ARP_TRY(launch_ln_bf16(h, ws.x, L.ln1_g, L.ln1_b, ws.xn, M, st));
+    xn_ready = false;
     if (l == c.layers - 1 && h->prune_last) {
       // ---- last block, class-token row only (see ArpHandle::prune_last) ----
       const int64_t B = c.max_batch;
@@ -1096,12 +1120,26 @@ static int encode_chunk(ArpHandle* h, int pipe, const uint8_t* ob, int64_t n, in
     ARP_TRY(launch_gemm(h, ws.xn, Mcap, L.w_qkv, ws.qkv, false, ACT_NONE, M, 3 * W, W, 3 * W, L.b_qkv, nullptr, 0,
                         nullptr, 0, st));
     ARP_TRY(launch_attention(h, ws.qkv, ws.attn, (int)n, h->tokens, st, Mcap));
-    ARP_TRY(launch_gemm(h, ws.attn, Mcap, L.w_out, ws.x, true, ACT_NONE, M, W, W, W, L.b_out, ws.x, W, nullptr, 0, st));
-    ARP_TRY(launch_ln_bf16(h, ws.x, L.ln2_g, L.ln2_b, ws.xn, M, st));
+    if (h->ln_fuse) {
+      const LnFuseArgs f2{L.ln2_g, L.ln2_b, ws.xn, ws.ln_cnt};
+      ARP_TRY(launch_gemm(h, ws.attn, Mcap, L.w_out, ws.x, true, ACT_NONE, M, W, W, W, L.b_out, ws.x, W, nullptr, 0, st,
+                          nullptr, &f2));
+    } else {
+      ARP_TRY(launch_gemm(h, ws.attn, Mcap, L.w_out, ws.x, true, ACT_NONE, M, W, W, W, L.b_out, ws.x, W, nullptr, 0, st));
+      ARP_TRY(launch_ln_bf16(h, ws.x, L.ln2_g, L.ln2_b, ws.xn, M, st));
+    }
     ARP_TRY(launch_gemm(h, ws.xn, Mcap, L.w_fc, ws.hid, false, ACT_QUICKGELU, M, 4 * W, W, 4 * W, L.b_fc, nullptr, 0,
                         nullptr, 0, st));
-    ARP_TRY(launch_gemm(h, ws.hid, Mcap, L.w_proj, ws.x, true, ACT_NONE, M, W, 4 * W, W, L.b_proj, ws.x, W, nullptr,
-                        0, st));
+    if (h->ln_fuse && l + 1 < c.layers) {
+      const LayerW& Ln = h->layers[l + 1];
+      const LnFuseArgs f1{Ln.ln1_g, Ln.ln1_b, ws.xn, ws.ln_cnt};
+      ARP_TRY(launch_gemm(h, ws.hid, Mcap, L.w_proj, ws.x, true, ACT_NONE, M, W, 4 * W, W, L.b_proj, ws.x, W, nullptr, 0,
+                          st, nullptr, &f1));
+      xn_ready = true;
+    } else {
+      ARP_TRY(launch_gemm(h, ws.hid, Mcap, L.w_proj, ws.x, true, ACT_NONE, M, W, 4 * W, W, L.b_proj, ws.x, W, nullptr,
+                          0, st));
+    }
     if (h->adapter) {
       gather_cls_bf16_kernel<768><<<(unsigned)((n + 7) / 8), 256, 0, st>>>(ws.x, ws.taps, (int)n, h->tokens,
                                                                          c.layers * W, l * W);

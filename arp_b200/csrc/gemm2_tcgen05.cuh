@@ -14,6 +14,7 @@
 
 #include "common.cuh"
 #include "gemm_tcgen05.cuh"  // GemmArgs, GemmAct, tile constants
+#include "layernorm.cuh"     // ln_row (LayerNorm fused behind the residual GEMM)
 
 namespace arp {
 
@@ -42,7 +43,7 @@ struct G2Cfg {
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + G2_STAGING_BYTES + 1024 + 256;
 };
 
-enum G2Mode : int { G2_STORE = 0, G2_REDUCE = 1, G2_RESID_LN = 2, G2_LNFOLD = 3 };
+enum G2Mode : int { G2_STORE = 0, G2_REDUCE = 1, G2_RESID_LN = 2, G2_LNFOLD = 3, G2_REDUCE_LN = 4 };
 
 template <typename OutT, int ACT, int CG, int MODE>
 __global__ void __launch_bounds__(G2_THREADS, 1)
@@ -59,6 +60,7 @@ gemm2_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gr
   uint64_t* tfull_bar = bars + 2 * STAGES;
   uint64_t* tempty_bar = tfull_bar + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  int* ln_last = reinterpret_cast<int*>(tmem_slot + 1);     // fused LayerNorm: "this CTA completed the row block"
   static_assert(MODE != G2_RESID_LN || sizeof(OutT) == 4, "the residual stream is fp32");
 
   // warp index through a shuffle: provably warp-uniform, so the MMA / TMA issue paths keep their descriptors in
@@ -182,6 +184,33 @@ gemm2_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gr
     uint32_t acc_phase = 0;
     uint32_t buf = 0;
     const int sw = lane & 7;
+    int ln_prev_blk = -1;                      // fused LayerNorm: row block whose arrival is still to be signalled
+    // `pending` = bulk groups this lane may leave in flight (those of the tile issued after row block `blk`'s)
+    auto ln_fused_block = [&](int blk, int pending) {
+      if (MODE != G2_REDUCE_LN) return;
+      if (lane == 0) {
+        if (pending) tma_store_wait_all<(sizeof(OutT) == 4 ? 4 : 2)>(); else tma_store_wait_all<0>();
+        __threadfence();
+      }
+      named_bar_sync(1, G2_EPI_WARPS * 32);                      // every epilogue warp's reduce-adds of that tile are done
+      if (ew == 0 && lane == 0) {
+        const int prev = atomicAdd(args.ln_cnt + blk, 1);
+        __threadfence();
+        *ln_last = prev == num_n - 1;
+      }
+      named_bar_sync(1, G2_EPI_WARPS * 32);
+      if (*ln_last) {
+        const float* xo = reinterpret_cast<const float*>(args.out);
+        constexpr int RPW = GEMM_BM / G2_EPI_WARPS;             // 16 rows per epilogue warp
+#pragma unroll 1
+        for (int r = 0; r < RPW; r += 4) {
+          const int grow = blk * GEMM_BM + ew * RPW + r;
+          if (grow < args.M)
+            ln_rows_cg_bf16<768, 4>(xo, args.ldo, args.ln_gamma, args.ln_beta, args.eps, args.ln_out, grow, args.M);
+        }
+      }
+      named_bar_sync(1, G2_EPI_WARPS * 32);                      // ln_last is rewritten by the next call
+    };
     float4 xres[2][8];                         // MODE 2: residual values in the coalesced layout, ping-pong over units
     auto load_resid = [&](float4 (&dst)[8], int r0, int c0) {
 #pragma unroll
@@ -330,7 +359,7 @@ gemm2_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gr
           fence_proxy_async_smem();
           __syncwarp();
           if (lane == 0) {
-            if (MODE == G2_REDUCE) tma_reduce_add_2d(&tmap_out, sbuf, n0, row0);
+            if (MODE == G2_REDUCE || MODE == G2_REDUCE_LN) tma_reduce_add_2d(&tmap_out, sbuf, n0, row0);
             else tma_store_2d(&tmap_out, sbuf, n0, row0);
             tma_store_commit();
           }
@@ -353,7 +382,18 @@ gemm2_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gr
             reinterpret_cast<float2*>(args.stats_out)[static_cast<size_t>(gr) * nh_out + n_blk * 2 + half] = make_float2(a, b);
         }
       }
+      if (MODE == G2_REDUCE_LN && sizeof(OutT) == 4) {
+        {
+          // ---- LayerNorm fused behind the residual update (see GemmArgs::ln_cnt), one tile late: the reduce-adds of the
+          //      PREVIOUS tile have had a whole tile period to complete, so waiting for them costs nothing ----
+          if (ln_prev_blk >= 0) ln_fused_block(ln_prev_blk, UNITS);
+          ln_prev_blk = m_blk * CG + static_cast<int>(rank);
+        }
+      }
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+    if (MODE == G2_REDUCE_LN && sizeof(OutT) == 4) {
+      if (ln_prev_blk >= 0) ln_fused_block(ln_prev_blk, 0);
     }
     if (lane == 0) tma_store_wait_all<0>();
   }

@@ -29,6 +29,15 @@ struct GemmArgs {
   int ldr;
   const float* rowtab;  // fp32 [period, N] added to row (row % period), or nullptr (pos-emb + cls)
   int period;
+  // ---- LayerNorm fused behind the residual GEMM (gemm2 MODE 1 only; all null = off) ----
+  // After a CTA's TMA reduce-adds of a tile have completed it bumps ln_cnt[row block of 128]; the CTA that brings the
+  // count to N/256 (every column tile of those rows is in) normalises the 128 rows right there — they are still in
+  // L2 — and writes ln_out (bf16 [M, N]) = LN(out rows; ln_gamma, ln_beta). Replaces a standalone LayerNorm kernel
+  // that re-read the whole fp32 residual stream from HBM.
+  const float* ln_gamma;
+  const float* ln_beta;
+  __nv_bfloat16* ln_out;
+  int* ln_cnt;          // [ceil(M/128)] zeroed before the launch
   int reverse;          // gemm2: walk the tiles from the last row block to the first (snake order across kernels,
                         // so a kernel starts on the rows its predecessor wrote last — still in L2)
   // ---- LayerNorm fold (gemm2 MODE 2 / 3) ----

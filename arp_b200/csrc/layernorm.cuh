@@ -17,14 +17,16 @@ struct RowRegs {
   float4 v[kVec];
 };
 
-template <int W>
+// CG = true: read the row with ld.global.cg (L2 only) — for rows another SM has just updated inside the same kernel.
+template <int W, bool CG = false>
 __device__ __forceinline__ void ln_row(const float* __restrict__ x, const float* __restrict__ gamma,
                                        const float* __restrict__ beta, float eps, RowRegs<W>& r) {
   const int lane = threadIdx.x & 31;
   float s = 0.f;
 #pragma unroll
   for (int i = 0; i < RowRegs<W>::kVec; ++i) {
-    r.v[i] = *reinterpret_cast<const float4*>(x + (i * 32 + lane) * 4);
+    r.v[i] = CG ? __ldcg(reinterpret_cast<const float4*>(x + (i * 32 + lane) * 4))
+                : *reinterpret_cast<const float4*>(x + (i * 32 + lane) * 4);
     s += (r.v[i].x + r.v[i].y) + (r.v[i].z + r.v[i].w);
   }
   const float mean = warp_sum(s) * (1.0f / W);
@@ -43,6 +45,56 @@ __device__ __forceinline__ void ln_row(const float* __restrict__ x, const float*
     r.v[i].y = (r.v[i].y - mean) * rstd * g.y + b.y;
     r.v[i].z = (r.v[i].z - mean) * rstd * g.z + b.z;
     r.v[i].w = (r.v[i].w - mean) * rstd * g.w + b.w;
+  }
+}
+
+// NB rows per warp at once, read with ld.global.cg: all NB*W/128 row loads are issued before the first reduction, so a
+// lone warp (the fused LayerNorm in the residual GEMM's epilogue has only 8 per SM) keeps NB rows of L2 latency in
+// flight. Same arithmetic, in the same order, as ln_row. rows [row0, row0+NB) clipped to M; y = bf16 [M, W].
+template <int W, int NB>
+__device__ __forceinline__ void ln_rows_cg_bf16(const float* __restrict__ x, int ldx, const float* __restrict__ gamma,
+                                                const float* __restrict__ beta, float eps, __nv_bfloat16* __restrict__ y,
+                                                int row0, int M) {
+  constexpr int KV = W / 128;
+  const int lane = threadIdx.x & 31;
+  float4 v[NB][KV];
+#pragma unroll
+  for (int r = 0; r < NB; ++r) {
+    const int row = min(row0 + r, M - 1);
+#pragma unroll
+    for (int i = 0; i < KV; ++i) v[r][i] = __ldcg(reinterpret_cast<const float4*>(x + static_cast<size_t>(row) * ldx) + i * 32 + lane);
+  }
+  float mean[NB], rstd[NB];
+#pragma unroll
+  for (int r = 0; r < NB; ++r) {
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < KV; ++i) s += (v[r][i].x + v[r][i].y) + (v[r][i].z + v[r][i].w);
+    mean[r] = warp_sum(s) * (1.0f / W);
+  }
+#pragma unroll
+  for (int r = 0; r < NB; ++r) {
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < KV; ++i) {
+      const float a = v[r][i].x - mean[r], b = v[r][i].y - mean[r], c = v[r][i].z - mean[r], d = v[r][i].w - mean[r];
+      q += (a * a + b * b) + (c * c + d * d);
+    }
+    rstd[r] = rsqrtf(warp_sum(q) * (1.0f / W) + eps);
+  }
+#pragma unroll
+  for (int i = 0; i < KV; ++i) {
+    const float4 g = __ldg(reinterpret_cast<const float4*>(gamma) + i * 32 + lane);
+    const float4 b = __ldg(reinterpret_cast<const float4*>(beta) + i * 32 + lane);
+#pragma unroll
+    for (int r = 0; r < NB; ++r) {
+      if (row0 + r < M) {
+        const float o0 = (v[r][i].x - mean[r]) * rstd[r] * g.x + b.x, o1 = (v[r][i].y - mean[r]) * rstd[r] * g.y + b.y;
+        const float o2 = (v[r][i].z - mean[r]) * rstd[r] * g.z + b.z, o3 = (v[r][i].w - mean[r]) * rstd[r] * g.w + b.w;
+        reinterpret_cast<uint2*>(y + static_cast<size_t>(row0 + r) * W)[i * 32 + lane] =
+            make_uint2(pack_bf16(o0, o1), pack_bf16(o2, o3));
+      }
+    }
   }
 }
 
