@@ -114,7 +114,7 @@ class RewardLabeler:
 
     def __init__(self, model_type: str, text, frame_hw: tuple[int, int], *, model_ckpt_dir=None,
                  clip_state_dict=None, arch: str = "ViT-B/16", use_crop: bool = False, reduce: str = "first",
-                 max_batch: int = 512, device: int | None = None, precision: str = "bf16"):
+                 max_batch: int = 1024, device: int | None = None, precision: str = "bf16"):
         head, pre = _head_for(model_type)
         if precision not in ("bf16", "fp32"):
             raise ValueError(f"precision must be 'bf16' or 'fp32', got {precision!r}")
@@ -202,7 +202,7 @@ def label_reward(
     clip_state_dict=None,
     arch="ViT-B/16",
     reduce="first",
-    max_batch=512,
+    max_batch=1024,
     slab_frames=16384,
     device=None,
     distributed=None,
@@ -328,7 +328,7 @@ def main():
     # extensions
     parser.add_argument("--arch", type=str, default="ViT-B/16")
     parser.add_argument("--reduce", type=str, default="first", choices=["first", "mean"])
-    parser.add_argument("--max_batch", type=int, default=512)
+    parser.add_argument("--max_batch", type=int, default=1024)
     parser.add_argument("--precision", type=str, default="bf16", choices=["bf16", "fp32"])
     args = parser.parse_args()
 

@@ -45,7 +45,7 @@ def parse():
     ap.add_argument("--episodes", type=int, default=500)
     ap.add_argument("--size", type=int, default=256)
     ap.add_argument("--num-frames", type=int, default=8)
-    ap.add_argument("--max-batch", type=int, default=512)
+    ap.add_argument("--max-batch", type=int, default=1024)
     ap.add_argument("--cpu-sample-frames", type=int, default=400)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
