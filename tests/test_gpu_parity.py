@@ -261,6 +261,38 @@ def test_label_reward_fp32_path_matches_reference_golden(tmp_path, name):
             assert err / LOGIT_SCALE_RANDOM_INIT <= TOL_F32_COS_ABS
 
 
+def test_label_reward_through_the_h5py_api(tmp_path):
+    """The reference's container is h5py.File(data_path, "a") (label_reward.py:69). h5py is not installable in this image,
+    so the product's h5py code path (open_store -> h5py.File, `ds[lo:hi, -1]` reads, create_dataset with
+    compression / chunks / maxshape, in-place overwrite on a re-run) is driven through the in-memory stand-in that the
+    reference itself was run on when the goldens were made (oracle/shims/h5py)."""
+    import h5py  # the oracle's stand-in (tests/_util.py puts oracle/shims on sys.path); a real h5py works the same
+    from arp_b200.label_reward import label_reward
+    meta, gold = load_golden("g1_clip_b32_64")
+    data, clip_sd, _ = rebuild_inputs(meta)
+    path = str(tmp_path / "data.hdf5")
+    f = h5py.File(path, "w")
+    for k in ("ob", "done", "reward", "act"):
+        f.create_dataset(k, data=data[k])
+    f.close()
+    for _ in range(2):                                  # second pass: keys exist -> assigned in place (:288-289)
+        label_reward("coinrun", "hard", 500, 0, meta["text"], str(tmp_path), data_path=path, model_type="clip",
+                     clip_state_dict=clip_sd, arch=meta["arch"], max_batch=64, env_type="none")
+        g = h5py.File(path, "r")
+        assert sorted(k for k in g.keys() if k.startswith("ob_")) == sorted(gold)
+        for key, ref in gold.items():
+            got = np.array(g[key][:])
+            assert got.shape == ref.shape and got.dtype == ref.dtype
+        r = np.array(g["ob_clip_reward"][:])[:, -1]
+        assert np.abs(r - gold["ob_clip_reward"][:, -1]).max() / LOGIT_SCALE_RANDOM_INIT <= TOL_COS_ABS
+        from oracle import port
+        idx = port.episode_index(data["done"][:, -1])
+        F = data["done"].shape[1]
+        gs = np.array(g["ob_clip_pos_rtg"][:])
+        for lo, hi in zip(idx[:-1], idx[1:]):
+            assert np.array_equal(gs[lo:hi], port.stack_outputs(port.discount_cumsum(r[lo:hi]), F))
+
+
 def test_rerun_overwrites_in_place_and_is_idempotent(tmp_path):
     """label_reward.py:288-289: when the keys already exist the datasets are assigned in place."""
     meta, gold = load_golden("g3_clip_b32_crop")
