@@ -334,9 +334,9 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
       if (quarter == 0) ATC_TRACE(3, qt, it);
       if (C::QT == 2) {     // wait for this warp's exp2 turn
         const int my_turn = 2 * static_cast<int>(it) + qt;
-        if (xu_turn[quarter] != my_turn) {
+        if (lds_volatile(xu_turn + quarter) != my_turn) {
           const long long t0 = clock64();
-          while (xu_turn[quarter] != my_turn) {
+          while (lds_volatile(xu_turn + quarter) != my_turn) {
             if (clock64() - t0 > ARP_WATCHDOG_CYCLES) __trap();
           }
         }
@@ -389,7 +389,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
       }
       if (C::QT == 2) {     // hand the exp2 turn to the other slot's warp of this quarter
         __syncwarp();
-        if (lane == 0) xu_turn[quarter] = 2 * static_cast<int>(it) + qt + 1;
+        if (lane == 0) sts_volatile(xu_turn + quarter, 2 * static_cast<int>(it) + qt + 1);
       }
       tmem_st_wait();
       tc_fence_before();
@@ -399,7 +399,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
         int last = 0;
         if (lane == 0) {
           __threadfence_block();
-          last = (atomicAdd(&cnt_p[qt], 1) & 3) == 3;
+          last = (atoms_add(&cnt_p[qt], 1) & 3) == 3;
           __threadfence_block();
         }
         last = __shfl_sync(0xffffffffu, last, 0);
@@ -431,7 +431,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
         int last = 0;
         if (lane == 0) {
           __threadfence_block();
-          last = (atomicAdd(&cnt_e[qt], 1) & 3) == 3;
+          last = (atoms_add(&cnt_e[qt], 1) & 3) == 3;
           __threadfence_block();
         }
         last = __shfl_sync(0xffffffffu, last, 0);

@@ -120,6 +120,22 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   }
 }
 
+// shared-memory flag / counter accesses spelled in the shared state space (a generic volatile access compiles to
+// LD.E.STRONG.SYS / a generic ATOM; these are LDS / STS / ATOMS)
+__device__ __forceinline__ int lds_volatile(const volatile int* p) {
+  int v;
+  asm volatile("ld.volatile.shared.s32 %0, [%1];" : "=r"(v) : "r"(smem_u32(const_cast<const int*>(p))) : "memory");
+  return v;
+}
+__device__ __forceinline__ void sts_volatile(volatile int* p, int v) {
+  asm volatile("st.volatile.shared.s32 [%0], %1;" ::"r"(smem_u32(const_cast<int*>(p))), "r"(v) : "memory");
+}
+__device__ __forceinline__ int atoms_add(int* p, int v) {
+  int old;
+  asm volatile("atom.shared.add.s32 %0, [%1], %2;" : "=r"(old) : "r"(smem_u32(p)), "r"(v) : "memory");
+  return old;
+}
+
 // ----------------------------------------------------------------------------
 // TMA
 // ----------------------------------------------------------------------------
