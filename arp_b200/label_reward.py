@@ -173,9 +173,36 @@ def _slabs(ep_offsets: np.ndarray, e_lo: int, e_hi: int, slab_frames: int):
         e = j
 
 
-def _rows_array(ds, lo: int, hi: int) -> np.ndarray:
+SIDECAR_SUFFIX = "_last"   # "<img_key>_last": uint8 [T,H,W,3], the scored (last stacked) frame of every row
+
+
+def write_destacked_sidecar(store, img_key: str = "ob", rows_per_pass: int = 4096) -> str:
+    """the recorder stores every row as F stacked frames in gzip chunks (1,F,H,W,3)
+    (data/PPG/trajectory_recorder.py:154-162), so scoring the LAST frame of a row inflates F times more bytes than it
+    uses (label_reward.py:268). This writes the scored frames once as "<img_key>_last" [T,H,W,3]; label_reward() reads
+    the sidecar when it exists. Returns the sidecar key."""
+    ds = store[img_key]
+    T = ds.shape[0]
+    key = img_key + SIDECAR_SUFFIX
+    if store.get(key) is not None:
+        return key
+    out = store.create_dataset(key, shape=(T,) + tuple(ds.shape[2:]), dtype=np.uint8, chunks=(1,) + tuple(ds.shape[2:]),
+                               compression="gzip")
+    for lo in range(0, T, rows_per_pass):
+        hi = min(T, lo + rows_per_pass)
+        out[lo:hi] = np.asarray(ds[lo:hi, -1])
+    return key
+
+
+def _rows_array(ds, lo: int, hi: int, sidecar=None) -> np.ndarray:
     """Rows [lo, hi) of an image dataset as a C-contiguous host array WITHOUT touching the frames that
-    are not scored when the container allows it (memory-mapped store); h5py reads only `[:, -1]`."""
+    are not scored when the container allows it (memory-mapped store); h5py reads only `[:, -1]`; a de-stacked
+    sidecar ([T,H,W,3], see write_destacked_sidecar) is read instead of the stacked dataset when present."""
+    if sidecar is not None:
+        arr = getattr(sidecar, "array", None)
+        if arr is not None and arr.flags.c_contiguous:
+            return arr[lo:hi]
+        return np.ascontiguousarray(sidecar[lo:hi])
     arr = getattr(ds, "array", None)
     if arr is not None and arr.flags.c_contiguous:
         return arr[lo:hi]                       # strided pointer goes straight to arp_label_host
@@ -243,12 +270,15 @@ def label_reward(
         e_lo, e_hi = shards[rank]
         for img_key in image_keys:
             ds = g[img_key]
+            side = g.get(img_key + SIDECAR_SUFFIX)
+            if side is not None and (side.shape[0] != ds.shape[0] or tuple(side.shape[1:]) != tuple(ds.shape[2:])):
+                side = None                      # stale or foreign sidecar: fall back to the stacked dataset
             parts_r, parts_g = [], []
             for s_lo, s_hi in _slabs(off, e_lo, e_hi, slab_frames):
                 lo, hi = int(off[s_lo]), int(off[s_hi])
                 if hi <= lo:
                     continue
-                r, _, rs, gs = labeler.label_slab(_rows_array(ds, lo, hi), off[s_lo:s_hi + 1] - lo, num_frames)
+                r, _, rs, gs = labeler.label_slab(_rows_array(ds, lo, hi, side), off[s_lo:s_hi + 1] - lo, num_frames)
                 if labeler.goal:
                     rs, gs = _goal_float64(r, off[s_lo:s_hi + 1] - lo, num_frames)
                 parts_r.append(rs)

@@ -293,6 +293,24 @@ def test_label_reward_through_the_h5py_api(tmp_path):
             assert np.array_equal(gs[lo:hi], port.stack_outputs(port.discount_cumsum(r[lo:hi]), F))
 
 
+def test_destacked_sidecar_gives_identical_labels(tmp_path):
+    """with a "<key>_last" sidecar the labeler reads 1/F of the image bytes; the labels do not change."""
+    from arp_b200.label_reward import label_reward, write_destacked_sidecar
+    from arp_b200.store import NpyStore
+    meta, _ = load_golden("g3_clip_b32_crop")
+    data, clip_sd, _ = rebuild_inputs(meta)
+    a = _run_product(tmp_path, meta, data, clip_sd, None)
+    s = NpyStore(tmp_path / "ds", "a")
+    write_destacked_sidecar(s, "ob")
+    s.close()
+    label_reward("coinrun", "hard", 500, 0, meta["text"], str(tmp_path), data_path=str(tmp_path / "ds"),
+                 model_type="clip", use_crop=True, clip_state_dict=clip_sd, arch=meta["arch"], max_batch=64, env_type="none")
+    s = NpyStore(tmp_path / "ds", "r")
+    for k, v in a.items():
+        assert np.array_equal(np.array(s[k][:]), v), k
+    s.close()
+
+
 def test_rerun_overwrites_in_place_and_is_idempotent(tmp_path):
     """label_reward.py:288-289: when the keys already exist the datasets are assigned in place."""
     meta, gold = load_golden("g3_clip_b32_crop")

@@ -135,3 +135,23 @@ def test_partition_is_contiguous_and_balanced(world):
     # fewer episodes than ranks: empty ranges, still a partition
     small = partition_episodes(np.array([0, 5, 9]), 4)
     assert small[0][0] == 0 and small[-1][1] == 2 and all(a[1] == b[0] for a, b in zip(small, small[1:]))
+
+
+def test_destacked_sidecar_roundtrip(tmp_path):
+    """"<key>_last" holds exactly ob[:, -1]; _rows_array prefers it and ignores a stale one."""
+    from arp_b200.label_reward import SIDECAR_SUFFIX, _rows_array, write_destacked_sidecar
+    from arp_b200.store import NpyStore
+    from arp_b200.synth import make_dataset, write_dataset
+    data = make_dataset(n_episodes=3, len_lo=2, len_hi=6, size=64, num_frames=4, seed=9)
+    s = NpyStore(tmp_path / "ds", "w")
+    write_dataset(s, data)
+    key = write_destacked_sidecar(s, "ob", rows_per_pass=5)
+    assert key == "ob" + SIDECAR_SUFFIX and write_destacked_sidecar(s, "ob") == key      # idempotent
+    s.close()
+    s = NpyStore(tmp_path / "ds", "r")
+    T = data["ob"].shape[0]
+    assert s[key].shape == (T, 64, 64, 3) and np.array_equal(np.array(s[key][:]), data["ob"][:, -1])
+    a = _rows_array(s["ob"], 1, T - 1, s[key])
+    b = _rows_array(s["ob"], 1, T - 1)
+    assert a.shape == (T - 2, 64, 64, 3) and np.array_equal(a, b[:, -1] if b.ndim == 5 else b)
+    s.close()
