@@ -31,7 +31,7 @@ EXPORTS = (
     "arp_set_text", "arp_label", "arp_label_host", "arp_compute_reward", "arp_encode_image", "arp_decode_only",
     "arp_scan_only", "arp_gemm_bf16", "arp_layernorm_bf16", "arp_attention", "arp_launch_count",
     "arp_profile_begin", "arp_profile_end", "arp_online_reward", "arp_preprocess_rtgs",
-    "arp_quantile_f32",
+    "arp_quantile_f32", "arp_encode_taps_chw",
 )
 PROFILE_CLASSES = ("gemm", "attention", "layernorm", "decode", "head", "scan", "other")
 
@@ -85,6 +85,7 @@ def load_library() -> C.CDLL:
     lib.arp_online_reward.argtypes = [vp, vp, i32, vp, vp, vp]
     lib.arp_preprocess_rtgs.argtypes = [vp, vp, i64, vp, i32, i32, i32, vp, vp, vp, vp, vp]
     lib.arp_quantile_f32.argtypes = [vp, vp, i64, i64, i64, vp, vp]
+    lib.arp_encode_taps_chw.argtypes = [vp, vp, i64, vp, vp, vp]
     lib.arp_encode_image.argtypes = [vp, vp, i64, i64, vp, vp]
     lib.arp_decode_only.argtypes = [vp, vp, i64, i64, vp, vp]
     lib.arp_scan_only.argtypes = [vp, vp, i64, vp, i32, i32, f32, vp, vp, vp, vp]
@@ -301,6 +302,17 @@ class Engine:
         self._check(self._lib.arp_quantile_f32(self._h, _ptr(x), x.numel(), int(k_lo), int(k_hi),
                                                C.c_void_p(out.ctypes.data), _stream_ptr(self.device)))
         return out
+
+    def encode_taps(self, chw: torch.Tensor):
+        """Frozen-CLIP features of preprocessed images: chw float32 [T,3,224,224] (device) ->
+        (taps [T, layers*width] — class-token row of every block — , clip feature [T, embed_dim])."""
+        x = chw.to(self.device, torch.float32).contiguous()
+        assert x.dim() == 4 and tuple(x.shape[1:]) == (3, 224, 224), x.shape
+        T = x.shape[0]
+        taps = torch.empty(T, self.cfg.layers * self.cfg.width, device=self.device, dtype=torch.float32)
+        feat = torch.empty(T, self.cfg.embed_dim, device=self.device, dtype=torch.float32)
+        self._check(self._lib.arp_encode_taps_chw(self._h, _ptr(x), T, _ptr(taps), _ptr(feat), _stream_ptr(self.device)))
+        return taps, feat
 
     def encode_image(self, ob: torch.Tensor) -> torch.Tensor:
         T, p, stride = self._frames_view(ob)

@@ -116,6 +116,10 @@ struct ArpHandle {
   // Last-layer pruning: every head reads only the class-token row of the last resblock's output (ln_post(x[:,0]),
   // adapter taps = CLS rows), so that block computes K/V for all tokens but Q, attention, out_proj and the MLP for
   // the class-token row only — same result, 2.4 of 35.1 GFLOP per frame less. ARP_PRUNE_LAST=0 disables.
+  // arp_encode_taps_chw: the chunk's input is a caller-preprocessed fp32 image batch instead of dataset bytes, and the
+  // class-token row of every block's output is copied out (fp32 [n, layers*W]) — the frozen-CLIP side of fine-tuning
+  const float* cur_chw = nullptr;
+  float* cur_taps32 = nullptr;
   bool prune_last = true;
   // LayerNorm fused behind the residual GEMMs (GemmArgs::ln_cnt, gemm2 MODE 4): out_proj emits ln_2(x), c_proj the next
   // block's ln_1(x), by the CTA that completes a 128-row block. Correct (all parity tests pass with ARP_LN_FUSE=1) but
@@ -1023,7 +1027,18 @@ static int encode_chunk(ArpHandle* h, int pipe, const uint8_t* ob, int64_t n, in
   const int64_t M = n * h->tokens;
   const int64_t Mcap = (int64_t)c.max_batch * h->tokens;
   bf16* patches = ws.hid;  // aliases the MLP hidden buffer (dead until layer 0's c_fc)
-  ARP_TRY(launch_decode(h, ob, n, stride, patches, DEC_OUT_PATCH_BF16, st));
+  if (h->cur_chw) {
+    ProfScope prof(h, PC_DECODE, 0.0, (double)n * (3.0 * DEC_OUT * DEC_OUT * 4 + (double)h->tokens * h->kp * 2), st);
+    patchify_chw_bf16_kernel<<<kNumSMs * 8, 256, 0, st>>>(h->cur_chw, patches, (int)n, c.patch, h->grid, h->tokens);
+    h->launches++;
+  } else {
+    ARP_TRY(launch_decode(h, ob, n, stride, patches, DEC_OUT_PATCH_BF16, st));
+  }
+  auto tap = [&](const float* xsrc_, int tok_, int l_) {      // fp32 class-token rows of block l_'s output
+    if (!h->cur_taps32) return;
+    gather_cls_f32_kernel<768><<<(unsigned)((n + 7) / 8), 256, 0, st>>>(xsrc_, h->cur_taps32, (int)n, tok_, c.layers * W, l_ * W);
+    h->launches++;
+  };
   // patch embed (+ positional embedding, + class embedding on the all-zero row 0 of each frame)
   ARP_TRY(launch_gemm(h, patches, Mcap, h->conv1, ws.x, true, ACT_NONE, M, W, h->kp, W, nullptr, nullptr, 0,
                       h->rowtab, h->tokens, st));
@@ -1066,6 +1081,7 @@ static int encode_chunk(ArpHandle* h, int pipe, const uint8_t* ob, int64_t n, in
                                                                            c.layers * W, l * W);
         h->launches++;
       }
+      tap(ws.x, h->tokens, l);
     }
     ARP_CUDA(h, cudaGetLastError());
     return ARP_OK;
@@ -1114,6 +1130,7 @@ static int encode_chunk(ArpHandle* h, int pipe, const uint8_t* ob, int64_t n, in
                                                                            l * W);
         h->launches++;
       }
+      tap(ws.xcls, 1, l);
       ws.pruned = true;
       break;
     }
@@ -1145,6 +1162,7 @@ static int encode_chunk(ArpHandle* h, int pipe, const uint8_t* ob, int64_t n, in
                                                                          c.layers * W, l * W);
       h->launches++;
     }
+    tap(ws.x, h->tokens, l);
   }
   ARP_CUDA(h, cudaGetLastError());
   return ARP_OK;
@@ -1175,8 +1193,9 @@ static int encode_chunk_f32(ArpHandle* h, int pipe, const uint8_t* ob, int64_t n
   const int64_t M = n * h->tokens;
   if (h->tokens != 197 && h->tokens != 50) return fail(h, ARP_ERR_INVALID, "unsupported token count %d", h->tokens);
   float* patches = ws.hid32;   // dead until layer 0's c_fc
-  ARP_TRY(launch_decode(h, ob, n, stride, ws.chw32, DEC_OUT_CHW_F32, st));
-  im2col_f32_kernel<<<kNumSMs * 8, 256, 0, st>>>(ws.chw32, patches, (int)n, c.patch, h->grid, h->tokens);
+  if (!h->cur_chw) ARP_TRY(launch_decode(h, ob, n, stride, ws.chw32, DEC_OUT_CHW_F32, st));
+  im2col_f32_kernel<<<kNumSMs * 8, 256, 0, st>>>(h->cur_chw ? h->cur_chw : ws.chw32, patches, (int)n, c.patch, h->grid,
+                                                 h->tokens);
   h->launches++;
   ARP_TRY(launch_sgemm(h, patches, h->kp, h->conv1, ws.x, W, F32_ACT_NONE, M, W, h->kp, nullptr, nullptr, 0, h->rowtab,
                        h->tokens, st));
@@ -1208,6 +1227,11 @@ static int encode_chunk_f32(ArpHandle* h, int pipe, const uint8_t* ob, int64_t n
                          st));
     if (h->adapter) {
       gather_cls_f32_kernel<768><<<(unsigned)((n + 7) / 8), 256, 0, st>>>(ws.x, ws.taps32, (int)n, h->tokens,
+                                                                        c.layers * W, l * W);
+      h->launches++;
+    }
+    if (h->cur_taps32) {
+      gather_cls_f32_kernel<768><<<(unsigned)((n + 7) / 8), 256, 0, st>>>(ws.x, h->cur_taps32, (int)n, h->tokens,
                                                                         c.layers * W, l * W);
       h->launches++;
     }
@@ -1388,6 +1412,28 @@ extern "C" int arp_encode_image(ArpHandle* h, const uint8_t* ob_dev, int64_t T, 
     ARP_CUDA(h, cudaGetLastError());
   }
   return ARP_OK;
+}
+
+extern "C" int arp_encode_taps_chw(ArpHandle* h, const float* chw_dev, int64_t T, float* taps_dev, float* feat_dev,
+                                   void* stream) {
+  if (!h || !chw_dev || (!taps_dev && !feat_dev) || T < 0) return fail(h, ARP_ERR_INVALID, "null argument");
+  if (h->adapter) return fail(h, ARP_ERR_INVALID, "arp_encode_taps_chw serves the frozen CLIP tower: use a clip head");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  ARP_CUDA(h, cudaSetDevice(h->cfg.device));
+  ARP_TRY(finalize_weights(h, st));
+  const int64_t B = h->cfg.max_batch;
+  const size_t img = (size_t)3 * DEC_OUT * DEC_OUT, tw = (size_t)h->cfg.layers * h->cfg.width;
+  int rc = ARP_OK;
+  for (int64_t t0 = 0; t0 < T && rc == ARP_OK; t0 += B) {
+    const int64_t n = std::min(B, T - t0);
+    h->cur_chw = chw_dev + t0 * img;
+    h->cur_taps32 = taps_dev ? taps_dev + t0 * tw : nullptr;
+    rc = encode_chunk(h, 0, nullptr, n, 0, st);
+    if (rc == ARP_OK && feat_dev) rc = head_chunk(h, 0, n, nullptr, nullptr, feat_dev + t0 * h->feat_dim, st);
+  }
+  h->cur_chw = nullptr;
+  h->cur_taps32 = nullptr;
+  return rc;
 }
 
 static int scan_launch(ArpHandle* h, const float* reward, int64_t T, const int64_t* ep_off, int n_eps, int F,

@@ -286,6 +286,31 @@ cls_attention_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* _
       __floats2bfloat162_rn(o0 * inv, o1 * inv);
 }
 
+// fp32 [T,3,224,224] (already resized / augmented / normalised by the caller) -> bf16 patch rows of the patch-embed GEMM:
+// A[b*tokens + 1 + py*G + px, c*P*P + ph*P + pw]; row b*tokens (class-token slot) = 0. One thread per 8 outputs.
+__global__ void __launch_bounds__(256)
+patchify_chw_bf16_kernel(const float* __restrict__ chw, __nv_bfloat16* __restrict__ A, int T, int P, int G, int tokens) {
+  const int K = 3 * P * P;
+  const size_t total8 = static_cast<size_t>(T) * tokens * K / 8;
+  for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total8;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const size_t e = i * 8;
+    const int col = static_cast<int>(e % K);          // 8 consecutive pw of one (c, ph): P is a multiple of 8
+    const size_t row = e / K;
+    const int tok = static_cast<int>(row % tokens);
+    const size_t b = row / tokens;
+    uint4 o = make_uint4(0, 0, 0, 0);
+    if (tok > 0) {
+      const int py = (tok - 1) / G, px = (tok - 1) % G;
+      const int c = col / (P * P), ph = (col / P) % P, pw = col % P;
+      const float* src = chw + ((b * 3 + c) * 224 + py * P + ph) * 224 + px * P + pw;
+      const float4 lo = *reinterpret_cast<const float4*>(src), hi = *reinterpret_cast<const float4*>(src + 4);
+      o = make_uint4(pack_bf16(lo.x, lo.y), pack_bf16(lo.z, lo.w), pack_bf16(hi.x, hi.y), pack_bf16(hi.z, hi.w));
+    }
+    *reinterpret_cast<uint4*>(A + e) = o;
+  }
+}
+
 // fp32 -> bf16 conversion of a contiguous buffer (weights at load time, adapter features).
 __global__ void __launch_bounds__(256)
 f32_to_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, size_t n) {

@@ -70,9 +70,12 @@ def random_clip_state_dict(arch: str = "ViT-B/16", seed: int = 0, device="cpu", 
     return sd
 
 
-def random_adapter_state_dict(arch: str = "ViT-B/16", seed: int = 0, device="cpu", clip_sd: dict | None = None) -> dict:
+def random_adapter_state_dict(arch: str = "ViT-B/16", seed: int = 0, device="cpu", clip_sd: dict | None = None,
+                              with_inverse: bool = False, action_dim: int = 15) -> dict:
     """Random CLIPMultiscaleAdapter checkpoint (inference keys only), keyed like
-    finetune_module/clip_multiscale_adapter.py's state_dict with CLIP nested under `clip_model.`."""
+    finetune_module/clip_multiscale_adapter.py's state_dict with CLIP nested under `clip_model.`.
+    with_inverse adds the training-only tensors (`inverse_layer.*`, `lambda_id`; :91-96, :111) AFTER the inference
+    ones, so the inference tensors are the same values either way."""
     patch, vw, vl, ed, tw, tl, ctx, vocab = ARCH[arch]
     device = torch.device(device)
     gen = torch.Generator(device=device).manual_seed(seed + 7919)
@@ -88,6 +91,13 @@ def random_adapter_state_dict(arch: str = "ViT-B/16", seed: int = 0, device="cpu
         sd[f"{side}_adapter.layers.3.weight"] = torch.randn(D, 2 * D, generator=gen, device=device) * math.sqrt(1.0 / (2 * D))
         sd[f"{side}_adapter.layers.3.bias"] = torch.zeros(D, device=device)
         sd[f"{side}_residual_weight"] = torch.tensor(4.0, device=device)
+    if with_inverse:
+        hid = 2 * ed   # AdapterMLP(input_dim=4*output_dim*(L+1), hidden_dim=1024, output_dim=action_dim)
+        sd["inverse_layer.layers.0.weight"] = torch.randn(hid, 4 * D, generator=gen, device=device) * math.sqrt(2.0 / (4 * D))
+        sd["inverse_layer.layers.0.bias"] = torch.zeros(hid, device=device)
+        sd["inverse_layer.layers.3.weight"] = torch.randn(action_dim, hid, generator=gen, device=device) * math.sqrt(1.0 / hid)
+        sd["inverse_layer.layers.3.bias"] = torch.zeros(action_dim, device=device)
+        sd["lambda_id"] = torch.tensor(math.log(1 / 0.07), device=device)
     return sd
 
 

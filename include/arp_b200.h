@@ -168,6 +168,16 @@ ARP_API int arp_compute_reward(ArpHandle* h, const uint8_t* ob_dev, int64_t T, i
 ARP_API int arp_encode_image(ArpHandle* h, const uint8_t* ob_dev, int64_t T, int64_t row_stride_bytes, float* feat_dev,
                      void* stream);
 
+/* The frozen-CLIP side of adapter fine-tuning (finetune_module/clip_multiscale_adapter.py:135-143 inside forward
+ * :179-252; CLIP's parameters are frozen, finetune.py:147-148): images the caller has already resized / augmented /
+ * normalised (`preprocess(x, train=True)`, :121-133), fp32 [T,3,224,224] DEVICE ->
+ *   taps_dev fp32 [T, layers*width]  class-token row of every resblock's output (what the forward hooks capture,
+ *                                    finetune_module/utils.py:6-18), block l at columns [l*width, (l+1)*width)
+ *   feat_dev fp32 [T, embed_dim]     clip_model.encode_image(image)
+ * Either output may be NULL. Clip heads only (the trainable adapter stays with the caller's autograd). */
+ARP_API int arp_encode_taps_chw(ArpHandle* h, const float* chw_dev, int64_t T, float* taps_dev, float* feat_dev,
+                        void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * seams of the reference (unit-test hooks; same kernels the hot path runs)
  * ---------------------------------------------------------------------------------------------- */

@@ -294,6 +294,41 @@ class AdapterOracle:
 
 
 # ---------------------------------------------------------------------------------------------------
+# (f)4: adapter fine-tuning forward (value only)              clip_multiscale_adapter.py:179-252
+# ---------------------------------------------------------------------------------------------------
+@torch.no_grad()
+def finetune_loss(adapter: "AdapterOracle", batch: dict, goal_conditioned: bool = False, use_vip_loss: bool = True,
+                  use_id_loss: bool = True, gamma: float = 0.98) -> float:
+    """CLIPMultiscaleAdapter.forward(batch) restated on the AdapterOracle (augmentation = identity). `adapter.sd` must
+    hold `inverse_layer.layers.{0,3}.*` and `lambda_id`; discrete actions (CrossEntropyLoss, finetune.py:139)."""
+    sd = adapter.sd
+    total = 0.0
+    for key in batch["image1"].keys():
+        imgs = [preprocess_bilinear(torch.as_tensor(batch[f"image{i}"][key])) for i in range(4)]     # :199-203
+        a0, a1, a2 = (adapter.encode_image(x) for x in imgs[:3])                                     # :207-211
+        if goal_conditioned:                                                                          # :214-218
+            a3 = adapter.encode_image(imgs[3])
+            s0, s1, s2 = (-torch.linalg.norm(a3 - a, dim=-1) for a in (a0, a1, a2))
+            other = a3
+        else:                                                                                         # :220-224
+            t = adapter.encode_text(torch.as_tensor(batch["instruct"]))
+            scale = adapter.logit_scale.exp()
+            s0, s1, s2 = (torch.diag(scale * (a @ t.T), 0) for a in (a0, a1, a2))
+            other = t
+        r = torch.as_tensor(batch["r"]).float() - 1                                                   # :227
+        vip = (1 - gamma) * -s0.mean() + torch.log(1e-8 + torch.mean(torch.exp(-(r + gamma * s2 - s1))))
+        x = torch.cat([a1, other, a2, other], dim=-1)                                                 # :233-244
+        h = torch.relu(F.linear(x, sd["inverse_layer.layers.0.weight"], sd["inverse_layer.layers.0.bias"]))
+        logits = F.linear(h, sd["inverse_layer.layers.3.weight"], sd["inverse_layer.layers.3.bias"])
+        id_loss = F.cross_entropy(logits, torch.as_tensor(batch["action"]).long())
+        if use_vip_loss:
+            total = total + vip
+        if use_id_loss:
+            total = total + sd["lambda_id"] * id_loss
+    return float(total)
+
+
+# ---------------------------------------------------------------------------------------------------
 # (f)1: online reward of a rollout                    arp_dt/envs/vl_reward.py:11-77, rollout_procgen.py:133-150
 # ---------------------------------------------------------------------------------------------------
 def _online_image(obs: np.ndarray) -> torch.Tensor:
