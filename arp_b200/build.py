@@ -44,11 +44,17 @@ def _sources_digest() -> str:
     return h.hexdigest()
 
 
+def _file_digest(path: Path) -> str:
+    return hashlib.sha256(path.read_bytes()).hexdigest()
+
+
 def build(force: bool = False, verbose: bool = False) -> Path:
     """Compile csrc/*.cu into _lib/libarp_b200.so if sources changed. Returns the library path."""
     LIBDIR.mkdir(exist_ok=True)
     digest = _sources_digest()
-    if not force and LIB.exists() and STAMP.exists() and STAMP.read_text().strip() == digest:
+    # the stamp binds the SOURCES to the BINARY: "<sources sha256> <library sha256>". A stamp restored by git next to a
+    # library built from other sources (a stash / checkout while experimenting) must not pass for up to date.
+    if not force and LIB.exists() and STAMP.exists() and STAMP.read_text().split() == [digest, _file_digest(LIB)]:
         return LIB
     cmd = [_nvcc(), *NVCC_FLAGS, "-o", str(LIB), str(CSRC / "capi.cu")]
     if verbose:
@@ -60,7 +66,7 @@ def build(force: bool = False, verbose: bool = False) -> Path:
         raise RuntimeError(f"nvcc failed:\n{res.stdout}\n{res.stderr}")
     if verbose:
         print(res.stderr, file=sys.stderr)
-    STAMP.write_text(digest)
+    STAMP.write_text(f"{digest} {_file_digest(LIB)}")
     return LIB
 
 
