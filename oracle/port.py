@@ -293,6 +293,19 @@ class AdapterOracle:
         return r.float().cpu().numpy()
 
 
+def _adapter_compute_reward_goal(self, images: np.ndarray, use_crop: bool = False) -> np.ndarray:
+    """label_reward.py:180-196 (`clip_*_goal_conditioned`): distance of every frame's adapted feature to the episode's
+    LAST frame — POSITIVE here (no `-1 *`, unlike the plain-CLIP branch :160), float64 through `.item()`."""
+    if use_crop:
+        s = images.shape[-2]
+        images = center_crop_np(images, (s // 2, s // 2))
+    f = self.encode_image(preprocess_bilinear(torch.from_numpy(np.ascontiguousarray(images))))
+    return np.array([torch.norm(x - f[-1], p=2).item() for x in f])
+
+
+AdapterOracle.compute_reward_goal = _adapter_compute_reward_goal
+
+
 # ---------------------------------------------------------------------------------------------------
 # (f)4: adapter fine-tuning forward (value only)              clip_multiscale_adapter.py:179-252
 # ---------------------------------------------------------------------------------------------------
@@ -445,6 +458,8 @@ def label_reward_port(data: dict, *, model=None, adapter: AdapterOracle | None =
             r = compute_reward_clip(model, imgs, text, use_crop, reduce, preprocess)
         elif model_type == "clip_goal_conditioned":
             r = compute_reward_clip_goal(model, imgs, use_crop)
+        elif "_goal_conditioned" in model_type:
+            r = adapter.compute_reward_goal(imgs, use_crop)
         else:
             r = adapter.compute_reward(imgs, text, use_crop, ensemble="ensemble" in model_type, reduce=reduce)
         g = discount_cumsum(r)

@@ -242,6 +242,34 @@ def test_label_reward_matches_reference_golden(tmp_path, name):
     assert np.abs(out[gk] - gold[gk]).max() <= (2e-2 if goal else TOL_REWARD_REL_TO_MAX) * max(np.abs(gold[gk]).max(), 1e-6) * 4
 
 
+@pytest.mark.parametrize("model_type", ["clip_multiscale_ensemble", "clip_ft_goal_conditioned"])
+def test_adapter_variants_the_reference_cannot_run_match_the_port(tmp_path, model_type):
+    """BASELINE configs[2] names `clip_multiscale_ensemble`; in the reference every `clip_*` name except `clip_ft` reaches
+    `model.load_state_dict` with `model` unbound (label_reward.py:165-176), so no golden can exist. The
+    compute_reward bodies behind them are restated in the port (:180-196 positive feature distance, float64; :217-222
+    per-scale normalised features, logits / 13) and the product is held to the port on the clip_ft golden's inputs."""
+    from oracle import port
+    meta, _ = load_golden("g6_clipft_b16_64")
+    data, clip_sd, adapter_sd = rebuild_inputs(meta)
+    meta = dict(meta, model_type=model_type)
+    out = _run_product(tmp_path, meta, data, clip_sd, adapter_sd)
+    ref = port.label_reward_port(data, adapter=port.AdapterOracle(adapter_sd, meta["arch"]), model_type=model_type,
+                                 text=meta["text"], preprocess="bilinear")
+    rk, gk = f"ob_{model_type}_reward", f"ob_{model_type}_pos_rtg"
+    assert sorted(out) == [gk, rk]
+    n = ref["frames"]
+    r, r_ref = out[rk][:n, -1], ref["reward"]
+    assert out[rk].dtype == ref[rk].dtype == (np.float64 if "goal" in model_type else np.float32)
+    if "goal" in model_type:
+        assert r.min() >= 0 and np.abs(r - r_ref).max() <= 2e-2 * np.abs(r_ref).max()
+        for lo, hi in zip(ref["g_traj_idx"][:-1], ref["g_traj_idx"][1:]):
+            assert r[hi - 1] == 0.0                                     # the goal frame itself
+    else:
+        dcos = np.abs(r - r_ref).max() / LOGIT_SCALE_RANDOM_INIT
+        assert dcos <= TOL_COS_ABS, f"|dcos| {dcos:.2e}"
+    assert np.abs(out[gk][:n] - ref[gk]).max() <= 2e-2 * max(np.abs(ref[gk]).max(), 1e-6) * 4
+
+
 @pytest.mark.parametrize("name", golden_names())
 def test_label_reward_fp32_path_matches_reference_golden(tmp_path, name):
     """precision="fp32": the same pipeline with fp32 weights / activations / FMA contractions must reproduce the
