@@ -174,6 +174,8 @@ struct ArpHandle {
     float *chw32 = nullptr, *xn32 = nullptr, *qkv32 = nullptr, *attn32 = nullptr, *hid32 = nullptr;
     float *taps32 = nullptr, *hid2_32 = nullptr;
   } ws[2];
+  int gemm_sms = kNumSMs, attn_sms = kNumSMs;   // persistent-grid caps (ARP_GEMM_SMS / ARP_ATTN_SMS): with ARP_PIPES=2 a
+                                               // partition lets one chunk's attention run beside the other's GEMMs
   int n_pipes = 1;                       // ARP_PIPES=2: two chunks in flight (measured: no gain on B200 — a resident
                                          // persistent GEMM CTA leaves no room the scheduler will give to another kernel)
   cudaStream_t pipe_stream[2] = {nullptr, nullptr};
@@ -548,6 +550,8 @@ extern "C" int arp_create(const ArpConfig* cfg, ArpHandle** out) {
   const size_t B = cfg->max_batch, M = B * h->tokens, W = cfg->width;
 #define CREATE_TRY(e) do { int _r = (e); if (_r != ARP_OK) return bail(_r); } while (0)
   if (const char* e = getenv("ARP_PIPES")) h->n_pipes = atoi(e) == 2 ? 2 : 1;
+  if (const char* e = getenv("ARP_GEMM_SMS")) h->gemm_sms = std::max(2, std::min(kNumSMs, atoi(e)));
+  if (const char* e = getenv("ARP_ATTN_SMS")) h->attn_sms = std::max(1, std::min(kNumSMs, atoi(e)));
   CREATE_TRY(dev_alloc(h, &h->rowtab, (size_t)h->tokens * W));
   for (int p = 0; p < h->n_pipes; ++p) {
     ArpHandle::Work& w = h->ws[p];
@@ -841,7 +845,7 @@ static int launch_gemm2(ArpHandle* h, const bf16* a, int64_t a_rows_alloc, const
     g.resid = nullptr;
   }
   const int tiles = (int)((g.M + GEMM_BM * cg - 1) / (GEMM_BM * cg)) * (g.N / GEMM_BN);
-  const int grid = std::min(tiles * cg, kNumSMs / cg * cg);
+  const int grid = std::min(tiles * cg, h->gemm_sms / cg * cg);
   const int smem = cg == 2 ? G2Cfg<2>::SMEM_BYTES : G2Cfg<1>::SMEM_BYTES;
   ProfScope prof(h, PC_GEMM, 2.0 * (double)g.M * g.N * g.K,
                  (double)g.M * g.K * 2 + (double)g.N * g.K * 2 + (double)g.M * g.N * (out_f32 ? 4 : 2) * (reduce || resid_ln ? 2 : 1) +
@@ -988,7 +992,7 @@ static int launch_attention(ArpHandle* h, const bf16* qkv, bf16* out, int B, int
     const CUtensorMap *tq, *tkv;
     ARP_TRY(get_tmap(h, qkv, rows, 3 * W, 3 * W, 128, &tq));
     ARP_TRY(get_tmap(h, qkv, rows, 3 * W, 3 * W, nk, &tkv));
-    const int grid = std::min(B * h->cfg.heads, kNumSMs);
+    const int grid = std::min(B * h->cfg.heads, h->attn_sms);
     const int rev = h->snake ? (h->dir ^= 1) : 0;
     if (tokens == 197)
       attention_tc_kernel<197><<<grid, ATC_THREADS, AtcCfg<197>::SMEM_BYTES, st>>>(*tq, *tkv, out, B, h->cfg.heads, W, scale_log2e, rev);
