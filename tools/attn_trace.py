@@ -24,7 +24,7 @@ torch.cuda.synchronize()
 n = lib.arp_debug_attn_trace(C.c_void_p(buf.ctypes.data), len(buf))
 tr = buf.reshape(2, ITEMS, EV)
 t0 = tr[tr > 0].min()
-names = ["S_issue", "PV_issue", "S_ready", "pass1_done", "turn", "P_arrive", "O_ready", "epi_done", "PV_seen", "S_seen"]
+names = ["S_issue", "PV_issue", "S_ready", "pass1_done", "turn", "P_arrive", "O_ready", "epi_done", "pass2_end", "st_waited"]
 rows = [(tr[s, i, e] - t0, s, i, names[e]) for s in range(2) for i in range(ITEMS) for e in range(EV) if tr[s, i, e] > 0]
 for t, s, i, nm in sorted(rows):
     if 3 <= i < 6:
