@@ -21,7 +21,7 @@
 extern "C" {
 #endif
 
-#define ARP_B200_ABI_VERSION 2
+#define ARP_B200_ABI_VERSION 3   /* 3: + arp_encode_taps_chw (additive) */
 
 #if defined(__GNUC__)
 #define ARP_API __attribute__((visibility("default")))
