@@ -16,7 +16,7 @@ eng = capi.Engine(device=0, max_batch=8)
 lib = eng._lib
 B, L = 512, 197
 qkv = (torch.randn(B * L, 2304, device="cuda") * 1.5).bfloat16()
-ITEMS, EV = 10, 10
+ITEMS, EV = 10, 24
 buf = np.zeros(2 * ITEMS * EV, np.int64)
 for _ in range(3):
     eng.attention(qkv, B, L)
@@ -24,7 +24,7 @@ torch.cuda.synchronize()
 n = lib.arp_debug_attn_trace(C.c_void_p(buf.ctypes.data), len(buf))
 tr = buf.reshape(2, ITEMS, EV)
 t0 = tr[tr > 0].min()
-names = ["S_issue", "PV_issue", "S_ready", "pass1_done", "turn", "P_arrive", "O_ready", "epi_done", "pass2_end", "st_waited"]
+names = ["S_issue", "PV_issue", "S_ready", "pass1_done", "turn", "P_arrive", "O_ready", "epi_done"] + [f"pass2_end.q{q}" for q in range(4)] + [f"O_seen.q{q}" for q in range(4)] + [f"drained.q{q}" for q in range(4)] + [f"st_waited.q{q}" for q in range(4)]
 rows = [(tr[s, i, e] - t0, s, i, names[e]) for s in range(2) for i in range(ITEMS) for e in range(EV) if tr[s, i, e] > 0]
 for t, s, i, nm in sorted(rows):
     if 3 <= i < 6:
