@@ -144,8 +144,9 @@ __device__ __forceinline__ void tmem_st_32x16(uint32_t taddr, const uint32_t (&r
 
 #ifdef ARP_ATTN_TRACE
 // dev-only timeline of block 0: clock64 stamps kept in shared memory (a plain st.shared per event), dumped at exit.
-// events: 0 S_issue 1 PV_issue 2 S_ready 3 pass1_done 4 turn_acquired 5 P_arrive 6 O_ready 7 epilogue_done
-constexpr int ATC_TR_ITEMS = 10, ATC_TR_EVENTS = 10;
+// events: 0 S_issue 1 PV_issue 2 S_ready 3 pass1_done 4 turn_acquired 5 P_arrive 6 O_ready 7 epilogue_done (quarter-0
+// warps), then per lane quarter q: 8+q pass2_end, 12+q O_seen, 16+q drained, 20+q P stores retired
+constexpr int ATC_TR_ITEMS = 10, ATC_TR_EVENTS = 24;
 __device__ long long g_attn_trace[2 * ATC_TR_ITEMS * ATC_TR_EVENTS];
 #define ATC_TRACE(ev, slot, item)                                                                              \
   do {                                                                                                         \
@@ -391,7 +392,9 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
         __syncwarp();
         if (lane == 0) sts_volatile(xu_turn + quarter, 2 * static_cast<int>(it) + qt + 1);
       }
+      ATC_TRACE(8 + quarter, qt, it);
       tmem_st_wait();
+      ATC_TRACE(20 + quarter, qt, it);
       tc_fence_before();
       __syncwarp();
       {
@@ -418,6 +421,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
       mbar_wait(&o_full[qt], ph);
       tc_fence_after();
       if (quarter == 0) ATC_TRACE(6, qt, it);
+      ATC_TRACE(12 + quarter, qt, it);
       uint32_t o0[32], o1[32], osum[16];
       tmem_ld_32x32(t_s + C::O_COL, o0);
       tmem_ld_32x32(t_s + C::O_COL + 32, o1);
@@ -445,6 +449,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
         }
       }
       if (quarter == 0) ATC_TRACE(7, qt, it);
+      ATC_TRACE(16 + quarter, qt, it);
       if (qrow < L) {
         uint4* dst = reinterpret_cast<uint4*>(out + (static_cast<size_t>(frame) * L + qrow) * width + head * ATC_DH);
 #pragma unroll
