@@ -127,7 +127,7 @@ struct ArpHandle {
   // A stream has evicted the block's x rows from L2 (ncu: DRAM reads 0.94 -> 1.67 GB, L2 hit 52 %), the gpu-scope
   // fence of the hand-off invalidates L1 every tile, and 8 epilogue warps per SM hide HBM latency far worse than the
   // standalone kernel's 64 (c_proj 320 -> 505 us, out_proj 125 -> 394 us vs 2 x 63 us of LayerNorm kernels saved).
-  bool ln_fuse = false;
+  int ln_fuse = 0;      // bit 0: ln_2 behind out_proj, bit 1: next block's ln_1 behind c_proj (ARP_LN_FUSE=1 both, 2 / 3 one)
   bool f32 = false;   // cfg.precision == ARP_PREC_F32: verification path (fp32_path.cuh); GEMM weights are stored as fp32
   int attn_impl = 2;  // 1 = mma.sync kernel, 2 = tcgen05 kernel (ARP_ATTN_IMPL overrides)
   int gemm_impl = 3;  // 1 = v1 (register stores), 2 = v2 single-CTA, 3 = v2 CTA pairs (ARP_GEMM_IMPL overrides)
@@ -530,10 +530,10 @@ extern "C" int arp_create(const ArpConfig* cfg, ArpHandle** out) {
   if (const char* e = getenv("ARP_ATTN_IMPL")) h->attn_impl = atoi(e) == 1 ? 1 : 2;
   if (const char* e = getenv("ARP_SNAKE")) h->snake = atoi(e) != 0;
   if (const char* e = getenv("ARP_PRUNE_LAST")) h->prune_last = atoi(e) != 0;
-  if (const char* e = getenv("ARP_LN_FUSE")) h->ln_fuse = atoi(e) != 0;
+  if (const char* e = getenv("ARP_LN_FUSE")) { const int v = atoi(e); h->ln_fuse = v == 1 ? 3 : v == 2 ? 1 : v == 3 ? 2 : 0; }
   if (const char* e = getenv("ARP_LN_FOLD")) h->ln_fold = std::max(0, std::min(2, atoi(e)));
   if (h->gemm_impl < 2 || h->f32) h->ln_fold = 0;   // the fold lives in the v2 epilogue
-  if (h->gemm_impl < 2 || h->f32) h->ln_fuse = false;
+  if (h->gemm_impl < 2 || h->f32) h->ln_fuse = 0;
   h->grid = DEC_OUT / cfg->patch;
   h->tokens = h->grid * h->grid + 1;
   h->kp = 3 * cfg->patch * cfg->patch;
@@ -1141,7 +1141,7 @@ static int encode_chunk(ArpHandle* h, int pipe, const uint8_t* ob, int64_t n, in
     ARP_TRY(launch_gemm(h, ws.xn, Mcap, L.w_qkv, ws.qkv, false, ACT_NONE, M, 3 * W, W, 3 * W, L.b_qkv, nullptr, 0,
                         nullptr, 0, st));
     ARP_TRY(launch_attention(h, ws.qkv, ws.attn, (int)n, h->tokens, st, Mcap));
-    if (h->ln_fuse) {
+    if (h->ln_fuse & 1) {
       const LnFuseArgs f2{L.ln2_g, L.ln2_b, ws.xn, ws.ln_cnt};
       ARP_TRY(launch_gemm(h, ws.attn, Mcap, L.w_out, ws.x, true, ACT_NONE, M, W, W, W, L.b_out, ws.x, W, nullptr, 0, st,
                           nullptr, &f2));
@@ -1151,7 +1151,7 @@ static int encode_chunk(ArpHandle* h, int pipe, const uint8_t* ob, int64_t n, in
     }
     ARP_TRY(launch_gemm(h, ws.xn, Mcap, L.w_fc, ws.hid, false, ACT_QUICKGELU, M, 4 * W, W, 4 * W, L.b_fc, nullptr, 0,
                         nullptr, 0, st));
-    if (h->ln_fuse && l + 1 < c.layers) {
+    if ((h->ln_fuse & 2) && l + 1 < c.layers) {
       const LayerW& Ln = h->layers[l + 1];
       const LnFuseArgs f1{Ln.ln1_g, Ln.ln1_b, ws.xn, ws.ln_cnt};
       ARP_TRY(launch_gemm(h, ws.hid, Mcap, L.w_proj, ws.x, true, ACT_NONE, M, W, 4 * W, W, L.b_proj, ws.x, W, nullptr, 0,
