@@ -155,3 +155,43 @@ def test_destacked_sidecar_roundtrip(tmp_path):
     b = _rows_array(s["ob"], 1, T - 1)
     assert a.shape == (T - 2, 64, 64, 3) and np.array_equal(a, b[:, -1] if b.ndim == 5 else b)
     s.close()
+
+
+# ---- property tests (hypothesis): ragged, empty and degenerate episode layouts -------------------------------------
+from hypothesis import given, settings, strategies as st  # noqa: E402
+
+
+@settings(max_examples=200, deadline=None)
+@given(lens=st.lists(st.integers(0, 999), min_size=0, max_size=60), world=st.integers(1, 9), first=st.integers(0, 50))
+def test_partition_properties(lens, world, first):
+    """Any episode layout (zero-length episodes, fewer episodes than ranks, a non-zero first offset): the ranges are a
+    contiguous partition in file order, and no rank is further from its fair share than the longest episode."""
+    off = first + np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
+    parts = partition_episodes(off, world)
+    n = len(lens)
+    assert len(parts) == world and parts[0][0] == 0 and parts[-1][1] == n
+    assert all(a <= b for a, b in parts) and all(a[1] == b[0] for a, b in zip(parts, parts[1:]))
+    total = int(off[-1] - off[0])
+    longest = max(lens, default=0)
+    ends = [int(off[b] - off[0]) for _, b in parts]
+    for k, e in enumerate(ends[:-1], start=1):
+        assert abs(e - total * k / world) <= longest       # every cut sits within one episode of its ideal place
+
+
+@settings(max_examples=200, deadline=None)
+@given(lens=st.lists(st.integers(0, 400), min_size=1, max_size=40), budget=st.integers(1, 600), data=st.data())
+def test_slabs_properties(lens, budget, data):
+    """Slabs are whole episodes in order, cover exactly [e_lo, e_hi), and only a single over-long episode may exceed
+    the frame budget."""
+    off = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
+    n = len(lens)
+    e_lo = data.draw(st.integers(0, n))
+    e_hi = data.draw(st.integers(e_lo, n))
+    slabs = list(_slabs(off, e_lo, e_hi, budget))
+    if e_lo == e_hi:
+        assert slabs == []
+        return
+    assert slabs[0][0] == e_lo and slabs[-1][1] == e_hi
+    assert all(a < b for a, b in slabs) and all(a[1] == b[0] for a, b in zip(slabs, slabs[1:]))
+    for a, b in slabs:
+        assert off[b] - off[a] <= budget or b == a + 1
