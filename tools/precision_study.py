@@ -39,11 +39,23 @@ def rnd(t, fmt):
     return t.to(torch.bfloat16 if fmt == "bf16" else torch.float16).float()
 
 
-def tower(op: str, resid: str, p_fmt: str | None = None):
+def tower(op: str, resid: str, p_fmt: str | None = None, fold: bool = False):
     """op = operand format of every contraction, resid = storage format of the residual stream, p_fmt = format of the
-    softmax weights fed to P.V (defaults to op)."""
+    softmax weights fed to P.V (defaults to op); fold = LayerNorm folded into the consumer GEMM:
+    the operand is the rounded RAW x, the weight is rounded gamma*W, and rstd*(acc - mu*colsum) + beta W^T is applied
+    after the contraction."""
     p_fmt = p_fmt or op
     mm = lambda a, w: rnd(a, op) @ rnd(w, op).t()  # noqa: E731
+
+    def ln_mm(x, pfx, w, b):
+        if not fold:
+            return mm(F.layer_norm(x, (768,), sd[pfx + ".weight"], sd[pfx + ".bias"], 1e-5), w) + b
+        g, beta = sd[pfx + ".weight"], sd[pfx + ".bias"]
+        wg = rnd(w * g, op)
+        acc = rnd(x, op) @ wg.t()
+        mu = x.mean(-1, keepdim=True)
+        rstd = torch.rsqrt(x.var(-1, unbiased=False, keepdim=True) + 1e-5)
+        return rstd * (acc - mu * wg.sum(1)) + (beta @ w.t() + b)
     W, heads = 768, 12
     patches = F.unfold(x0, 16, stride=16).transpose(1, 2)                        # [N,196,768]
     x = mm(patches, sd["visual.conv1.weight"].reshape(W, -1))
@@ -52,8 +64,7 @@ def tower(op: str, resid: str, p_fmt: str | None = None):
     x = rnd(ln(x, "visual.ln_pre"), resid)
     for l in range(12):
         p = f"visual.transformer.resblocks.{l}."
-        h = ln(x, p + "ln_1")
-        qkv = rnd(mm(h, sd[p + "attn.in_proj_weight"]) + sd[p + "attn.in_proj_bias"], op)    # stored in the operand format
+        qkv = rnd(ln_mm(x, p + "ln_1", sd[p + "attn.in_proj_weight"], sd[p + "attn.in_proj_bias"]), op)  # stored as operands
         q, k, v = (t.view(N, 197, heads, 64).transpose(1, 2) for t in qkv.chunk(3, -1))
         s = (q @ k.transpose(-1, -2)) * 0.125
         pw = torch.softmax(s, -1)
@@ -61,8 +72,7 @@ def tower(op: str, resid: str, p_fmt: str | None = None):
         o = (pw @ v) / pw.sum(-1, keepdim=True)                                 # normalised by the rounded weights' own sum
         o = rnd(o.transpose(1, 2).reshape(N, 197, W), op)
         x = rnd(x + mm(o, sd[p + "attn.out_proj.weight"]) + sd[p + "attn.out_proj.bias"], resid)
-        h = ln(x, p + "ln_2")
-        h = mm(h, sd[p + "mlp.c_fc.weight"]) + sd[p + "mlp.c_fc.bias"]
+        h = ln_mm(x, p + "ln_2", sd[p + "mlp.c_fc.weight"], sd[p + "mlp.c_fc.bias"])
         h = rnd(h * torch.sigmoid(1.702 * h), op)
         x = rnd(x + mm(h, sd[p + "mlp.c_proj.weight"]) + sd[p + "mlp.c_proj.bias"], resid)
     f = ln(x[:, 0], "visual.ln_post") @ sd["visual.proj"]
@@ -71,8 +81,10 @@ def tower(op: str, resid: str, p_fmt: str | None = None):
 
 ref = tower("fp32", "fp32")
 print(f"{N} frames, |cos| of the reference: mean {ref.abs().mean():.3e}, max {ref.abs().max():.3e}")
-print(f"{'operands':8s} {'residual':8s} {'P':5s}  max|dcos|   mean|dcos|")
-for op, resid, pf in (("bf16", "fp32", None), ("fp16", "fp32", None), ("fp16", "fp32", "bf16"), ("bf16", "bf16", None),
-                      ("bf16", "fp16", None), ("fp16", "fp16", None), ("fp16", "bf16", None)):
-    d = (tower(op, resid, pf) - ref).abs()
-    print(f"{op:8s} {resid:8s} {(pf or op):5s}  {d.max():.3e}   {d.mean():.3e}")
+print(f"{'operands':8s} {'residual':8s} {'P':5s} {'LN':5s}  max|dcos|   mean|dcos|")
+for op, resid, pf, fold in (("bf16", "fp32", None, False), ("fp16", "fp32", None, False), ("fp16", "fp32", "bf16", False),
+                            ("bf16", "bf16", None, False), ("bf16", "fp16", None, False), ("fp16", "fp16", None, False),
+                            ("fp16", "bf16", None, False), ("bf16", "fp32", None, True), ("fp16", "fp32", None, True),
+                            ("fp16", "fp16", None, True)):
+    d = (tower(op, resid, pf, fold) - ref).abs()
+    print(f"{op:8s} {resid:8s} {(pf or op):5s} {'fold' if fold else 'own':5s}  {d.max():.3e}   {d.mean():.3e}")
