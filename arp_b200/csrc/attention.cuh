@@ -49,24 +49,24 @@ struct AttnCfg {
 // out: bf16 [B*L, width].
 template <int L>
 __global__ void __launch_bounds__(ATT_THREADS)
-attention_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ out, int width,
+attention_kernel(const op_t* __restrict__ qkv, op_t* __restrict__ out, int width,
                  float scale_log2e) {
   using C = AttnCfg<L>;
   extern __shared__ __align__(16) uint8_t att_smem[];
-  __nv_bfloat16* sK = reinterpret_cast<__nv_bfloat16*>(att_smem);
-  __nv_bfloat16* sV = sK + C::LP * ATT_ROW;
+  op_t* sK = reinterpret_cast<op_t*>(att_smem);
+  op_t* sV = sK + C::LP * ATT_ROW;
 
   const int head = blockIdx.x;
   const int frame = blockIdx.y;
   const int ld = 3 * width;
-  const __nv_bfloat16* base = qkv + static_cast<size_t>(frame) * L * ld + head * ATT_DH;
+  const op_t* base = qkv + static_cast<size_t>(frame) * L * ld + head * ATT_DH;
 
   // ---- stage K and V (16-byte loads; padded tail rows zeroed so 0 * garbage never makes a NaN) ----
   for (int i = threadIdx.x; i < C::LP * 8; i += ATT_THREADS) {
     const int row = i >> 3, ch = i & 7;
     uint4 k = make_uint4(0, 0, 0, 0), v = make_uint4(0, 0, 0, 0);
     if (row < L) {
-      const __nv_bfloat16* p = base + static_cast<size_t>(row) * ld + ch * 8;
+      const op_t* p = base + static_cast<size_t>(row) * ld + ch * 8;
       k = *reinterpret_cast<const uint4*>(p + width);
       v = *reinterpret_cast<const uint4*>(p + 2 * width);
     }
@@ -87,8 +87,8 @@ attention_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restric
     uint32_t qa[4][4];
     {
       const int r0 = q0 + g, r1 = q0 + g + 8;
-      const __nv_bfloat16* p0 = base + static_cast<size_t>(r0) * ld;
-      const __nv_bfloat16* p1 = base + static_cast<size_t>(r1) * ld;
+      const op_t* p0 = base + static_cast<size_t>(r0) * ld;
+      const op_t* p1 = base + static_cast<size_t>(r1) * ld;
 #pragma unroll
       for (int ks = 0; ks < 4; ++ks) {
         const int c = ks * 16 + 2 * t;
@@ -150,10 +150,10 @@ attention_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restric
 #pragma unroll
     for (int kk = 0; kk < C::MT; ++kk) {
       uint32_t pa[4];
-      pa[0] = pack_bf16(s[2 * kk][0], s[2 * kk][1]);
-      pa[1] = pack_bf16(s[2 * kk][2], s[2 * kk][3]);
-      pa[2] = pack_bf16(s[2 * kk + 1][0], s[2 * kk + 1][1]);
-      pa[3] = pack_bf16(s[2 * kk + 1][2], s[2 * kk + 1][3]);
+      pa[0] = pack_op(s[2 * kk][0], s[2 * kk][1]);
+      pa[1] = pack_op(s[2 * kk][2], s[2 * kk][3]);
+      pa[2] = pack_op(s[2 * kk + 1][0], s[2 * kk + 1][1]);
+      pa[3] = pack_op(s[2 * kk + 1][2], s[2 * kk + 1][3]);
 #pragma unroll
       for (int np = 0; np < 4; ++np) {
         // matrices: keys kk*16 + {0..7, 8..15} x dh (np*16 + {0, 8}); transposed on load
@@ -168,15 +168,15 @@ attention_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restric
     // ---- normalise and store ----
     const float i0 = 1.0f / l0, i1 = 1.0f / l1;
     const int r0 = q0 + g, r1 = q0 + g + 8;
-    __nv_bfloat16* ob = out + static_cast<size_t>(frame) * L * width + head * ATT_DH + 2 * t;
+    op_t* ob = out + static_cast<size_t>(frame) * L * width + head * ATT_DH + 2 * t;
 #pragma unroll
     for (int nd = 0; nd < 8; ++nd) {
       if (r0 < L)
         *reinterpret_cast<uint32_t*>(ob + static_cast<size_t>(r0) * width + nd * 8) =
-            pack_bf16(o[nd][0] * i0, o[nd][1] * i0);
+            pack_op(o[nd][0] * i0, o[nd][1] * i0);
       if (r1 < L)
         *reinterpret_cast<uint32_t*>(ob + static_cast<size_t>(r1) * width + nd * 8) =
-            pack_bf16(o[nd][2] * i1, o[nd][3] * i1);
+            pack_op(o[nd][2] * i1, o[nd][3] * i1);
     }
   }
 }

@@ -27,7 +27,7 @@
 #include "scan.cuh"
 
 using namespace arp;
-typedef __nv_bfloat16 bf16;
+typedef arp::op_t bf16;   // the operand format (common.cuh: bf16 by default, fp16 with -DARP_OP_FP16=1)
 
 // ------------------------------------------------------------------------------------------------
 // errors

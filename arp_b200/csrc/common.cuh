@@ -7,6 +7,7 @@
 
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -53,8 +54,33 @@ __device__ __forceinline__ float warp_max(float v) {
   return v;
 }
 
-__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
-  __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+// ----------------------------------------------------------------------------
+// The 16-bit OPERAND format of every contraction (GEMM A / W, Q K V, attention output, MLP hidden): bf16 by default,
+// fp16 with -DARP_OP_FP16=1. tcgen05 kind::f16 runs both at the same rate with fp32 accumulation; fp16 carries three more
+// mantissa bits (tools/precision_study.py: max |dcos| 4.5e-5 against 3.8e-4) at the range the reference's own CUDA path
+// uses (clip.load keeps fp16 weights). Everything below names the format only through these.
+// ----------------------------------------------------------------------------
+#ifndef ARP_OP_FP16
+#define ARP_OP_FP16 0
+#endif
+#if ARP_OP_FP16
+using op_t = __half;
+using op2_t = __half2;
+constexpr uint32_t kOpFormat = 0;   // kind::f16 instruction descriptor a_format / b_format: 0 = F16
+__device__ __forceinline__ op2_t floats_to_op2(float lo, float hi) { return __floats2half2_rn(lo, hi); }
+__device__ __forceinline__ op_t float_to_op(float v) { return __float2half_rn(v); }
+__device__ __forceinline__ float op_to_float(op_t v) { return __half2float(v); }
+#else
+using op_t = __nv_bfloat16;
+using op2_t = __nv_bfloat162;
+constexpr uint32_t kOpFormat = 1;   // 1 = BF16
+__device__ __forceinline__ op2_t floats_to_op2(float lo, float hi) { return __floats2bfloat162_rn(lo, hi); }
+__device__ __forceinline__ op_t float_to_op(float v) { return __float2bfloat16_rn(v); }
+__device__ __forceinline__ float op_to_float(op_t v) { return __bfloat162float(v); }
+#endif
+
+__device__ __forceinline__ uint32_t pack_op(float lo, float hi) {
+  op2_t v = floats_to_op2(lo, hi);
   return *reinterpret_cast<uint32_t*>(&v);
 }
 
@@ -319,10 +345,10 @@ __device__ __forceinline__ uint64_t umma_desc_kmajor_sw128(uint32_t smem_addr) {
   return d;
 }
 
-// Instruction descriptor for kind::f16, bf16 x bf16 -> fp32, both operands K-major.
-// c_format [4,6)=1 (F32) | a_format [7,10)=1 (BF16) | b_format [10,13)=1 | N>>3 [17,23) | M>>4 [24,29).
+// Instruction descriptor for kind::f16, op_t x op_t -> fp32, both operands K-major.
+// c_format [4,6)=1 (F32) | a_format [7,10) = b_format [10,13) = kOpFormat (0 F16, 1 BF16) | N>>3 [17,23) | M>>4 [24,29).
 __host__ __device__ constexpr uint32_t umma_idesc_bf16(int M, int N, int a_mn_major = 0, int b_mn_major = 0) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(a_mn_major) << 15) |
+  return (1u << 4) | (kOpFormat << 7) | (kOpFormat << 10) | (static_cast<uint32_t>(a_mn_major) << 15) |
          (static_cast<uint32_t>(b_mn_major) << 16) | (static_cast<uint32_t>(N >> 3) << 17) |
          (static_cast<uint32_t>(M >> 4) << 24);
 }

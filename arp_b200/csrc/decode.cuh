@@ -166,14 +166,14 @@ decode_kernel(const DecodeArgs a) {
   }
 
   float* s_outf = reinterpret_cast<float*>(s_out);
-  __nv_bfloat16* s_outh = reinterpret_cast<__nv_bfloat16*>(s_out);
+  op_t* s_outh = reinterpret_cast<op_t*>(s_out);
   const int P = a.patch, G = a.grid;
   const bool patch_out = a.out_kind == DEC_OUT_PATCH_BF16;
   // In patch mode the band is staged as [px][c][ph(16)][pw(P)] so that global writes are long runs.
   auto put = [&](int y, int x, int c, float v) {
     if (patch_out) {
       const int px = x / P, pw = x - px * P;
-      s_outh[((px * 3 + c) * DEC_BAND + y) * P + pw] = __float2bfloat16_rn(v);
+      s_outh[((px * 3 + c) * DEC_BAND + y) * P + pw] = float_to_op(v);
     } else {
       s_outf[(c * DEC_BAND + y) * DEC_OUT + x] = v;
     }
@@ -265,7 +265,7 @@ decode_kernel(const DecodeArgs a) {
 
   // ---- write the band out ----
   if (patch_out) {
-    __nv_bfloat16* A = reinterpret_cast<__nv_bfloat16*>(a.out);
+    op_t* A = reinterpret_cast<op_t*>(a.out);
     const int K = 3 * P * P;
     const int py = y0 / P, ph0 = y0 - py * P;  // band = 16 rows [ph0, ph0+16) of patch row py
     const int vec_per_run = P / 8;             // 16-byte vectors per (px,c,ph) run of P bf16

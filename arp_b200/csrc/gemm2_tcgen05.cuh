@@ -328,8 +328,8 @@ gemm2_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gr
             q = make_uint4(__float_as_uint(v[4 * c]), __float_as_uint(v[4 * c + 1]), __float_as_uint(v[4 * c + 2]),
                            __float_as_uint(v[4 * c + 3]));
           } else {
-            q = make_uint4(pack_bf16(v[8 * c], v[8 * c + 1]), pack_bf16(v[8 * c + 2], v[8 * c + 3]),
-                           pack_bf16(v[8 * c + 4], v[8 * c + 5]), pack_bf16(v[8 * c + 6], v[8 * c + 7]));
+            q = make_uint4(pack_op(v[8 * c], v[8 * c + 1]), pack_op(v[8 * c + 2], v[8 * c + 3]),
+                           pack_op(v[8 * c + 4], v[8 * c + 5]), pack_op(v[8 * c + 6], v[8 * c + 7]));
           }
           srow[c ^ sw] = q;   // 128B swizzle: 16-byte chunk index XOR (row & 7)
         }
@@ -349,7 +349,7 @@ gemm2_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gr
               if (gr < args.M) {
                 *reinterpret_cast<float4*>(xo + static_cast<size_t>(gr) * args.ldo + n0 + c * 4) = y;
                 *reinterpret_cast<uint2*>(args.xb + static_cast<size_t>(gr) * args.N + n0 + c * 4) =
-                    make_uint2(pack_bf16(y.x, y.y), pack_bf16(y.z, y.w));
+                    make_uint2(pack_op(y.x, y.y), pack_op(y.z, y.w));
               }
               rs1[i] += (y.x + y.y) + (y.z + y.w);
               rs2[i] += (y.x * y.x + y.y * y.y) + (y.z * y.z + y.w * y.w);

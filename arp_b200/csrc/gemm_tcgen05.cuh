@@ -36,7 +36,7 @@ struct GemmArgs {
   // that re-read the whole fp32 residual stream from HBM.
   const float* ln_gamma;
   const float* ln_beta;
-  __nv_bfloat16* ln_out;
+  op_t* ln_out;
   int* ln_cnt;          // [ceil(M/128)] zeroed before the launch
   int reverse;          // gemm2: walk the tiles from the last row block to the first (snake order across kernels,
                         // so a kernel starts on the rows its predecessor wrote last — still in L2)
@@ -47,7 +47,7 @@ struct GemmArgs {
   // MODE 3 (LN applied algebraically): A was the RAW bf16 residual stream and W' = W*diag(gamma), so
   //   LN(x) W^T + bias = rstd_r * (acc - mean_r * svec_n) + cvec_n with svec = W' 1, cvec = W beta + bias;
   //   mean_r / rstd_r come from `stats_in` [M, 2*stats_nh] (moments over K = 128*stats_nh columns).
-  __nv_bfloat16* xb;
+  op_t* xb;
   float* stats_out;
   const float* stats_in;
   int stats_nh;
@@ -217,11 +217,11 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
 #pragma unroll
             for (int j = 0; j < 8; ++j) o[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
           } else {
-            uint4* o = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(out_row) + n0);
+            uint4* o = reinterpret_cast<uint4*>(reinterpret_cast<op_t*>(out_row) + n0);
 #pragma unroll
             for (int j = 0; j < 4; ++j)
-              o[j] = make_uint4(pack_bf16(v[8 * j], v[8 * j + 1]), pack_bf16(v[8 * j + 2], v[8 * j + 3]),
-                                pack_bf16(v[8 * j + 4], v[8 * j + 5]), pack_bf16(v[8 * j + 6], v[8 * j + 7]));
+              o[j] = make_uint4(pack_op(v[8 * j], v[8 * j + 1]), pack_op(v[8 * j + 2], v[8 * j + 3]),
+                                pack_op(v[8 * j + 4], v[8 * j + 5]), pack_op(v[8 * j + 6], v[8 * j + 7]));
           }
         }
       }

@@ -53,7 +53,7 @@ __device__ __forceinline__ void ln_row(const float* __restrict__ x, const float*
 // flight. Same arithmetic, in the same order, as ln_row. rows [row0, row0+NB) clipped to M; y = bf16 [M, W].
 template <int W, int NB>
 __device__ __forceinline__ void ln_rows_cg_bf16(const float* __restrict__ x, int ldx, const float* __restrict__ gamma,
-                                                const float* __restrict__ beta, float eps, __nv_bfloat16* __restrict__ y,
+                                                const float* __restrict__ beta, float eps, op_t* __restrict__ y,
                                                 int row0, int M) {
   constexpr int KV = W / 128;
   const int lane = threadIdx.x & 31;
@@ -92,7 +92,7 @@ __device__ __forceinline__ void ln_rows_cg_bf16(const float* __restrict__ x, int
         const float o0 = (v[r][i].x - mean[r]) * rstd[r] * g.x + b.x, o1 = (v[r][i].y - mean[r]) * rstd[r] * g.y + b.y;
         const float o2 = (v[r][i].z - mean[r]) * rstd[r] * g.z + b.z, o3 = (v[r][i].w - mean[r]) * rstd[r] * g.w + b.w;
         reinterpret_cast<uint2*>(y + static_cast<size_t>(row0 + r) * W)[i * 32 + lane] =
-            make_uint2(pack_bf16(o0, o1), pack_bf16(o2, o3));
+            make_uint2(pack_op(o0, o1), pack_op(o2, o3));
       }
     }
   }
@@ -102,7 +102,7 @@ __device__ __forceinline__ void ln_rows_cg_bf16(const float* __restrict__ x, int
 template <int W>
 __global__ void __launch_bounds__(256)
 layernorm_f32_bf16_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
-                          const float* __restrict__ beta, __nv_bfloat16* __restrict__ y, int M, float eps,
+                          const float* __restrict__ beta, op_t* __restrict__ y, int M, float eps,
                           int reverse) {
   int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= M) return;
@@ -113,7 +113,7 @@ layernorm_f32_bf16_kernel(const float* __restrict__ x, const float* __restrict__
   uint2* out = reinterpret_cast<uint2*>(y + static_cast<size_t>(row) * W);
 #pragma unroll
   for (int i = 0; i < RowRegs<W>::kVec; ++i)
-    out[i * 32 + lane] = make_uint2(pack_bf16(r.v[i].x, r.v[i].y), pack_bf16(r.v[i].z, r.v[i].w));
+    out[i * 32 + lane] = make_uint2(pack_op(r.v[i].x, r.v[i].y), pack_op(r.v[i].z, r.v[i].w));
 }
 
 // x fp32 [M,W] = LN(x) in place                    (ln_pre)
@@ -137,7 +137,7 @@ layernorm_f32_inplace_kernel(float* __restrict__ x, const float* __restrict__ ga
 template <int W>
 __global__ void __launch_bounds__(256)
 layernorm_pre_fold_kernel(float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
-                          __nv_bfloat16* __restrict__ xb, float* __restrict__ stats, int M, float eps) {
+                          op_t* __restrict__ xb, float* __restrict__ stats, int M, float eps) {
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= M) return;
   const int lane = threadIdx.x & 31;
@@ -149,7 +149,7 @@ layernorm_pre_fold_kernel(float* __restrict__ x, const float* __restrict__ gamma
 #pragma unroll
   for (int i = 0; i < RowRegs<W>::kVec; ++i) {      // float4 i of lane l is column (i*32 + l)*4: span i = columns [128i, 128i+128)
     reinterpret_cast<float4*>(xr)[i * 32 + lane] = r.v[i];
-    ob[i * 32 + lane] = make_uint2(pack_bf16(r.v[i].x, r.v[i].y), pack_bf16(r.v[i].z, r.v[i].w));
+    ob[i * 32 + lane] = make_uint2(pack_op(r.v[i].x, r.v[i].y), pack_op(r.v[i].z, r.v[i].w));
     const float a = warp_sum((r.v[i].x + r.v[i].y) + (r.v[i].z + r.v[i].w));
     const float b = warp_sum((r.v[i].x * r.v[i].x + r.v[i].y * r.v[i].y) + (r.v[i].z * r.v[i].z + r.v[i].w * r.v[i].w));
     if (lane == 0) st[i] = make_float2(a, b);
@@ -161,7 +161,7 @@ layernorm_pre_fold_kernel(float* __restrict__ x, const float* __restrict__ gamma
 // svec uses the ROUNDED weights so that acc - mean*svec cancels the mean exactly as the tensor core saw it.
 __global__ void __launch_bounds__(256)
 fold_ln_weights_kernel(const float* __restrict__ Wt, const float* __restrict__ gamma, const float* __restrict__ beta,
-                       const float* __restrict__ bias, __nv_bfloat16* __restrict__ Wf, float* __restrict__ svec,
+                       const float* __restrict__ bias, op_t* __restrict__ Wf, float* __restrict__ svec,
                        float* __restrict__ cvec, int N, int K) {
   const int n = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (n >= N) return;
@@ -169,9 +169,9 @@ fold_ln_weights_kernel(const float* __restrict__ Wt, const float* __restrict__ g
   float s = 0.f, c = 0.f;
   for (int k = lane; k < K; k += 32) {
     const float w = Wt[static_cast<size_t>(n) * K + k];
-    const __nv_bfloat16 wf = __float2bfloat16_rn(w * gamma[k]);
+    const op_t wf = float_to_op(w * gamma[k]);
     Wf[static_cast<size_t>(n) * K + k] = wf;
-    s += __bfloat162float(wf);
+    s += op_to_float(wf);
     c = fmaf(w, beta[k], c);
   }
   s = warp_sum(s);
@@ -187,7 +187,7 @@ fold_ln_weights_kernel(const float* __restrict__ Wt, const float* __restrict__ g
 // (finetune_module/utils.py:6-18, clip_multiscale_adapter.py:138-143).
 template <int W>
 __global__ void __launch_bounds__(256)
-gather_cls_bf16_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ taps, int B, int tokens,
+gather_cls_bf16_kernel(const float* __restrict__ x, op_t* __restrict__ taps, int B, int tokens,
                        int ld_taps, int col0) {
   const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (b >= B) return;
@@ -197,7 +197,7 @@ gather_cls_bf16_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ 
 #pragma unroll
   for (int i = 0; i < W / 128; ++i) {
     const float4 v = src[i * 32 + lane];
-    dst[i * 32 + lane] = make_uint2(pack_bf16(v.x, v.y), pack_bf16(v.z, v.w));
+    dst[i * 32 + lane] = make_uint2(pack_op(v.x, v.y), pack_op(v.z, v.w));
   }
 }
 
@@ -221,8 +221,8 @@ gather_cls_rows_f32_kernel(const float* __restrict__ x, float* __restrict__ xcls
 // Lanes own keys for the scores (fp32 dot products, fp32 softmax with the true max), then own 2 head dims for P V.
 template <int L>
 __global__ void __launch_bounds__(256)
-cls_attention_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __restrict__ qkv,
-                     __nv_bfloat16* __restrict__ out, int B, int heads, int width, float scale) {
+cls_attention_kernel(const op_t* __restrict__ q, const op_t* __restrict__ qkv,
+                     op_t* __restrict__ out, int B, int heads, int width, float scale) {
   __shared__ float s_p[8][L + 3];
   __shared__ float s_q[8][64];
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -230,13 +230,13 @@ cls_attention_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* _
   if (item >= B * heads) return;
   const int frame = item / heads, head = item - frame * heads;
   {
-    const __nv_bfloat162 v = reinterpret_cast<const __nv_bfloat162*>(q + static_cast<size_t>(frame) * width + head * 64)[lane];
-    s_q[w][2 * lane] = __bfloat162float(v.x) * scale;      // torch scales q by 1/sqrt(d) before q k^T
-    s_q[w][2 * lane + 1] = __bfloat162float(v.y) * scale;
+    const op2_t v = reinterpret_cast<const op2_t*>(q + static_cast<size_t>(frame) * width + head * 64)[lane];
+    s_q[w][2 * lane] = op_to_float(v.x) * scale;      // torch scales q by 1/sqrt(d) before q k^T
+    s_q[w][2 * lane + 1] = op_to_float(v.y) * scale;
   }
   __syncwarp();
-  const __nv_bfloat16* kbase = qkv + static_cast<size_t>(frame) * L * 3 * width + width + head * 64;
-  const __nv_bfloat16* vbase = kbase + width;
+  const op_t* kbase = qkv + static_cast<size_t>(frame) * L * 3 * width + width + head * 64;
+  const op_t* vbase = kbase + width;
   // scores: lane -> (key lane/8 of a group of 4, 16-byte chunk lane%8): every load instruction covers four whole 128-byte
   // K rows; the 8 partial dot products of a key are combined with 3 shuffles
   float m = -INFINITY;
@@ -250,11 +250,11 @@ cls_attention_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* _
     float s = 0.f;
     if (j < L) {
       const uint4 u = __ldg(reinterpret_cast<const uint4*>(kbase + static_cast<size_t>(j) * 3 * width) + kc);
-      const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&u);
+      const op2_t* h2 = reinterpret_cast<const op2_t*>(&u);
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
-        s = fmaf(qv[2 * e], __bfloat162float(h2[e].x), s);
-        s = fmaf(qv[2 * e + 1], __bfloat162float(h2[e].y), s);
+        s = fmaf(qv[2 * e], op_to_float(h2[e].x), s);
+        s = fmaf(qv[2 * e + 1], op_to_float(h2[e].y), s);
       }
     }
     s += __shfl_xor_sync(0xffffffffu, s, 1);
@@ -276,20 +276,20 @@ cls_attention_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* _
   float o0 = 0.f, o1 = 0.f;
 #pragma unroll 16      // 16 independent 128-byte row loads in flight per warp: the loop is pure load latency otherwise
   for (int j = 0; j < L; ++j) {
-    const __nv_bfloat162 v = __ldg(reinterpret_cast<const __nv_bfloat162*>(vbase + static_cast<size_t>(j) * 3 * width) + lane);
+    const op2_t v = __ldg(reinterpret_cast<const op2_t*>(vbase + static_cast<size_t>(j) * 3 * width) + lane);
     const float pj = s_p[w][j];
-    o0 = fmaf(pj, __bfloat162float(v.x), o0);
-    o1 = fmaf(pj, __bfloat162float(v.y), o1);
+    o0 = fmaf(pj, op_to_float(v.x), o0);
+    o1 = fmaf(pj, op_to_float(v.y), o1);
   }
   const float inv = 1.0f / sum;
-  reinterpret_cast<__nv_bfloat162*>(out + static_cast<size_t>(frame) * width + head * 64)[lane] =
-      __floats2bfloat162_rn(o0 * inv, o1 * inv);
+  reinterpret_cast<op2_t*>(out + static_cast<size_t>(frame) * width + head * 64)[lane] =
+      floats_to_op2(o0 * inv, o1 * inv);
 }
 
 // fp32 [T,3,224,224] (already resized / augmented / normalised by the caller) -> bf16 patch rows of the patch-embed GEMM:
 // A[b*tokens + 1 + py*G + px, c*P*P + ph*P + pw]; row b*tokens (class-token slot) = 0. One thread per 8 outputs.
 __global__ void __launch_bounds__(256)
-patchify_chw_bf16_kernel(const float* __restrict__ chw, __nv_bfloat16* __restrict__ A, int T, int P, int G, int tokens) {
+patchify_chw_bf16_kernel(const float* __restrict__ chw, op_t* __restrict__ A, int T, int P, int G, int tokens) {
   const int K = 3 * P * P;
   const size_t total8 = static_cast<size_t>(T) * tokens * K / 8;
   for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total8;
@@ -305,7 +305,7 @@ patchify_chw_bf16_kernel(const float* __restrict__ chw, __nv_bfloat16* __restric
       const int c = col / (P * P), ph = (col / P) % P, pw = col % P;
       const float* src = chw + ((b * 3 + c) * 224 + py * P + ph) * 224 + px * P + pw;
       const float4 lo = *reinterpret_cast<const float4*>(src), hi = *reinterpret_cast<const float4*>(src + 4);
-      o = make_uint4(pack_bf16(lo.x, lo.y), pack_bf16(lo.z, lo.w), pack_bf16(hi.x, hi.y), pack_bf16(hi.z, hi.w));
+      o = make_uint4(pack_op(lo.x, lo.y), pack_op(lo.z, lo.w), pack_op(hi.x, hi.y), pack_op(hi.z, hi.w));
     }
     *reinterpret_cast<uint4*>(A + e) = o;
   }
@@ -313,15 +313,15 @@ patchify_chw_bf16_kernel(const float* __restrict__ chw, __nv_bfloat16* __restric
 
 // fp32 -> bf16 conversion of a contiguous buffer (weights at load time, adapter features).
 __global__ void __launch_bounds__(256)
-f32_to_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, size_t n) {
+f32_to_bf16_kernel(const float* __restrict__ src, op_t* __restrict__ dst, size_t n) {
   size_t i = (static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x) * 4;
   const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x * 4;
   for (; i + 3 < n; i += stride) {
     const float4 v = *reinterpret_cast<const float4*>(src + i);
-    *reinterpret_cast<uint2*>(dst + i) = make_uint2(pack_bf16(v.x, v.y), pack_bf16(v.z, v.w));
+    *reinterpret_cast<uint2*>(dst + i) = make_uint2(pack_op(v.x, v.y), pack_op(v.z, v.w));
   }
   if (i < n) {  // ragged tail (n % 4 != 0): at most one thread lands here
-    for (size_t j = i; j < n; ++j) dst[j] = __float2bfloat16_rn(src[j]);
+    for (size_t j = i; j < n; ++j) dst[j] = float_to_op(src[j]);
   }
 }
 
