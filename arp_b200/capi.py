@@ -31,7 +31,7 @@ EXPORTS = (
     "arp_set_text", "arp_label", "arp_label_host", "arp_compute_reward", "arp_encode_image", "arp_decode_only",
     "arp_scan_only", "arp_gemm_bf16", "arp_layernorm_bf16", "arp_attention", "arp_launch_count",
     "arp_profile_begin", "arp_profile_end", "arp_online_reward", "arp_preprocess_rtgs",
-    "arp_quantile_f32", "arp_encode_taps_chw",
+    "arp_quantile_f32", "arp_encode_taps_chw", "arp_operand_dtype",
 )
 PROFILE_CLASSES = ("gemm", "attention", "layernorm", "decode", "head", "scan", "other")
 
@@ -76,6 +76,7 @@ def load_library() -> C.CDLL:
     lib.arp_last_error.argtypes = [vp]
     lib.arp_last_error.restype = C.c_char_p
     lib.arp_abi_version.argtypes = []
+    lib.arp_operand_dtype.argtypes = []
     lib.arp_set_weight.argtypes = [vp, C.c_char_p, vp, i32, C.POINTER(i64), i32, vp]
     lib.arp_missing_weights.argtypes = [vp, C.c_char_p, i64]
     lib.arp_set_text.argtypes = [vp, vp, i32, i32, f32, vp]
@@ -104,6 +105,11 @@ def load_library() -> C.CDLL:
 
 
 _TORCH_DT = {torch.float32: DT_F32, torch.bfloat16: DT_BF16, torch.float16: DT_F16}
+
+
+def operand_dtype() -> torch.dtype:
+    """The 16-bit format the library's contractions run in (bf16 unless it was built with -DARP_OP_FP16=1)."""
+    return {DT_BF16: torch.bfloat16, DT_F16: torch.float16}[load_library().arp_operand_dtype()]
 
 
 def _ptr(t: "torch.Tensor | None"):
@@ -339,25 +345,31 @@ class Engine:
         return g, rs, gs
 
     def gemm(self, a: torch.Tensor, w: torch.Tensor, bias=None, resid=None, act: int = ACT_NONE,
-             out_dtype=torch.bfloat16) -> torch.Tensor:
-        assert a.dtype == torch.bfloat16 and w.dtype == torch.bfloat16 and a.is_contiguous() and w.is_contiguous()
+             out_dtype=None) -> torch.Tensor:
+        """Test hook. a, w: 16-bit float tensors (converted to the library's operand format if they are in the other
+        one); out_dtype None = operand format, or torch.float32."""
+        op = operand_dtype()
+        assert a.dtype in (torch.bfloat16, torch.float16) and w.dtype in (torch.bfloat16, torch.float16)
+        a, w = a.to(op).contiguous(), w.to(op).contiguous()
         M, K = a.shape
         N = w.shape[0]
+        out_dtype = op if out_dtype in (None, torch.bfloat16, torch.float16) else out_dtype
         out = torch.empty(M, N, device=self.device, dtype=out_dtype)
         self._check(self._lib.arp_gemm_bf16(self._h, _ptr(a), _ptr(w), _ptr(out),
-                                            DT_F32 if out_dtype == torch.float32 else DT_BF16, M, N, K, _ptr(bias),
+                                            DT_F32 if out_dtype == torch.float32 else _TORCH_DT[op], M, N, K, _ptr(bias),
                                             _ptr(resid), act, _stream_ptr(self.device)))
         return out
 
     def layernorm(self, x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor) -> torch.Tensor:
         assert x.dtype == torch.float32 and x.is_contiguous() and x.shape[-1] == 768
-        y = torch.empty(x.shape, device=self.device, dtype=torch.bfloat16)
+        y = torch.empty(x.shape, device=self.device, dtype=operand_dtype())
         self._check(self._lib.arp_layernorm_bf16(self._h, _ptr(x), _ptr(gamma), _ptr(beta), _ptr(y),
                                                  x.numel() // 768, _stream_ptr(self.device)))
         return y
 
     def attention(self, qkv: torch.Tensor, B: int, tokens: int) -> torch.Tensor:
-        assert qkv.dtype == torch.bfloat16 and qkv.is_contiguous()
-        out = torch.empty(B * tokens, qkv.shape[-1] // 3, device=self.device, dtype=torch.bfloat16)
+        assert qkv.dtype in (torch.bfloat16, torch.float16)
+        qkv = qkv.to(operand_dtype()).contiguous()
+        out = torch.empty(B * tokens, qkv.shape[-1] // 3, device=self.device, dtype=qkv.dtype)
         self._check(self._lib.arp_attention(self._h, _ptr(qkv), _ptr(out), B, tokens, _stream_ptr(self.device)))
         return out

@@ -124,8 +124,13 @@ __device__ __forceinline__ uint32_t pack_bf16_int(float lo, float hi) {
 // the truncated values (ones block), so the one-sided error cancels in the mean and what remains has the spread of
 // round-to-nearest.
 __device__ __forceinline__ uint32_t pack_bf16_trunc(float lo, float hi) {
+#if ARP_OP_FP16
+  return pack_op(lo, hi);   // fp16 has no truncation shortcut: one F2FP (round to nearest) per pair
+#else
   return (__float_as_uint(lo) >> 16) | (__float_as_uint(hi) & 0xffff0000u);
+#endif
 }
+constexpr uint32_t kOnes2 = ARP_OP_FP16 ? 0x3c003c00u : 0x3f803f80u;   // two 1.0 in the operand format
 
 __device__ __forceinline__ float ex2_approx(float x) {
   float y;
@@ -210,7 +215,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
   }
   if (warp == 1 && lane < 4) { xu_turn[lane] = 0; cnt_p[lane] = 0; }   // cnt_p[0..1], cnt_e[0..1] are contiguous
   for (int i = threadIdx.x; i < C::ONES_BYTES / 16; i += ATC_THREADS)      // swizzle-invariant: every element is 1.0
-    reinterpret_cast<uint4*>(ones)[i] = make_uint4(0x3f803f80u, 0x3f803f80u, 0x3f803f80u, 0x3f803f80u);
+    reinterpret_cast<uint4*>(ones)[i] = make_uint4(kOnes2, kOnes2, kOnes2, kOnes2);
   fence_proxy_async_smem();                                                // generic-proxy writes -> tensor-core reads
   if (warp == 1) tmem_alloc<512>(tmem_slot);
   tc_fence_before();

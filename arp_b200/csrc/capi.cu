@@ -28,6 +28,7 @@
 
 using namespace arp;
 typedef arp::op_t bf16;   // the operand format (common.cuh: bf16 by default, fp16 with -DARP_OP_FP16=1)
+#define ARP_OP_DTYPE (ARP_OP_FP16 ? ARP_F16 : ARP_BF16)   // ... as an ArpDType of include/arp_b200.h
 
 // ------------------------------------------------------------------------------------------------
 // errors
@@ -434,6 +435,7 @@ __global__ void build_rowtab_kernel(const float* __restrict__ pos, const float* 
 // C ABI: lifetime
 // ------------------------------------------------------------------------------------------------
 extern "C" int arp_abi_version(void) { return ARP_B200_ABI_VERSION; }
+extern "C" int arp_operand_dtype(void) { return ARP_OP_DTYPE; }
 
 extern "C" const char* arp_last_error(const ArpHandle* h) { return h ? h->err.c_str() : g_create_error.c_str(); }
 
@@ -690,21 +692,23 @@ extern "C" int arp_set_weight(ArpHandle* h, const char* name, const void* data, 
   void* dst = *s.dst;
   const size_t n = static_cast<size_t>(numel);
   if (s.as_bf16) {
+    // the CALLER's tensor dtype (ARP_F32 / ARP_F16 / ARP_BF16) -> the library's operand format (bf16 = op_t)
     if (dtype == ARP_F32) launch_convert<float, bf16>(h, data, dst, n, st);
+    else if (dtype == ARP_OP_DTYPE) ARP_CUDA(h, cudaMemcpyAsync(dst, data, n * 2, cudaMemcpyDeviceToDevice, st));
     else if (dtype == ARP_F16) launch_convert<__half, bf16>(h, data, dst, n, st);
-    else if (dtype == ARP_BF16) ARP_CUDA(h, cudaMemcpyAsync(dst, data, n * 2, cudaMemcpyDeviceToDevice, st));
+    else if (dtype == ARP_BF16) launch_convert<__nv_bfloat16, bf16>(h, data, dst, n, st);
     else return fail(h, ARP_ERR_INVALID, "bad dtype %d", dtype);
   } else {
     if (dtype == ARP_F32) ARP_CUDA(h, cudaMemcpyAsync(dst, data, n * 4, cudaMemcpyDeviceToDevice, st));
     else if (dtype == ARP_F16) launch_convert<__half, float>(h, data, dst, n, st);
-    else if (dtype == ARP_BF16) launch_convert<bf16, float>(h, data, dst, n, st);
+    else if (dtype == ARP_BF16) launch_convert<__nv_bfloat16, float>(h, data, dst, n, st);
     else return fail(h, ARP_ERR_INVALID, "bad dtype %d", dtype);
   }
   if (s.dst_f32 && *s.dst_f32) {
     void* d32 = *s.dst_f32;
     if (dtype == ARP_F32) ARP_CUDA(h, cudaMemcpyAsync(d32, data, n * 4, cudaMemcpyDeviceToDevice, st));
     else if (dtype == ARP_F16) launch_convert<__half, float>(h, data, d32, n, st);
-    else launch_convert<bf16, float>(h, data, d32, n, st);
+    else launch_convert<__nv_bfloat16, float>(h, data, d32, n, st);
   }
   ARP_CUDA(h, cudaGetLastError());
   s.set = true;
@@ -792,7 +796,7 @@ static int get_tmap(ArpHandle* h, const void* ptr, uint64_t rows, uint64_t cols,
     cuuint32_t estr[2] = {1, 1};
     if ((reinterpret_cast<uintptr_t>(ptr) & 15) || (gstr[0] & 15))
       return fail(h, ARP_ERR_INVALID, "GEMM operand must be 16-byte aligned with a 16-byte multiple row pitch");
-    CUresult r = get_encode_tiled()(&m, elem == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32,
+    CUresult r = get_encode_tiled()(&m, elem == 2 ? (ARP_OP_FP16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16) : CU_TENSOR_MAP_DATA_TYPE_FLOAT32,
                                     2, const_cast<void*>(ptr), gdim, gstr, box,
                                     estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -1761,7 +1765,7 @@ extern "C" int arp_gemm_bf16(ArpHandle* h, const void* a_dev, const void* w_dev,
                              int64_t M, int32_t N, int32_t K, const float* bias_dev, const float* resid_dev,
                              int32_t act, void* stream) {
   if (!h || !a_dev || !w_dev || !out_dev) return fail(h, ARP_ERR_INVALID, "null argument");
-  if (act < 0 || act > 2 || (out_dtype != ARP_F32 && out_dtype != ARP_BF16)) return fail(h, ARP_ERR_INVALID, "bad act / out_dtype");
+  if (act < 0 || act > 2 || (out_dtype != ARP_F32 && out_dtype != ARP_OP_DTYPE)) return fail(h, ARP_ERR_INVALID, "bad act / out_dtype");
   ARP_CUDA(h, cudaSetDevice(h->cfg.device));
   return launch_gemm(h, static_cast<const bf16*>(a_dev), M, static_cast<const bf16*>(w_dev), out_dev,
                      out_dtype == ARP_F32, act, M, N, K, N, bias_dev, resid_dev, N, nullptr, 0,

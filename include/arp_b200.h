@@ -21,7 +21,7 @@
 extern "C" {
 #endif
 
-#define ARP_B200_ABI_VERSION 3   /* 3: + arp_encode_taps_chw (additive) */
+#define ARP_B200_ABI_VERSION 4   /* 3: + arp_encode_taps_chw, 4: + arp_operand_dtype (both additive) */
 
 #if defined(__GNUC__)
 #define ARP_API __attribute__((visibility("default")))
@@ -86,6 +86,10 @@ ARP_API int arp_create(const ArpConfig* cfg, ArpHandle** out);
 ARP_API void arp_destroy(ArpHandle* h);
 ARP_API const char* arp_last_error(const ArpHandle* h); /* h may be NULL: last error of arp_create */
 ARP_API int arp_abi_version(void);
+/* ArpDType of the 16-bit operand format this build runs its contractions in: ARP_BF16 (default build) or ARP_F16
+ * (-DARP_OP_FP16=1; the reference's own CUDA path keeps CLIP in fp16, clip.load). The "bf16" buffers of the test hooks
+ * below (arp_gemm_bf16, arp_layernorm_bf16, arp_attention) are in THIS format. */
+ARP_API int arp_operand_dtype(void);
 
 /* ------------------------------------------------------------------------------------------------
  * weights: one call per state_dict entry, names exactly as in openai/CLIP's state_dict
@@ -190,7 +194,7 @@ ARP_API int arp_scan_only(ArpHandle* h, const float* reward_dev, int64_t T, cons
                   int32_t num_frames, float gamma, float* rtg_dev, float* reward_stacked_dev,
                   float* rtg_stacked_dev, void* stream);
 /* C[M,N] = act(A[M,K] W[N,K]^T + bias) (+ resid): the tcgen05 GEMM behind every linear layer.
- * A, W bf16 device; out bf16 (out_dtype=ARP_BF16) or fp32; act 0 none, 1 QuickGELU, 2 ReLU;
+ * A, W in the operand format (arp_operand_dtype) on the device; out in that format (out_dtype = it) or fp32; act 0 none, 1 QuickGELU, 2 ReLU;
  * bias / resid fp32 or NULL; N % 256 == 0, K % 64 == 0. */
 ARP_API int arp_gemm_bf16(ArpHandle* h, const void* a_dev, const void* w_dev, void* out_dev, int32_t out_dtype, int64_t M,
                   int32_t N, int32_t K, const float* bias_dev, const float* resid_dev, int32_t act, void* stream);
