@@ -71,8 +71,10 @@ def test_gemm_vs_torch(eng, M, N, K, act, bias, resid, out_dtype):
 def test_gemm_residual_in_place(eng):
     """The residual stream is updated in place (out aliases resid) on the hot path."""
     dev = eng.device
-    a = torch.randn(300, 768, device=dev).bfloat16()
-    w = (torch.randn(768, 768, device=dev) * 0.05).bfloat16()
+    from arp_b200 import capi as _capi
+    op = _capi.operand_dtype()                     # raw pointers go straight to the C ABI: use the library's own format
+    a = torch.randn(300, 768, device=dev).to(op)
+    w = (torch.randn(768, 768, device=dev) * 0.05).to(op)
     x = torch.randn(300, 768, device=dev)
     ref = x + a.float() @ w.float().t()
     import ctypes as C
