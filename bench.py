@@ -335,7 +335,8 @@ def main():
         print(json.dumps({
             "metric": "reward-labeled frames/sec", "value": value, "unit": "frames/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "scaling": "weak", "vs_baseline": None,
+            "dtype": "fp16" if capi.operand_dtype() == torch.float16 else "bf16", "data": "synthetic",
             "config": workload_config(args, T), "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
             "roofline": roofline, "cpu_baseline": cpu,
         }))
