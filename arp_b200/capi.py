@@ -22,7 +22,8 @@ HEAD_CLIP, HEAD_ADAPTER, HEAD_ADAPTER_ENSEMBLE, HEAD_CLIP_GOAL, HEAD_ADAPTER_GOA
 REDUCE_FIRST, REDUCE_MEAN = 0, 1
 DT_F32, DT_BF16, DT_F16 = 0, 1, 2
 ACT_NONE, ACT_QUICKGELU, ACT_RELU = 0, 1, 2
-PREC_BF16, PREC_F32 = 0, 1
+PREC_BF16, PREC_F32, PREC_F32RESID = 0, 1, 2   # PREC_BF16 = the 16-bit tensor-core path (name is historical)
+PREC_16BIT = PREC_BF16
 MAX_TEXT = 16
 
 #: every symbol include/arp_b200.h declares (tests check the library exports exactly these)
@@ -31,7 +32,7 @@ EXPORTS = (
     "arp_set_text", "arp_label", "arp_label_host", "arp_compute_reward", "arp_encode_image", "arp_decode_only",
     "arp_scan_only", "arp_gemm_bf16", "arp_layernorm_bf16", "arp_attention", "arp_launch_count",
     "arp_profile_begin", "arp_profile_end", "arp_online_reward", "arp_preprocess_rtgs",
-    "arp_quantile_f32", "arp_encode_taps_chw", "arp_operand_dtype",
+    "arp_quantile_f32", "arp_encode_taps_chw", "arp_operand_dtype", "arp_ln_gemm",
 )
 PROFILE_CLASSES = ("gemm", "attention", "layernorm", "decode", "head", "scan", "other")
 
@@ -91,6 +92,7 @@ def load_library() -> C.CDLL:
     lib.arp_decode_only.argtypes = [vp, vp, i64, i64, vp, vp]
     lib.arp_scan_only.argtypes = [vp, vp, i64, vp, i32, i32, f32, vp, vp, vp, vp]
     lib.arp_gemm_bf16.argtypes = [vp, vp, vp, vp, i32, i64, i32, i32, vp, vp, i32, vp]
+    lib.arp_ln_gemm.argtypes = [vp, vp, vp, vp, vp, vp, vp, i64, i32, i32, vp]
     lib.arp_layernorm_bf16.argtypes = [vp, vp, vp, vp, vp, i64, vp]
     lib.arp_attention.argtypes = [vp, vp, vp, i32, i32, vp]
     lib.arp_launch_count.argtypes = [vp]
@@ -347,7 +349,8 @@ class Engine:
     def gemm(self, a: torch.Tensor, w: torch.Tensor, bias=None, resid=None, act: int = ACT_NONE,
              out_dtype=None) -> torch.Tensor:
         """Test hook. a, w: 16-bit float tensors (converted to the library's operand format if they are in the other
-        one); out_dtype None = operand format, or torch.float32."""
+        one); out_dtype None = operand format, or torch.float32; resid is converted to the output dtype (the residual
+        stream is accumulated into in that format)."""
         op = operand_dtype()
         assert a.dtype in (torch.bfloat16, torch.float16) and w.dtype in (torch.bfloat16, torch.float16)
         a, w = a.to(op).contiguous(), w.to(op).contiguous()
@@ -355,9 +358,24 @@ class Engine:
         N = w.shape[0]
         out_dtype = op if out_dtype in (None, torch.bfloat16, torch.float16) else out_dtype
         out = torch.empty(M, N, device=self.device, dtype=out_dtype)
+        if resid is not None:
+            resid = resid.to(out_dtype).contiguous()
         self._check(self._lib.arp_gemm_bf16(self._h, _ptr(a), _ptr(w), _ptr(out),
                                             DT_F32 if out_dtype == torch.float32 else _TORCH_DT[op], M, N, K, _ptr(bias),
                                             _ptr(resid), act, _stream_ptr(self.device)))
+        return out
+
+    def ln_gemm(self, x: torch.Tensor, gamma, beta, w: torch.Tensor, bias: torch.Tensor, act: int = ACT_NONE) -> torch.Tensor:
+        """Test hook: act(LayerNorm(x) W^T + bias) with the LayerNorm folded into the GEMM (default-path ln_1/ln_2).
+        x [M,768] 16-bit (converted to the operand format); gamma, beta, w [N,768], bias fp32."""
+        op = operand_dtype()
+        x = x.to(op).contiguous()
+        f = lambda t: t.to(self.device, torch.float32).contiguous()  # noqa: E731
+        gamma, beta, w, bias = f(gamma), f(beta), f(w), f(bias)
+        M, N = x.shape[0], w.shape[0]
+        out = torch.empty(M, N, device=self.device, dtype=op)
+        self._check(self._lib.arp_ln_gemm(self._h, _ptr(x), _ptr(gamma), _ptr(beta), _ptr(w), _ptr(bias), _ptr(out),
+                                          M, N, act, _stream_ptr(self.device)))
         return out
 
     def layernorm(self, x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor) -> torch.Tensor:

@@ -123,9 +123,17 @@ __device__ __forceinline__ uint32_t pack_bf16_int(float lo, float hi) {
 // bf16 pair by TRUNCATION (two ALU ops, no rounding adds): the weights P are normalised by the tensor core's own sum of
 // the truncated values (ones block), so the one-sided error cancels in the mean and what remains has the spread of
 // round-to-nearest.
+//
+// fp16 operands: the same shortcut exists if the exponential is produced PRE-SCALED. For an fp32 value v·2^-112 the bit
+// pattern shifted right by 13 is exactly the fp16 pattern of v truncated (5 exponent + 10 mantissa bits line up once the
+// bias difference 127-15 is taken out; fp32 denormals map onto fp16 denormals). The softmax therefore computes
+// p' = exp2(s·scale − max·scale + 15 − 112): the largest weight of a row is 2^15 instead of 1 (fp16 tops out at 65504),
+// the smallest one kept is 2^-29 of it (ex2.approx.ftz flushes below 2^-126), and the common factor 2^15 cancels in
+// O / rowsum because the row sum comes from the same operand. No F2FP on the XU pipe, which MUFU.EX2 needs.
+constexpr float kPExpOffset = ARP_OP_FP16 ? 97.0f : 0.0f;   // subtracted from the exp2 argument (112 - 15)
 __device__ __forceinline__ uint32_t pack_bf16_trunc(float lo, float hi) {
 #if ARP_OP_FP16
-  return pack_op(lo, hi);   // fp16 has no truncation shortcut: one F2FP (round to nearest) per pair
+  return (__float_as_uint(lo) >> 13) | ((__float_as_uint(hi) << 3) & 0xffff0000u);
 #else
   return (__float_as_uint(lo) >> 16) | (__float_as_uint(hi) & 0xffff0000u);
 #endif
@@ -336,7 +344,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
             if (NFULL * 32 + j < L) m = fmaxf(m, __uint_as_float(r[j]));
         }
       }
-      const float mo = m * scale_log2e;
+      const float mo = m * scale_log2e + kPExpOffset;   // exp2 argument offset: row maximum (+ the fp16 pre-scale)
       if (quarter == 0) ATC_TRACE(3, qt, it);
       if (C::QT == 2) {     // wait for this warp's exp2 turn
         const int my_turn = 2 * static_cast<int>(it) + qt;

@@ -1,6 +1,6 @@
 // C-ABI implementation of include/arp_b200.h: handle, weight packing, TMA descriptors and the
-// stream-ordered pipeline   decode -> patch-embed GEMM -> 12 x [LN, QKV, attention, out-proj, LN, c_fc, c_proj]
-// -> reward head -> per-episode return-to-go scan.
+// stream-ordered pipeline   decode -> patch-embed GEMM -> ln_pre -> 12 x [QKV (ln_1 folded), attention, out-proj (+= x),
+// row moments, c_fc (ln_2 folded, QuickGELU), c_proj (+= x), row moments] -> reward head -> per-episode return-to-go scan.
 // Host logic only; every kernel lives in the .cuh next to this file.
 #include <cuda.h>
 #include <cuda_runtime.h>
@@ -15,12 +15,10 @@
 #include <vector>
 
 #include "../../include/arp_b200.h"
-#include "attention.cuh"
 #include "attention_tc.cuh"
 #include "decode.cuh"
 #include "fp32_path.cuh"
 #include "gemm_tcgen05.cuh"
-#include "gemm2_tcgen05.cuh"
 #include "head.cuh"
 #include "layernorm.cuh"
 #include "rtgstats.cuh"
@@ -77,8 +75,8 @@ struct LayerW {
   float *ln1_g = nullptr, *ln1_b = nullptr, *ln2_g = nullptr, *ln2_b = nullptr;
   bf16 *w_qkv = nullptr, *w_out = nullptr, *w_fc = nullptr, *w_proj = nullptr;
   float *b_qkv = nullptr, *b_out = nullptr, *b_fc = nullptr, *b_proj = nullptr;
-  // LayerNorm fold: fp32 originals of the two LN-consuming weights, gamma-folded bf16 operands, and the
-  // per-output-column vectors of the algebraic LayerNorm (gemm2 MODE 3)
+  // LayerNorm fold (16-bit residual path): fp32 originals of the two LN-consuming weights, their gamma-folded
+  // operands, and the per-output-column vectors of the algebraic LayerNorm (gemm_tcgen05.cuh G2_LNFOLD)
   float *w_qkv_f32 = nullptr, *w_fc_f32 = nullptr;
   bf16 *w_qkv_fold = nullptr, *w_fc_fold = nullptr;
   float *s_qkv = nullptr, *c_qkv = nullptr, *s_fc = nullptr, *c_fc = nullptr;
@@ -105,11 +103,11 @@ struct ArpHandle {
   ArpConfig cfg;
   std::string err;
   int64_t launches = 0;
-  // LayerNorm applied inside the GEMM epilogues (ARP_LN_FOLD): 0 = standalone LN kernels (default), 1 = ln_1 folded
-  // (c_proj emits bf16 x + moments, QKV applies them), 2 = ln_1 and ln_2 folded. Measured on B200 (tools/fold_check.py):
-  // numerically equivalent, but the register-path residual epilogue (gemm2 MODE 2) is latency-bound on the x loads
-  // (out_proj 137 -> 236 us), which cancels the 2 x 63 us of LN kernels it removes; kept off until MODE 2 stages x by TMA.
-  int ln_fold = 0;
+  // Residual stream format. true (ARP_PREC_BF16, the default 16-bit path): x is kept in the operand format, updated by
+  // 16-bit TMA reduce-adds, and IS the A operand of the QKV / c_fc GEMMs, which apply LayerNorm algebraically in their
+  // epilogues from per-row moments — no LayerNorm kernels, no normalised copy, no fp32 read-modify-write.
+  // false (ARP_PREC_F32RESID): fp32 x, standalone LayerNorm kernels writing a 16-bit copy (round 1's pipeline).
+  bool resid16 = true;
   // Snake order: consecutive kernels of a chunk walk the rows in opposite directions, so each starts on what its
   // predecessor wrote last (the tail of a 150-600 MB activation is still in the 126 MB L2). ARP_SNAKE=0 disables.
   bool snake = true;
@@ -122,16 +120,7 @@ struct ArpHandle {
   const float* cur_chw = nullptr;
   float* cur_taps32 = nullptr;
   bool prune_last = true;
-  // LayerNorm fused behind the residual GEMMs (GemmArgs::ln_cnt, gemm2 MODE 4): out_proj emits ln_2(x), c_proj the next
-  // block's ln_1(x), by the CTA that completes a 128-row block. Correct (all parity tests pass with ARP_LN_FUSE=1) but
-  // measured slower on B200 and therefore OFF: by the time the last column tile of a row block lands, c_proj's 620 MB
-  // A stream has evicted the block's x rows from L2 (ncu: DRAM reads 0.94 -> 1.67 GB, L2 hit 52 %), the gpu-scope
-  // fence of the hand-off invalidates L1 every tile, and 8 epilogue warps per SM hide HBM latency far worse than the
-  // standalone kernel's 64 (c_proj 320 -> 505 us, out_proj 125 -> 394 us vs 2 x 63 us of LayerNorm kernels saved).
-  int ln_fuse = 0;      // bit 0: ln_2 behind out_proj, bit 1: next block's ln_1 behind c_proj (ARP_LN_FUSE=1 both, 2 / 3 one)
   bool f32 = false;   // cfg.precision == ARP_PREC_F32: verification path (fp32_path.cuh); GEMM weights are stored as fp32
-  int attn_impl = 2;  // 1 = mma.sync kernel, 2 = tcgen05 kernel (ARP_ATTN_IMPL overrides)
-  int gemm_impl = 3;  // 1 = v1 (register stores), 2 = v2 single-CTA, 3 = v2 CTA pairs (ARP_GEMM_IMPL overrides)
   int tokens = 0, grid = 0, kp = 0;  // 197, 14, 768
   bool adapter = false, goal = false;
   int n_scales = 0, feat_dim = 0;    // 13, 6656 for adapter heads
@@ -159,28 +148,21 @@ struct ArpHandle {
   float* lut = nullptr;
   int crop_top = 0, crop_left = 0, src_h = 0, src_w = 0;
 
-  // workspaces (each sized for cfg.max_batch frames). Optionally two chunks are in flight on two internal
-  // streams (ARP_PIPES=2), each with its own workspace.
+  // workspace, sized for cfg.max_batch frames
   struct Work {
-    float* x = nullptr;
+    bf16* x16 = nullptr;      // [M, W] 16-bit residual stream (resid16)
+    float2* stats = nullptr;  // [M] (rstd, -mean*rstd) of the rows of x16: the LayerNorm the next GEMM folds in
+    float* x = nullptr;       // [M, W] fp32 residual stream (!resid16, fp32 path); resid16: fp32 patch-embed output, aliases qkv
     bf16 *xn = nullptr, *qkv = nullptr, *attn = nullptr, *hid = nullptr;
     bf16 *taps = nullptr, *featb = nullptr, *hid2 = nullptr;
     float *featf = nullptr, *mlp = nullptr;
-    float* stats = nullptr;   // [M, 2*W/128] partial LayerNorm moments (LN fold)
-    int* ln_cnt = nullptr;                                       // [ceil(M/128)] row-block arrival counters (fused LayerNorm)
-    bool pruned = false;                                         // the heads read xcls (stride 1) instead of x (stride tokens)
+    bool cls_compact = false;                                    // the heads read xcls (stride 1) instead of x (stride tokens)
     float* xcls = nullptr;                                       // [B, W] class-token residual rows (last-layer pruning)
     bf16 *xncls = nullptr, *qcls = nullptr, *acls = nullptr, *hcls = nullptr;   // [B,W] x3, [B,4W]
     // fp32 verification path
     float *chw32 = nullptr, *xn32 = nullptr, *qkv32 = nullptr, *attn32 = nullptr, *hid32 = nullptr;
     float *taps32 = nullptr, *hid2_32 = nullptr;
-  } ws[2];
-  int gemm_sms = kNumSMs, attn_sms = kNumSMs;   // persistent-grid caps (ARP_GEMM_SMS / ARP_ATTN_SMS): with ARP_PIPES=2 a
-                                               // partition lets one chunk's attention run beside the other's GEMMs
-  int n_pipes = 1;                       // ARP_PIPES=2: two chunks in flight (measured: no gain on B200 — a resident
-                                         // persistent GEMM CTA leaves no room the scheduler will give to another kernel)
-  cudaStream_t pipe_stream[2] = {nullptr, nullptr};
-  cudaEvent_t ev_fork = nullptr, ev_join[2] = {nullptr, nullptr};
+  } ws;
 
   // scratch that grows with T (goal heads, host path)
   void* scratch[2] = {nullptr, nullptr};  // [0] label temporaries, [1] device outputs of the host path
@@ -487,11 +469,8 @@ extern "C" void arp_destroy(ArpHandle* h) {
     if (h->stage_dev[i]) cudaFree(h->stage_dev[i]);
     if (h->ev_copied[i]) cudaEventDestroy(h->ev_copied[i]);
     if (h->ev_consumed[i]) cudaEventDestroy(h->ev_consumed[i]);
-    if (h->ev_join[i]) cudaEventDestroy(h->ev_join[i]);
-    if (h->pipe_stream[i]) cudaStreamDestroy(h->pipe_stream[i]);
   }
   for (auto& kv : h->online_graphs) if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
-  if (h->ev_fork) cudaEventDestroy(h->ev_fork);
   for (auto& r : h->prof) { cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); }
   for (cudaEvent_t e : h->event_pool) cudaEventDestroy(e);
   if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
@@ -518,7 +497,7 @@ extern "C" int arp_create(const ArpConfig* cfg, ArpHandle** out) {
     return fail(nullptr, ARP_ERR_INVALID, "bad layers / max_batch / frame size");
   if (cfg->head < 0 || cfg->head > ARP_HEAD_ADAPTER_GOAL || cfg->preprocess < 0 || cfg->preprocess > 1)
     return fail(nullptr, ARP_ERR_INVALID, "bad head / preprocess enum");
-  if (cfg->precision != ARP_PREC_BF16 && cfg->precision != ARP_PREC_F32)
+  if (cfg->precision != ARP_PREC_BF16 && cfg->precision != ARP_PREC_F32 && cfg->precision != ARP_PREC_F32RESID)
     return fail(nullptr, ARP_ERR_INVALID, "bad precision enum");
   if (!get_encode_tiled()) return fail(nullptr, ARP_ERR_CUDA, "cuTensorMapEncodeTiled not available from the driver");
 
@@ -527,15 +506,9 @@ extern "C" int arp_create(const ArpConfig* cfg, ArpHandle** out) {
   auto bail = [&](int code) { g_create_error = h->err; arp_destroy(h); return code; };
   if (cudaSetDevice(cfg->device) != cudaSuccess) { h->err = "cudaSetDevice failed"; return bail(ARP_ERR_CUDA); }
   h->f32 = cfg->precision == ARP_PREC_F32;
-  if (const char* e = getenv("ARP_GEMM_IMPL")) h->gemm_impl = atoi(e);
-  if (h->gemm_impl < 1 || h->gemm_impl > 3) h->gemm_impl = 3;
-  if (const char* e = getenv("ARP_ATTN_IMPL")) h->attn_impl = atoi(e) == 1 ? 1 : 2;
-  if (const char* e = getenv("ARP_SNAKE")) h->snake = atoi(e) != 0;
-  if (const char* e = getenv("ARP_PRUNE_LAST")) h->prune_last = atoi(e) != 0;
-  if (const char* e = getenv("ARP_LN_FUSE")) { const int v = atoi(e); h->ln_fuse = v == 1 ? 3 : v == 2 ? 1 : v == 3 ? 2 : 0; }
-  if (const char* e = getenv("ARP_LN_FOLD")) h->ln_fold = std::max(0, std::min(2, atoi(e)));
-  if (h->gemm_impl < 2 || h->f32) h->ln_fold = 0;   // the fold lives in the v2 epilogue
-  if (h->gemm_impl < 2 || h->f32) h->ln_fuse = 0;
+  h->resid16 = cfg->precision == ARP_PREC_BF16;
+  if (const char* e = getenv("ARP_SNAKE")) h->snake = atoi(e) != 0;            // measurement switches, both exact:
+  if (const char* e = getenv("ARP_PRUNE_LAST")) h->prune_last = atoi(e) != 0;  // kernel order / last-block pruning
   h->grid = DEC_OUT / cfg->patch;
   h->tokens = h->grid * h->grid + 1;
   h->kp = 3 * cfg->patch * cfg->patch;
@@ -551,14 +524,11 @@ extern "C" int arp_create(const ArpConfig* cfg, ArpHandle** out) {
 
   const size_t B = cfg->max_batch, M = B * h->tokens, W = cfg->width;
 #define CREATE_TRY(e) do { int _r = (e); if (_r != ARP_OK) return bail(_r); } while (0)
-  if (const char* e = getenv("ARP_PIPES")) h->n_pipes = atoi(e) == 2 ? 2 : 1;
-  if (const char* e = getenv("ARP_GEMM_SMS")) h->gemm_sms = std::max(2, std::min(kNumSMs, atoi(e)));
-  if (const char* e = getenv("ARP_ATTN_SMS")) h->attn_sms = std::max(1, std::min(kNumSMs, atoi(e)));
   CREATE_TRY(dev_alloc(h, &h->rowtab, (size_t)h->tokens * W));
-  for (int p = 0; p < h->n_pipes; ++p) {
-    ArpHandle::Work& w = h->ws[p];
-    CREATE_TRY(dev_alloc(h, &w.x, M * W));
+  {
+    ArpHandle::Work& w = h->ws;
     if (h->f32) {
+      CREATE_TRY(dev_alloc(h, &w.x, M * W));
       CREATE_TRY(dev_alloc(h, &w.chw32, B * 3 * DEC_OUT * DEC_OUT));
       CREATE_TRY(dev_alloc(h, &w.xn32, M * W));
       CREATE_TRY(dev_alloc(h, &w.qkv32, M * 3 * W));
@@ -571,28 +541,33 @@ extern "C" int arp_create(const ArpConfig* cfg, ArpHandle** out) {
         CREATE_TRY(dev_alloc(h, &w.hid2_32, B * 2 * D));
         CREATE_TRY(dev_alloc(h, &w.mlp, B * D));
       }
-      continue;
-    }
-    CREATE_TRY(dev_alloc(h, &w.xn, M * W));
-    CREATE_TRY(dev_alloc(h, &w.qkv, M * 3 * W));
-    // padded key rows of a frame are the next frame's rows: keep every bit pattern in this buffer finite
-    if (cudaMemset(w.qkv, 0, M * 3 * W * sizeof(bf16)) != cudaSuccess) { h->err = "cudaMemset failed"; return bail(ARP_ERR_CUDA); }
-    CREATE_TRY(dev_alloc(h, &w.attn, M * W));
-    CREATE_TRY(dev_alloc(h, &w.hid, M * std::max<size_t>(4 * W, h->kp)));
-    if (h->ln_fold) CREATE_TRY(dev_alloc(h, &w.stats, M * 2 * (W / 128)));
-    CREATE_TRY(dev_alloc(h, &w.ln_cnt, M / 128 + 2));
-    CREATE_TRY(dev_alloc(h, &w.xcls, B * W));
-    CREATE_TRY(dev_alloc(h, &w.xncls, B * W));
-    CREATE_TRY(dev_alloc(h, &w.qcls, B * W));
-    CREATE_TRY(dev_alloc(h, &w.acls, B * W));
-    CREATE_TRY(dev_alloc(h, &w.hcls, B * 4 * W));
-    if (h->adapter) {
-      const size_t D = h->feat_dim;
-      CREATE_TRY(dev_alloc(h, &w.taps, B * cfg->layers * W));
-      CREATE_TRY(dev_alloc(h, &w.featf, B * D));
-      CREATE_TRY(dev_alloc(h, &w.featb, B * D));
-      CREATE_TRY(dev_alloc(h, &w.hid2, B * 2 * D));
-      CREATE_TRY(dev_alloc(h, &w.mlp, B * D));
+    } else {
+      CREATE_TRY(dev_alloc(h, &w.qkv, M * 3 * W));
+      // padded key rows of a frame are the next frame's rows: keep every bit pattern in this buffer finite
+      if (cudaMemset(w.qkv, 0, M * 3 * W * sizeof(bf16)) != cudaSuccess) { h->err = "cudaMemset failed"; return bail(ARP_ERR_CUDA); }
+      if (h->resid16) {
+        CREATE_TRY(dev_alloc(h, &w.x16, M * W));
+        CREATE_TRY(dev_alloc(h, &w.stats, M));
+        w.x = reinterpret_cast<float*>(w.qkv);   // fp32 [M, W] patch-embed output: 4MW of the 6MW bytes, dead before QKV
+      } else {
+        CREATE_TRY(dev_alloc(h, &w.x, M * W));
+        CREATE_TRY(dev_alloc(h, &w.xn, M * W));
+      }
+      CREATE_TRY(dev_alloc(h, &w.attn, M * W));
+      CREATE_TRY(dev_alloc(h, &w.hid, M * std::max<size_t>(4 * W, h->kp)));
+      CREATE_TRY(dev_alloc(h, &w.xcls, B * W));
+      CREATE_TRY(dev_alloc(h, &w.xncls, B * W));
+      CREATE_TRY(dev_alloc(h, &w.qcls, B * W));
+      CREATE_TRY(dev_alloc(h, &w.acls, B * W));
+      CREATE_TRY(dev_alloc(h, &w.hcls, B * 4 * W));
+      if (h->adapter) {
+        const size_t D = h->feat_dim;
+        CREATE_TRY(dev_alloc(h, &w.taps, B * cfg->layers * W));
+        CREATE_TRY(dev_alloc(h, &w.featf, B * D));
+        CREATE_TRY(dev_alloc(h, &w.featb, B * D));
+        CREATE_TRY(dev_alloc(h, &w.hid2, B * 2 * D));
+        CREATE_TRY(dev_alloc(h, &w.mlp, B * D));
+      }
     }
   }
   // weight buffers
@@ -603,13 +578,13 @@ extern "C" int arp_create(const ArpConfig* cfg, ArpHandle** out) {
     if (cudaMalloc(&p, s.numel * (s.as_bf16 ? 2 : 4) + 256) != cudaSuccess) { h->err = "cudaMalloc(weights) failed"; return bail(ARP_ERR_CUDA); }
     h->allocs.push_back(p);
     *s.dst = p;
-    if (s.dst_f32 && h->ln_fold) {
+    if (s.dst_f32 && h->resid16 && !h->f32) {
       float* q = nullptr;
       if (dev_alloc(h, &q, (size_t)s.numel) != ARP_OK) return bail(ARP_ERR_CUDA);
       *s.dst_f32 = q;
     }
   }
-  if (h->ln_fold) {
+  if (h->resid16 && !h->f32) {
     for (auto& L : h->layers) {
       if (dev_alloc(h, &L.w_qkv_fold, (size_t)3 * W * W) != ARP_OK || dev_alloc(h, &L.w_fc_fold, (size_t)4 * W * W) != ARP_OK ||
           dev_alloc(h, &L.s_qkv, (size_t)3 * W) != ARP_OK || dev_alloc(h, &L.c_qkv, (size_t)3 * W) != ARP_OK ||
@@ -618,24 +593,14 @@ extern "C" int arp_create(const ArpConfig* cfg, ArpHandle** out) {
     }
   }
   // opt-in shared memory
-  CREATE_TRY(set_smem(h, gemm_bf16_tcgen05_kernel<bf16, ACT_NONE>, GEMM_SMEM_BYTES));
-  CREATE_TRY(set_smem(h, gemm_bf16_tcgen05_kernel<bf16, ACT_QUICKGELU>, GEMM_SMEM_BYTES));
-  CREATE_TRY(set_smem(h, gemm_bf16_tcgen05_kernel<bf16, ACT_RELU>, GEMM_SMEM_BYTES));
-  CREATE_TRY(set_smem(h, gemm_bf16_tcgen05_kernel<float, ACT_NONE>, GEMM_SMEM_BYTES));
-  CREATE_TRY(set_smem(h, gemm_bf16_tcgen05_kernel<float, ACT_QUICKGELU>, GEMM_SMEM_BYTES));
-  CREATE_TRY(set_smem(h, gemm_bf16_tcgen05_kernel<float, ACT_RELU>, GEMM_SMEM_BYTES));
-#define G2_ATTR(T, A, R)                                                                              \
-  CREATE_TRY(set_smem(h, gemm2_bf16_tcgen05_kernel<T, A, 1, R>, G2Cfg<1>::SMEM_BYTES));               \
-  CREATE_TRY(set_smem(h, gemm2_bf16_tcgen05_kernel<T, A, 2, R>, G2Cfg<2>::SMEM_BYTES));
+#define G2_ATTR(T, A, R) CREATE_TRY(set_smem(h, gemm_tcgen05_kernel<T, A, 2, R>, G2Cfg<2>::SMEM_BYTES));
   G2_ATTR(bf16, ACT_NONE, G2_STORE) G2_ATTR(bf16, ACT_QUICKGELU, G2_STORE) G2_ATTR(bf16, ACT_RELU, G2_STORE)
   G2_ATTR(float, ACT_NONE, G2_STORE) G2_ATTR(float, ACT_QUICKGELU, G2_STORE) G2_ATTR(float, ACT_RELU, G2_STORE)
-  G2_ATTR(float, ACT_NONE, G2_REDUCE) G2_ATTR(float, ACT_NONE, G2_RESID_LN) G2_ATTR(float, ACT_NONE, G2_REDUCE_LN)
+  G2_ATTR(float, ACT_NONE, G2_REDUCE) G2_ATTR(bf16, ACT_NONE, G2_REDUCE)
   G2_ATTR(bf16, ACT_NONE, G2_LNFOLD) G2_ATTR(bf16, ACT_QUICKGELU, G2_LNFOLD)
 #undef G2_ATTR
   CREATE_TRY(set_smem(h, attention_tc_kernel<197>, AtcCfg<197>::SMEM_BYTES));
   CREATE_TRY(set_smem(h, attention_tc_kernel<50>, AtcCfg<50>::SMEM_BYTES));
-  CREATE_TRY(set_smem(h, attention_kernel<197>, AttnCfg<197>::SMEM));
-  CREATE_TRY(set_smem(h, attention_kernel<50>, AttnCfg<50>::SMEM));
   CREATE_TRY(set_smem(h, decode_kernel, 160 * 1024));
   CREATE_TRY(set_smem(h, clip_head_kernel<768, 512>, HEAD_SMEM_BYTES));
   CREATE_TRY(set_smem(h, attention_f32_kernel, attn_f32_smem_bytes(197)));
@@ -647,13 +612,7 @@ extern "C" int arp_create(const ArpConfig* cfg, ArpHandle** out) {
   for (int i = 0; i < 2; ++i) {
     cudaEventCreateWithFlags(&h->ev_copied[i], cudaEventDisableTiming);
     cudaEventCreateWithFlags(&h->ev_consumed[i], cudaEventDisableTiming);
-    cudaEventCreateWithFlags(&h->ev_join[i], cudaEventDisableTiming);
-    if (cudaStreamCreateWithFlags(&h->pipe_stream[i], cudaStreamNonBlocking) != cudaSuccess) {
-      h->err = "cudaStreamCreate failed";
-      return bail(ARP_ERR_CUDA);
-    }
   }
-  cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming);
 #undef CREATE_TRY
   *out = h;
   return ARP_OK;
@@ -743,7 +702,7 @@ static int finalize_weights(ArpHandle* h, cudaStream_t st) {
   const int n = h->tokens * h->cfg.width;
   build_rowtab_kernel<<<(n + 255) / 256, 256, 0, st>>>(h->pos_emb, h->class_emb, h->rowtab, h->tokens, h->cfg.width);
   h->launches++;
-  if (h->ln_fold) {
+  if (h->resid16 && !h->f32) {
     const int W = h->cfg.width;
     for (auto& L : h->layers) {
       fold_ln_weights_kernel<<<(3 * W + 7) / 8, 256, 0, st>>>(L.w_qkv_f32, L.ln1_g, L.ln1_b, L.b_qkv, L.w_qkv_fold, L.s_qkv, L.c_qkv, 3 * W, W);
@@ -825,46 +784,56 @@ static cudaError_t launch_clustered(K kernel, int grid, int cg, int smem, cudaSt
   return cudaLaunchKernelEx(&cfg, kernel, ta, tb, to, g);
 }
 
-// v2 GEMM: TMA-store epilogue, residual by TMA reduce-add, optional CTA pairs (gemm2_tcgen05.cuh)
-static int launch_gemm2(ArpHandle* h, const bf16* a, int64_t a_rows_alloc, const bf16* w, GemmArgs g, bool out_f32,
-                        int act, cudaStream_t st) {
-  const int cg = h->gemm_impl == 3 ? 2 : 1;
-  const CUtensorMap *ta, *tb, *to;
-  ARP_TRY(get_tmap(h, a, (uint64_t)a_rows_alloc, (uint64_t)g.K, (uint64_t)g.K, GEMM_BM, &ta));
-  ARP_TRY(get_tmap(h, w, (uint64_t)g.N, (uint64_t)g.K, (uint64_t)g.K, GEMM_BN / cg, &tb));
-  ARP_TRY(get_tmap(h, g.out, (uint64_t)g.M, (uint64_t)g.N, (uint64_t)g.ldo, 32, &to, out_f32 ? 32 : 64, out_f32 ? 4 : 2));
-  bool reduce = false;
-  const bool resid_ln = g.stats_out != nullptr;   // MODE 2: residual + bf16 copy + LN moments (reads the residual itself)
-  const bool lnfold = g.stats_in != nullptr;      // MODE 3: LayerNorm applied algebraically in the epilogue
-  if (resid_ln) {
-    if (!out_f32 || act != ACT_NONE || !g.resid || !g.xb || g.N % 256) return fail(h, ARP_ERR_INVALID, "bad residual+LN-moments GEMM");
-  } else if (lnfold) {
-    if (out_f32 || act == ACT_RELU || !g.svec || !g.cvec || g.K != 128 * g.stats_nh) return fail(h, ARP_ERR_INVALID, "bad LN-folded GEMM");
-  } else if (g.resid) {
-    if (!out_f32 || act != ACT_NONE) return fail(h, ARP_ERR_INVALID, "residual epilogue needs fp32 output and no activation");
-    if (g.resid != g.out)  // out-of-place residual (test hook only): seed the output, then accumulate into it
-      ARP_CUDA(h, cudaMemcpy2DAsync(g.out, (size_t)g.ldo * 4, g.resid, (size_t)g.ldr * 4, (size_t)g.N * 4, (size_t)g.M,
-                                    cudaMemcpyDeviceToDevice, st));
-    reduce = true;
-    g.resid = nullptr;
+// LayerNorm fold of one GEMM launch (gemm_tcgen05.cuh G2_LNFOLD): per-row statistics of A, per-column vectors of W
+struct LnFoldArgs { const float2* stats; const float* svec; const float* cvec; };
+
+// out[M, N] (ldo) = epilogue(a[M, K] · w[N, K]^T). `resid` (same dtype as out; must alias out on the hot path): the
+// output is ACCUMULATED into it by TMA reduce-add. a_rows_alloc: rows addressable behind `a` (>= M); the descriptor
+// covers them so that reading a partly filled workspace never depends on M (rows are independent; rows >= M are
+// computed and dropped by the clipped store).
+static int launch_gemm(ArpHandle* h, const bf16* a, int64_t a_rows_alloc, const bf16* w, void* out, bool out_f32,
+                       int act, int64_t M, int N, int K, int ldo, const float* bias, const void* resid, int ldr,
+                       const float* rowtab, int period, cudaStream_t st, const LnFoldArgs* fold = nullptr) {
+  if (M <= 0) return ARP_OK;
+  if (N % GEMM_BN || K % GEMM_BK) return fail(h, ARP_ERR_INVALID, "GEMM needs N %% 256 == 0 and K %% 64 == 0 (N=%d K=%d)", N, K);
+  if (M > 0x7fffffff / 2) return fail(h, ARP_ERR_INVALID, "GEMM M too large");
+  constexpr int cg = 2;
+  const size_t osz = out_f32 ? 4 : 2;
+  GemmArgs g;
+  memset(&g, 0, sizeof(g));
+  g.M = (int)M; g.N = N; g.K = K; g.out = out; g.ldo = ldo; g.bias = bias;
+  g.rowtab = rowtab; g.period = period > 0 ? period : 1;
+  g.reverse = h->snake ? (h->dir ^= 1) : 0;
+  const bool reduce = resid != nullptr;
+  if (fold) {
+    if (out_f32 || act == ACT_RELU || reduce || rowtab || !fold->stats || !fold->svec || !fold->cvec)
+      return fail(h, ARP_ERR_INVALID, "bad LayerNorm-folded GEMM");
+    g.ln_stats = fold->stats; g.svec = fold->svec; g.cvec = fold->cvec; g.bias = nullptr;   // cvec carries the bias
   }
-  const int tiles = (int)((g.M + GEMM_BM * cg - 1) / (GEMM_BM * cg)) * (g.N / GEMM_BN);
-  const int grid = std::min(tiles * cg, h->gemm_sms / cg * cg);
-  const int smem = cg == 2 ? G2Cfg<2>::SMEM_BYTES : G2Cfg<1>::SMEM_BYTES;
-  ProfScope prof(h, PC_GEMM, 2.0 * (double)g.M * g.N * g.K,
-                 (double)g.M * g.K * 2 + (double)g.N * g.K * 2 + (double)g.M * g.N * (out_f32 ? 4 : 2) * (reduce || resid_ln ? 2 : 1) +
-                     (resid_ln ? (double)g.M * g.N * 2 : 0.0), st);
+  if (reduce) {
+    if (act != ACT_NONE) return fail(h, ARP_ERR_INVALID, "the residual epilogue takes no activation");
+    if (resid != out)  // out-of-place residual (test hook only): seed the output, then accumulate into it
+      ARP_CUDA(h, cudaMemcpy2DAsync(out, (size_t)ldo * osz, resid, (size_t)ldr * osz, (size_t)N * osz, (size_t)M,
+                                    cudaMemcpyDeviceToDevice, st));
+  }
+  const CUtensorMap *ta, *tb, *to;
+  ARP_TRY(get_tmap(h, a, (uint64_t)a_rows_alloc, (uint64_t)K, (uint64_t)K, GEMM_BM, &ta));
+  ARP_TRY(get_tmap(h, w, (uint64_t)N, (uint64_t)K, (uint64_t)K, GEMM_BN / cg, &tb));
+  ARP_TRY(get_tmap(h, out, (uint64_t)M, (uint64_t)N, (uint64_t)ldo, 32, &to, out_f32 ? 32 : 64, out_f32 ? 4 : 2));
+  const int tiles = (int)((M + GEMM_BM * cg - 1) / (GEMM_BM * cg)) * (N / GEMM_BN);
+  const int grid = std::min(tiles * cg, kNumSMs / cg * cg);
+  const int smem = G2Cfg<cg>::SMEM_BYTES;
+  ProfScope prof(h, PC_GEMM, 2.0 * (double)M * N * K,
+                 (double)M * K * 2 + (double)N * K * 2 + (double)M * N * osz * (reduce ? 2 : 1), st);
   cudaError_t e;
-#define G2_LAUNCH(T, A, R)                                                                                         \
-  e = cg == 2 ? launch_clustered(gemm2_bf16_tcgen05_kernel<T, A, 2, R>, grid, 2, smem, st, *ta, *tb, *to, g)       \
-              : launch_clustered(gemm2_bf16_tcgen05_kernel<T, A, 1, R>, grid, 1, smem, st, *ta, *tb, *to, g)
-  if (resid_ln) G2_LAUNCH(float, ACT_NONE, G2_RESID_LN);
-  else if (lnfold) {
+#define G2_LAUNCH(T, A, R) e = launch_clustered(gemm_tcgen05_kernel<T, A, cg, R>, grid, cg, smem, st, *ta, *tb, *to, g)
+  if (fold) {
     if (act == ACT_NONE) G2_LAUNCH(bf16, ACT_NONE, G2_LNFOLD);
     else G2_LAUNCH(bf16, ACT_QUICKGELU, G2_LNFOLD);
-  } else if (reduce && g.ln_out) G2_LAUNCH(float, ACT_NONE, G2_REDUCE_LN);
-  else if (reduce) G2_LAUNCH(float, ACT_NONE, G2_REDUCE);
-  else if (out_f32) {
+  } else if (reduce) {
+    if (out_f32) G2_LAUNCH(float, ACT_NONE, G2_REDUCE);
+    else G2_LAUNCH(bf16, ACT_NONE, G2_REDUCE);
+  } else if (out_f32) {
     if (act == ACT_NONE) G2_LAUNCH(float, ACT_NONE, G2_STORE);
     else if (act == ACT_QUICKGELU) G2_LAUNCH(float, ACT_QUICKGELU, G2_STORE);
     else G2_LAUNCH(float, ACT_RELU, G2_STORE);
@@ -875,66 +844,7 @@ static int launch_gemm2(ArpHandle* h, const bf16* a, int64_t a_rows_alloc, const
   }
 #undef G2_LAUNCH
   h->launches++;
-  if (e != cudaSuccess) return fail(h, ARP_ERR_CUDA, "gemm2 launch failed: %s", cudaGetErrorString(e));
-  return ARP_OK;
-}
-
-// a_rows_alloc: rows addressable behind `a` (>= M); the descriptor covers them so that reading a partly
-// filled workspace never depends on M (rows are independent; rows >= M are computed and dropped).
-// LayerNorm-fold extras of one GEMM launch (gemm2 MODE 2 / MODE 3, see GemmArgs)
-struct LnFoldArgs {
-  bf16* xb = nullptr; float* stats_out = nullptr;                                         // MODE 2
-  const float* stats_in = nullptr; const float* svec = nullptr; const float* cvec = nullptr;  // MODE 3
-};
-
-// LayerNorm fused behind a residual GEMM (GemmArgs::ln_*)
-struct LnFuseArgs { const float* gamma; const float* beta; bf16* out; int* cnt; };
-
-static int launch_gemm(ArpHandle* h, const bf16* a, int64_t a_rows_alloc, const bf16* w, void* out, bool out_f32,
-                       int act, int64_t M, int N, int K, int ldo, const float* bias, const float* resid, int ldr,
-                       const float* rowtab, int period, cudaStream_t st, const LnFoldArgs* fold = nullptr,
-                       const LnFuseArgs* fuse = nullptr) {
-  if (M <= 0) return ARP_OK;
-  if (N % GEMM_BN || K % GEMM_BK) return fail(h, ARP_ERR_INVALID, "GEMM needs N %% 256 == 0 and K %% 64 == 0 (N=%d K=%d)", N, K);
-  if (M > 0x7fffffff / 2) return fail(h, ARP_ERR_INVALID, "GEMM M too large");
-  const CUtensorMap *ta, *tb;
-  ARP_TRY(get_tmap(h, a, (uint64_t)a_rows_alloc, (uint64_t)K, (uint64_t)K, GEMM_BM, &ta));
-  ARP_TRY(get_tmap(h, w, (uint64_t)N, (uint64_t)K, (uint64_t)K, GEMM_BN, &tb));
-  GemmArgs g;
-  memset(&g, 0, sizeof(g));
-  g.M = (int)M; g.N = N; g.K = K; g.out = out; g.ldo = ldo; g.bias = bias; g.resid = resid; g.ldr = ldr;
-  g.rowtab = rowtab; g.period = period > 0 ? period : 1;
-  g.eps = 1e-5f;
-  g.reverse = h->snake ? (h->dir ^= 1) : 0;
-  if (fold) {
-    if (h->gemm_impl < 2) return fail(h, ARP_ERR_INVALID, "the LayerNorm fold needs the v2 GEMM");
-    g.xb = fold->xb; g.stats_out = fold->stats_out; g.stats_in = fold->stats_in; g.stats_nh = K / 128;
-    g.svec = fold->svec; g.cvec = fold->cvec;
-  }
-  if (fuse) {
-    if (h->gemm_impl < 2 || !out_f32 || act != ACT_NONE || !resid || resid != out || N != 768 || ldo != 768)
-      return fail(h, ARP_ERR_INVALID, "fused LayerNorm needs the in-place fp32 residual GEMM with N = 768");
-    g.ln_gamma = fuse->gamma; g.ln_beta = fuse->beta; g.ln_out = fuse->out; g.ln_cnt = fuse->cnt;
-    ARP_CUDA(h, cudaMemsetAsync(fuse->cnt, 0, (size_t)((M + 127) / 128) * sizeof(int), st));
-  }
-  if (h->gemm_impl >= 2) return launch_gemm2(h, a, a_rows_alloc, w, g, out_f32, act, st);
-  const int tiles = (int)((M + GEMM_BM - 1) / GEMM_BM) * (N / GEMM_BN);
-  const int grid = std::min(tiles, kNumSMs);
-  ProfScope prof(h, PC_GEMM, 2.0 * (double)M * N * K,
-                 (double)M * K * 2 + (double)N * K * 2 + (double)M * N * (out_f32 ? 4 : 2) + (resid ? (double)M * N * 4 : 0), st);
-#define GEMM_CASE(T, A) gemm_bf16_tcgen05_kernel<T, A><<<grid, GEMM_THREADS, GEMM_SMEM_BYTES, st>>>(*ta, *tb, g)
-  if (out_f32) {
-    if (act == ACT_NONE) GEMM_CASE(float, ACT_NONE);
-    else if (act == ACT_QUICKGELU) GEMM_CASE(float, ACT_QUICKGELU);
-    else GEMM_CASE(float, ACT_RELU);
-  } else {
-    if (act == ACT_NONE) GEMM_CASE(bf16, ACT_NONE);
-    else if (act == ACT_QUICKGELU) GEMM_CASE(bf16, ACT_QUICKGELU);
-    else GEMM_CASE(bf16, ACT_RELU);
-  }
-#undef GEMM_CASE
-  h->launches++;
-  ARP_CUDA(h, cudaGetLastError());
+  if (e != cudaSuccess) return fail(h, ARP_ERR_CUDA, "GEMM launch failed: %s", cudaGetErrorString(e));
   return ARP_OK;
 }
 
@@ -982,42 +892,36 @@ static int launch_ln_bf16(ArpHandle* h, const float* x, const float* g, const fl
   return ARP_OK;
 }
 
+// (rstd, -mean*rstd) of every row of the 16-bit residual stream: the LayerNorm the next GEMM applies in its epilogue
+static int launch_row_moments(ArpHandle* h, const bf16* x, float2* stats, int64_t M, cudaStream_t st) {
+  if (M <= 0) return ARP_OK;
+  ProfScope prof(h, PC_LAYERNORM, 0.0, (double)M * (768 * 2 + 8), st);
+  row_moments_kernel<768><<<(unsigned)((M + 7) / 8), 256, 0, st>>>(x, stats, (int)M, 1e-5f, h->snake ? (h->dir ^= 1) : 0);
+  h->launches++;
+  ARP_CUDA(h, cudaGetLastError());
+  return ARP_OK;
+}
+
 static int launch_attention(ArpHandle* h, const bf16* qkv, bf16* out, int B, int tokens, cudaStream_t st,
                             int64_t rows_alloc = 0) {
   if (B <= 0) return ARP_OK;
   const float scale_log2e = 0.125f * 1.4426950408889634f;
-  ProfScope prof(h, PC_ATTENTION, 4.0 * (double)B * h->cfg.heads * tokens * tokens * ATT_DH,
+  ProfScope prof(h, PC_ATTENTION, 4.0 * (double)B * h->cfg.heads * tokens * tokens * 64,
                  (double)B * tokens * h->cfg.width * 2 * 4, st);
-  if (h->attn_impl == 2) {
-    if (tokens != 197 && tokens != 50) return fail(h, ARP_ERR_INVALID, "attention is built for 197 or 50 tokens, got %d", tokens);
-    const int W = h->cfg.width;
-    const uint64_t rows = rows_alloc > 0 ? (uint64_t)rows_alloc : (uint64_t)B * tokens;
-    const int nk = (tokens + 15) / 16 * 16;
-    const CUtensorMap *tq, *tkv;
-    ARP_TRY(get_tmap(h, qkv, rows, 3 * W, 3 * W, 128, &tq));
-    ARP_TRY(get_tmap(h, qkv, rows, 3 * W, 3 * W, nk, &tkv));
-    const int grid = std::min(B * h->cfg.heads, h->attn_sms);
-    const int rev = h->snake ? (h->dir ^= 1) : 0;
-    if (tokens == 197)
-      attention_tc_kernel<197><<<grid, ATC_THREADS, AtcCfg<197>::SMEM_BYTES, st>>>(*tq, *tkv, out, B, h->cfg.heads, W, scale_log2e, rev);
-    else
-      attention_tc_kernel<50><<<grid, ATC_THREADS, AtcCfg<50>::SMEM_BYTES, st>>>(*tq, *tkv, out, B, h->cfg.heads, W, scale_log2e, rev);
-    h->launches++;
-    ARP_CUDA(h, cudaGetLastError());
-    return ARP_OK;
-  }
-  for (int b0 = 0; b0 < B; b0 += 32768) {
-    const int cnt = std::min(32768, B - b0);
-    const bf16* q = qkv + (size_t)b0 * tokens * 3 * h->cfg.width;
-    bf16* o = out + (size_t)b0 * tokens * h->cfg.width;
-    if (tokens == 197)
-      attention_kernel<197><<<dim3(h->cfg.heads, cnt), ATT_THREADS, AttnCfg<197>::SMEM, st>>>(q, o, h->cfg.width, scale_log2e);
-    else if (tokens == 50)
-      attention_kernel<50><<<dim3(h->cfg.heads, cnt), ATT_THREADS, AttnCfg<50>::SMEM, st>>>(q, o, h->cfg.width, scale_log2e);
-    else
-      return fail(h, ARP_ERR_INVALID, "attention is built for 197 or 50 tokens, got %d", tokens);
-    h->launches++;
-  }
+  if (tokens != 197 && tokens != 50) return fail(h, ARP_ERR_INVALID, "attention is built for 197 or 50 tokens, got %d", tokens);
+  const int W = h->cfg.width;
+  const uint64_t rows = rows_alloc > 0 ? (uint64_t)rows_alloc : (uint64_t)B * tokens;
+  const int nk = (tokens + 15) / 16 * 16;
+  const CUtensorMap *tq, *tkv;
+  ARP_TRY(get_tmap(h, qkv, rows, 3 * W, 3 * W, 128, &tq));
+  ARP_TRY(get_tmap(h, qkv, rows, 3 * W, 3 * W, nk, &tkv));
+  const int grid = std::min(B * h->cfg.heads, kNumSMs);
+  const int rev = h->snake ? (h->dir ^= 1) : 0;
+  if (tokens == 197)
+    attention_tc_kernel<197><<<grid, ATC_THREADS, AtcCfg<197>::SMEM_BYTES, st>>>(*tq, *tkv, out, B, h->cfg.heads, W, scale_log2e, rev);
+  else
+    attention_tc_kernel<50><<<grid, ATC_THREADS, AtcCfg<50>::SMEM_BYTES, st>>>(*tq, *tkv, out, B, h->cfg.heads, W, scale_log2e, rev);
+  h->launches++;
   ARP_CUDA(h, cudaGetLastError());
   return ARP_OK;
 }
@@ -1025,12 +929,148 @@ static int launch_attention(ArpHandle* h, const bf16* qkv, bf16* out, int B, int
 // ------------------------------------------------------------------------------------------------
 // the encoder: n frames (n <= max_batch) -> residual stream x after the last block (+ CLS taps)
 // ------------------------------------------------------------------------------------------------
-static int encode_chunk_f32(ArpHandle* h, int pipe, const uint8_t* ob, int64_t n, int64_t stride, cudaStream_t st);
+static int encode_chunk_f32(ArpHandle* h, const uint8_t* ob, int64_t n, int64_t stride, cudaStream_t st);
 
-static int encode_chunk(ArpHandle* h, int pipe, const uint8_t* ob, int64_t n, int64_t stride, cudaStream_t st) {
-  if (h->f32) return encode_chunk_f32(h, pipe, ob, n, stride, st);
+// The last resblock for the class-token row only (see ArpHandle::prune_last). K and V of every token are already in
+// ws.qkv (columns [W, 3W)); XT = type of the residual stream `x` the class-token rows are gathered from.
+template <typename XT>
+static int last_block_cls(ArpHandle* h, const LayerW& L, const XT* x, int64_t n, cudaStream_t st) {
   const ArpConfig& c = h->cfg;
-  ArpHandle::Work& ws = h->ws[pipe];
+  ArpHandle::Work& ws = h->ws;
+  const int W = c.width;
+  const int64_t B = c.max_batch;
+  gather_cls_rows_f32_kernel<768, XT><<<(unsigned)((n + 7) / 8), 256, 0, st>>>(x, ws.xcls, (int)n, h->tokens, W, 0);
+  h->launches++;
+  ARP_TRY(launch_ln_bf16(h, ws.xcls, L.ln1_g, L.ln1_b, ws.xncls, n, st));
+  ARP_TRY(launch_gemm(h, ws.xncls, B, L.w_qkv, ws.qcls, false, ACT_NONE, n, W, W, W, L.b_qkv, nullptr, 0, nullptr, 0, st));
+  {
+    ProfScope prof(h, PC_ATTENTION, 4.0 * (double)n * c.heads * h->tokens * 64,
+                   (double)n * h->tokens * W * 2 * 2 + (double)n * W * 2 * 2, st);
+    const unsigned blocks = (unsigned)((n * c.heads + 7) / 8);
+    if (h->tokens == 197)
+      cls_attention_kernel<197><<<blocks, 256, 0, st>>>(ws.qcls, ws.qkv, ws.acls, (int)n, c.heads, W, 0.125f);
+    else if (h->tokens == 50)
+      cls_attention_kernel<50><<<blocks, 256, 0, st>>>(ws.qcls, ws.qkv, ws.acls, (int)n, c.heads, W, 0.125f);
+    else
+      return fail(h, ARP_ERR_INVALID, "attention is built for 197 or 50 tokens, got %d", h->tokens);
+    h->launches++;
+  }
+  ARP_TRY(launch_gemm(h, ws.acls, B, L.w_out, ws.xcls, true, ACT_NONE, n, W, W, W, L.b_out, ws.xcls, W, nullptr, 0, st));
+  ARP_TRY(launch_ln_bf16(h, ws.xcls, L.ln2_g, L.ln2_b, ws.xncls, n, st));
+  ARP_TRY(launch_gemm(h, ws.xncls, B, L.w_fc, ws.hcls, false, ACT_QUICKGELU, n, 4 * W, W, 4 * W, L.b_fc, nullptr, 0,
+                      nullptr, 0, st));
+  ARP_TRY(launch_gemm(h, ws.hcls, B, L.w_proj, ws.xcls, true, ACT_NONE, n, W, 4 * W, W, L.b_proj, ws.xcls, W, nullptr,
+                      0, st));
+  const int l = c.layers - 1;
+  if (h->adapter) {
+    gather_cls_bf16_kernel<768, float><<<(unsigned)((n + 7) / 8), 256, 0, st>>>(ws.xcls, ws.taps, (int)n, 1, c.layers * W, l * W);
+    h->launches++;
+  }
+  if (h->cur_taps32) {
+    gather_cls_rows_f32_kernel<768, float><<<(unsigned)((n + 7) / 8), 256, 0, st>>>(ws.xcls, h->cur_taps32, (int)n, 1,
+                                                                                 c.layers * W, l * W);
+    h->launches++;
+  }
+  ws.cls_compact = true;
+  return ARP_OK;
+}
+
+// class-token taps of block l's output: 16-bit for the adapter head, fp32 for arp_encode_taps_chw
+template <typename XT>
+static void gather_taps(ArpHandle* h, const XT* x, int64_t n, int l, cudaStream_t st) {
+  const ArpConfig& c = h->cfg;
+  if (h->adapter) {
+    gather_cls_bf16_kernel<768, XT><<<(unsigned)((n + 7) / 8), 256, 0, st>>>(x, h->ws.taps, (int)n, h->tokens,
+                                                                          c.layers * c.width, l * c.width);
+    h->launches++;
+  }
+  if (h->cur_taps32) {
+    gather_cls_rows_f32_kernel<768, XT><<<(unsigned)((n + 7) / 8), 256, 0, st>>>(x, h->cur_taps32, (int)n, h->tokens,
+                                                                              c.layers * c.width, l * c.width);
+    h->launches++;
+  }
+}
+
+// Default path: 16-bit residual stream, LayerNorm folded into the consumer GEMMs (ArpHandle::resid16).
+static int encode_blocks_r16(ArpHandle* h, int64_t n, cudaStream_t st) {
+  const ArpConfig& c = h->cfg;
+  ArpHandle::Work& ws = h->ws;
+  const int W = c.width;
+  const int64_t M = n * h->tokens, Mcap = (int64_t)c.max_batch * h->tokens;
+  {
+    ProfScope prof(h, PC_LAYERNORM, 0.0, (double)M * (768 * 6 + 8), st);
+    layernorm_pre_r16_kernel<768><<<(unsigned)((M + 7) / 8), 256, 0, st>>>(ws.x, h->ln_pre_g, h->ln_pre_b, ws.x16,
+                                                                          ws.stats, (int)M, 1e-5f);
+    h->launches++;
+  }
+  for (int l = 0; l < c.layers; ++l) {
+    const LayerW& L = h->layers[l];
+    if (l == c.layers - 1 && h->prune_last) {
+      // K and V of every token: rows [W, 3W) of in_proj, written at column W of the qkv buffer
+      const LnFoldArgs f_kv{ws.stats, L.s_qkv + W, L.c_qkv + W};
+      ARP_TRY(launch_gemm(h, ws.x16, Mcap, L.w_qkv_fold + (size_t)W * W, ws.qkv + W, false, ACT_NONE, M, 2 * W, W, 3 * W,
+                          nullptr, nullptr, 0, nullptr, 0, st, &f_kv));
+      ARP_TRY(last_block_cls(h, L, ws.x16, n, st));
+      break;
+    }
+    const LnFoldArgs f_qkv{ws.stats, L.s_qkv, L.c_qkv}, f_fc{ws.stats, L.s_fc, L.c_fc};
+    ARP_TRY(launch_gemm(h, ws.x16, Mcap, L.w_qkv_fold, ws.qkv, false, ACT_NONE, M, 3 * W, W, 3 * W, nullptr, nullptr, 0,
+                        nullptr, 0, st, &f_qkv));
+    ARP_TRY(launch_attention(h, ws.qkv, ws.attn, (int)n, h->tokens, st, Mcap));
+    ARP_TRY(launch_gemm(h, ws.attn, Mcap, L.w_out, ws.x16, false, ACT_NONE, M, W, W, W, L.b_out, ws.x16, W, nullptr, 0, st));
+    ARP_TRY(launch_row_moments(h, ws.x16, ws.stats, M, st));
+    ARP_TRY(launch_gemm(h, ws.x16, Mcap, L.w_fc_fold, ws.hid, false, ACT_QUICKGELU, M, 4 * W, W, 4 * W, nullptr, nullptr,
+                        0, nullptr, 0, st, &f_fc));
+    ARP_TRY(launch_gemm(h, ws.hid, Mcap, L.w_proj, ws.x16, false, ACT_NONE, M, W, 4 * W, W, L.b_proj, ws.x16, W, nullptr,
+                        0, st));
+    if (l + 1 < c.layers) ARP_TRY(launch_row_moments(h, ws.x16, ws.stats, M, st));
+    gather_taps(h, ws.x16, n, l, st);
+  }
+  if (!ws.cls_compact) {   // prune_last off: hand the heads compact fp32 class-token rows all the same
+    gather_cls_rows_f32_kernel<768, bf16><<<(unsigned)((n + 7) / 8), 256, 0, st>>>(ws.x16, ws.xcls, (int)n, h->tokens, W, 0);
+    h->launches++;
+    ws.cls_compact = true;
+  }
+  return ARP_OK;
+}
+
+// ARP_PREC_F32RESID: fp32 residual stream, standalone LayerNorm kernels writing the 16-bit GEMM operand.
+static int encode_blocks_r32(ArpHandle* h, int64_t n, cudaStream_t st) {
+  const ArpConfig& c = h->cfg;
+  ArpHandle::Work& ws = h->ws;
+  const int W = c.width;
+  const int64_t M = n * h->tokens, Mcap = (int64_t)c.max_batch * h->tokens;
+  {
+    ProfScope prof(h, PC_LAYERNORM, 0.0, (double)M * 768 * 8, st);
+    layernorm_f32_inplace_kernel<768><<<(unsigned)((M + 7) / 8), 256, 0, st>>>(ws.x, h->ln_pre_g, h->ln_pre_b, (int)M, 1e-5f);
+    h->launches++;
+  }
+  for (int l = 0; l < c.layers; ++l) {
+    const LayerW& L = h->layers[l];
+    ARP_TRY(launch_ln_bf16(h, ws.x, L.ln1_g, L.ln1_b, ws.xn, M, st));
+    if (l == c.layers - 1 && h->prune_last) {
+      ARP_TRY(launch_gemm(h, ws.xn, Mcap, L.w_qkv + (size_t)W * W, ws.qkv + W, false, ACT_NONE, M, 2 * W, W, 3 * W,
+                          L.b_qkv + W, nullptr, 0, nullptr, 0, st));
+      ARP_TRY(last_block_cls(h, L, ws.x, n, st));
+      break;
+    }
+    ARP_TRY(launch_gemm(h, ws.xn, Mcap, L.w_qkv, ws.qkv, false, ACT_NONE, M, 3 * W, W, 3 * W, L.b_qkv, nullptr, 0,
+                        nullptr, 0, st));
+    ARP_TRY(launch_attention(h, ws.qkv, ws.attn, (int)n, h->tokens, st, Mcap));
+    ARP_TRY(launch_gemm(h, ws.attn, Mcap, L.w_out, ws.x, true, ACT_NONE, M, W, W, W, L.b_out, ws.x, W, nullptr, 0, st));
+    ARP_TRY(launch_ln_bf16(h, ws.x, L.ln2_g, L.ln2_b, ws.xn, M, st));
+    ARP_TRY(launch_gemm(h, ws.xn, Mcap, L.w_fc, ws.hid, false, ACT_QUICKGELU, M, 4 * W, W, 4 * W, L.b_fc, nullptr, 0,
+                        nullptr, 0, st));
+    ARP_TRY(launch_gemm(h, ws.hid, Mcap, L.w_proj, ws.x, true, ACT_NONE, M, W, 4 * W, W, L.b_proj, ws.x, W, nullptr, 0, st));
+    gather_taps(h, ws.x, n, l, st);
+  }
+  return ARP_OK;
+}
+
+static int encode_chunk(ArpHandle* h, const uint8_t* ob, int64_t n, int64_t stride, cudaStream_t st) {
+  if (h->f32) return encode_chunk_f32(h, ob, n, stride, st);
+  const ArpConfig& c = h->cfg;
+  ArpHandle::Work& ws = h->ws;
   const int W = c.width;
   const int64_t M = n * h->tokens;
   const int64_t Mcap = (int64_t)c.max_batch * h->tokens;
@@ -1042,136 +1082,11 @@ static int encode_chunk(ArpHandle* h, int pipe, const uint8_t* ob, int64_t n, in
   } else {
     ARP_TRY(launch_decode(h, ob, n, stride, patches, DEC_OUT_PATCH_BF16, st));
   }
-  auto tap = [&](const float* xsrc_, int tok_, int l_) {      // fp32 class-token rows of block l_'s output
-    if (!h->cur_taps32) return;
-    gather_cls_f32_kernel<768><<<(unsigned)((n + 7) / 8), 256, 0, st>>>(xsrc_, h->cur_taps32, (int)n, tok_, c.layers * W, l_ * W);
-    h->launches++;
-  };
-  // patch embed (+ positional embedding, + class embedding on the all-zero row 0 of each frame)
+  // patch embed (+ positional embedding, + class embedding on the all-zero row 0 of each frame), fp32 out
   ARP_TRY(launch_gemm(h, patches, Mcap, h->conv1, ws.x, true, ACT_NONE, M, W, h->kp, W, nullptr, nullptr, 0,
                       h->rowtab, h->tokens, st));
-  if (h->ln_fold) {
-    ws.pruned = false;
-    // LayerNorm never runs as its own kernel inside the blocks: the residual GEMMs (out_proj, c_proj) emit a bf16
-    // copy of x and per-row moments, and the LN-consuming GEMMs (QKV, c_fc) apply mean / rstd / gamma / beta in
-    // their epilogues on top of gamma-folded weights (GemmArgs, gemm2 MODE 2 / 3).
-    {
-      ProfScope prof(h, PC_LAYERNORM, 0.0, (double)M * 768 * 10, st);
-      layernorm_pre_fold_kernel<768><<<(unsigned)((M + 7) / 8), 256, 0, st>>>(ws.x, h->ln_pre_g, h->ln_pre_b, ws.xn,
-                                                                             ws.stats, (int)M, 1e-5f);
-      h->launches++;
-    }
-    for (int l = 0; l < c.layers; ++l) {
-      const LayerW& L = h->layers[l];
-      LnFoldArgs f_qkv, f_fc, f_res;
-      f_qkv.stats_in = ws.stats; f_qkv.svec = L.s_qkv; f_qkv.cvec = L.c_qkv;
-      f_fc.stats_in = ws.stats; f_fc.svec = L.s_fc; f_fc.cvec = L.c_fc;
-      f_res.xb = ws.xn; f_res.stats_out = ws.stats;
-      ARP_TRY(launch_gemm(h, ws.xn, Mcap, L.w_qkv_fold, ws.qkv, false, ACT_NONE, M, 3 * W, W, 3 * W, nullptr, nullptr, 0,
-                          nullptr, 0, st, &f_qkv));
-      ARP_TRY(launch_attention(h, ws.qkv, ws.attn, (int)n, h->tokens, st, Mcap));
-      if (h->ln_fold >= 2) {
-        ARP_TRY(launch_gemm(h, ws.attn, Mcap, L.w_out, ws.x, true, ACT_NONE, M, W, W, W, L.b_out, ws.x, W, nullptr, 0, st,
-                            &f_res));
-        ARP_TRY(launch_gemm(h, ws.xn, Mcap, L.w_fc_fold, ws.hid, false, ACT_QUICKGELU, M, 4 * W, W, 4 * W, nullptr,
-                            nullptr, 0, nullptr, 0, st, &f_fc));
-      } else {
-        // out_proj (K = N = 768) is HBM-bound: its residual stays a TMA reduce-add and ln_2 a standalone kernel
-        ARP_TRY(launch_gemm(h, ws.attn, Mcap, L.w_out, ws.x, true, ACT_NONE, M, W, W, W, L.b_out, ws.x, W, nullptr, 0, st));
-        ARP_TRY(launch_ln_bf16(h, ws.x, L.ln2_g, L.ln2_b, ws.xn, M, st));
-        ARP_TRY(launch_gemm(h, ws.xn, Mcap, L.w_fc, ws.hid, false, ACT_QUICKGELU, M, 4 * W, W, 4 * W, L.b_fc, nullptr, 0,
-                            nullptr, 0, st));
-      }
-      ARP_TRY(launch_gemm(h, ws.hid, Mcap, L.w_proj, ws.x, true, ACT_NONE, M, W, 4 * W, W, L.b_proj, ws.x, W, nullptr, 0,
-                          st, &f_res));
-      if (h->adapter) {
-        gather_cls_bf16_kernel<768><<<(unsigned)((n + 7) / 8), 256, 0, st>>>(ws.x, ws.taps, (int)n, h->tokens,
-                                                                           c.layers * W, l * W);
-        h->launches++;
-      }
-      tap(ws.x, h->tokens, l);
-    }
-    ARP_CUDA(h, cudaGetLastError());
-    return ARP_OK;
-  }
-  {
-    ProfScope prof(h, PC_LAYERNORM, 0.0, (double)M * 768 * 8, st);
-    layernorm_f32_inplace_kernel<768><<<(unsigned)((M + 7) / 8), 256, 0, st>>>(ws.x, h->ln_pre_g, h->ln_pre_b, (int)M, 1e-5f);
-    h->launches++;
-  }
-  ws.pruned = false;
-  bool xn_ready = false;   // ws.xn already holds this block's ln_1(x): fused behind the previous block's c_proj
-  for (int l = 0; l < c.layers; ++l) {
-    const LayerW& L = h->layers[l];
-    if (!xn_ready) ARP_TRY(launch_ln_bf16(h, ws.x, L.ln1_g, L.ln1_b, ws.xn, M, st));
-    xn_ready = false;
-    if (l == c.layers - 1 && h->prune_last) {
-      // ---- last block, class-token row only (see ArpHandle::prune_last) ----
-      const int64_t B = c.max_batch;
-      // K and V of every token: rows [W, 3W) of in_proj, written at column W of the qkv buffer
-      ARP_TRY(launch_gemm(h, ws.xn, Mcap, L.w_qkv + (size_t)W * W, ws.qkv + W, false, ACT_NONE, M, 2 * W, W, 3 * W,
-                          L.b_qkv + W, nullptr, 0, nullptr, 0, st));
-      gather_cls_rows_f32_kernel<768><<<(unsigned)((n + 7) / 8), 256, 0, st>>>(ws.x, ws.xcls, (int)n, h->tokens);
-      h->launches++;
-      ARP_TRY(launch_ln_bf16(h, ws.xcls, L.ln1_g, L.ln1_b, ws.xncls, n, st));
-      ARP_TRY(launch_gemm(h, ws.xncls, B, L.w_qkv, ws.qcls, false, ACT_NONE, n, W, W, W, L.b_qkv, nullptr, 0, nullptr, 0, st));
-      {
-        ProfScope prof(h, PC_ATTENTION, 4.0 * (double)n * c.heads * h->tokens * 64,
-                       (double)n * h->tokens * W * 2 * 2 + (double)n * W * 2 * 2, st);
-        const unsigned blocks = (unsigned)((n * c.heads + 7) / 8);
-        if (h->tokens == 197)
-          cls_attention_kernel<197><<<blocks, 256, 0, st>>>(ws.qcls, ws.qkv, ws.acls, (int)n, c.heads, W, 0.125f);
-        else if (h->tokens == 50)
-          cls_attention_kernel<50><<<blocks, 256, 0, st>>>(ws.qcls, ws.qkv, ws.acls, (int)n, c.heads, W, 0.125f);
-        else
-          return fail(h, ARP_ERR_INVALID, "attention is built for 197 or 50 tokens, got %d", h->tokens);
-        h->launches++;
-      }
-      ARP_TRY(launch_gemm(h, ws.acls, B, L.w_out, ws.xcls, true, ACT_NONE, n, W, W, W, L.b_out, ws.xcls, W, nullptr, 0, st));
-      ARP_TRY(launch_ln_bf16(h, ws.xcls, L.ln2_g, L.ln2_b, ws.xncls, n, st));
-      ARP_TRY(launch_gemm(h, ws.xncls, B, L.w_fc, ws.hcls, false, ACT_QUICKGELU, n, 4 * W, W, 4 * W, L.b_fc, nullptr, 0,
-                          nullptr, 0, st));
-      ARP_TRY(launch_gemm(h, ws.hcls, B, L.w_proj, ws.xcls, true, ACT_NONE, n, W, 4 * W, W, L.b_proj, ws.xcls, W, nullptr,
-                          0, st));
-      if (h->adapter) {
-        gather_cls_bf16_kernel<768><<<(unsigned)((n + 7) / 8), 256, 0, st>>>(ws.xcls, ws.taps, (int)n, 1, c.layers * W,
-                                                                           l * W);
-        h->launches++;
-      }
-      tap(ws.xcls, 1, l);
-      ws.pruned = true;
-      break;
-    }
-    ARP_TRY(launch_gemm(h, ws.xn, Mcap, L.w_qkv, ws.qkv, false, ACT_NONE, M, 3 * W, W, 3 * W, L.b_qkv, nullptr, 0,
-                        nullptr, 0, st));
-    ARP_TRY(launch_attention(h, ws.qkv, ws.attn, (int)n, h->tokens, st, Mcap));
-    if (h->ln_fuse & 1) {
-      const LnFuseArgs f2{L.ln2_g, L.ln2_b, ws.xn, ws.ln_cnt};
-      ARP_TRY(launch_gemm(h, ws.attn, Mcap, L.w_out, ws.x, true, ACT_NONE, M, W, W, W, L.b_out, ws.x, W, nullptr, 0, st,
-                          nullptr, &f2));
-    } else {
-      ARP_TRY(launch_gemm(h, ws.attn, Mcap, L.w_out, ws.x, true, ACT_NONE, M, W, W, W, L.b_out, ws.x, W, nullptr, 0, st));
-      ARP_TRY(launch_ln_bf16(h, ws.x, L.ln2_g, L.ln2_b, ws.xn, M, st));
-    }
-    ARP_TRY(launch_gemm(h, ws.xn, Mcap, L.w_fc, ws.hid, false, ACT_QUICKGELU, M, 4 * W, W, 4 * W, L.b_fc, nullptr, 0,
-                        nullptr, 0, st));
-    if ((h->ln_fuse & 2) && l + 1 < c.layers) {
-      const LayerW& Ln = h->layers[l + 1];
-      const LnFuseArgs f1{Ln.ln1_g, Ln.ln1_b, ws.xn, ws.ln_cnt};
-      ARP_TRY(launch_gemm(h, ws.hid, Mcap, L.w_proj, ws.x, true, ACT_NONE, M, W, 4 * W, W, L.b_proj, ws.x, W, nullptr, 0,
-                          st, nullptr, &f1));
-      xn_ready = true;
-    } else {
-      ARP_TRY(launch_gemm(h, ws.hid, Mcap, L.w_proj, ws.x, true, ACT_NONE, M, W, 4 * W, W, L.b_proj, ws.x, W, nullptr,
-                          0, st));
-    }
-    if (h->adapter) {
-      gather_cls_bf16_kernel<768><<<(unsigned)((n + 7) / 8), 256, 0, st>>>(ws.x, ws.taps, (int)n, h->tokens,
-                                                                         c.layers * W, l * W);
-      h->launches++;
-    }
-    tap(ws.x, h->tokens, l);
-  }
+  ws.cls_compact = false;
+  ARP_TRY(h->resid16 ? encode_blocks_r16(h, n, st) : encode_blocks_r32(h, n, st));
   ARP_CUDA(h, cudaGetLastError());
   return ARP_OK;
 }
@@ -1193,10 +1108,10 @@ static int launch_sgemm(ArpHandle* h, const float* a, int lda, const void* w, fl
   return ARP_OK;
 }
 
-static int encode_chunk_f32(ArpHandle* h, int pipe, const uint8_t* ob, int64_t n, int64_t stride, cudaStream_t st) {
+static int encode_chunk_f32(ArpHandle* h, const uint8_t* ob, int64_t n, int64_t stride, cudaStream_t st) {
   const ArpConfig& c = h->cfg;
-  ArpHandle::Work& ws = h->ws[pipe];
-  ws.pruned = false;   // the verification path computes every row of every block
+  ArpHandle::Work& ws = h->ws;
+  ws.cls_compact = false;   // the verification path computes every row of every block
   const int W = c.width;
   const int64_t M = n * h->tokens;
   if (h->tokens != 197 && h->tokens != 50) return fail(h, ARP_ERR_INVALID, "unsupported token count %d", h->tokens);
@@ -1234,12 +1149,12 @@ static int encode_chunk_f32(ArpHandle* h, int pipe, const uint8_t* ob, int64_t n
     ARP_TRY(launch_sgemm(h, ws.hid32, 4 * W, L.w_proj, ws.x, W, F32_ACT_NONE, M, W, 4 * W, L.b_proj, ws.x, W, nullptr, 0,
                          st));
     if (h->adapter) {
-      gather_cls_f32_kernel<768><<<(unsigned)((n + 7) / 8), 256, 0, st>>>(ws.x, ws.taps32, (int)n, h->tokens,
+      gather_cls_rows_f32_kernel<768, float><<<(unsigned)((n + 7) / 8), 256, 0, st>>>(ws.x, ws.taps32, (int)n, h->tokens,
                                                                         c.layers * W, l * W);
       h->launches++;
     }
     if (h->cur_taps32) {
-      gather_cls_f32_kernel<768><<<(unsigned)((n + 7) / 8), 256, 0, st>>>(ws.x, h->cur_taps32, (int)n, h->tokens,
+      gather_cls_rows_f32_kernel<768, float><<<(unsigned)((n + 7) / 8), 256, 0, st>>>(ws.x, h->cur_taps32, (int)n, h->tokens,
                                                                         c.layers * W, l * W);
       h->launches++;
     }
@@ -1249,14 +1164,14 @@ static int encode_chunk_f32(ArpHandle* h, int pipe, const uint8_t* ob, int64_t n
 }
 
 // heads. reward_out [n] / logits_out [n, n_text] / feat_out [n, feat_dim] may each be null.
-static int head_chunk(ArpHandle* h, int pipe, int64_t n, float* reward_out, float* logits_out, float* feat_out,
+static int head_chunk(ArpHandle* h, int64_t n, float* reward_out, float* logits_out, float* feat_out,
                       cudaStream_t st) {
   const ArpConfig& c = h->cfg;
-  ArpHandle::Work& ws = h->ws[pipe];
+  ArpHandle::Work& ws = h->ws;
   const bool need_text = reward_out || logits_out;
   if (need_text && !h->goal && !h->text) return fail(h, ARP_ERR_STATE, "arp_set_text has not been called");
-  const float* xsrc = ws.pruned ? ws.xcls : ws.x;          // class-token rows: compact after last-layer pruning
-  const int xtok = ws.pruned ? 1 : h->tokens;
+  const float* xsrc = ws.cls_compact ? ws.xcls : ws.x;     // class-token rows: compact after last-layer pruning
+  const int xtok = ws.cls_compact ? 1 : h->tokens;
   if (!h->adapter) {
     ProfScope prof(h, PC_HEAD, 2.0 * (double)n * 768 * 512, (double)n * 768 * 4 + 768.0 * 512 * 4, st);
     clip_head_kernel<768, 512><<<(unsigned)((n + HEAD_FR - 1) / HEAD_FR), 256, HEAD_SMEM_BYTES, st>>>(
@@ -1352,19 +1267,6 @@ static int carve_label_tmp(ArpHandle* h, int64_t T, LabelTmp* t) {
   return ARP_OK;
 }
 
-// ---- chunk pipelining over the internal streams -------------------------------------------------------
-static int active_pipes(const ArpHandle* h, int64_t nchunks) { return (h->profiling || nchunks < 2) ? 1 : h->n_pipes; }
-static void pipes_fork(ArpHandle* h, cudaStream_t st, int np) {   // pipes start after everything queued on st
-  cudaEventRecord(h->ev_fork, st);
-  for (int p = 0; p < np; ++p) cudaStreamWaitEvent(h->pipe_stream[p], h->ev_fork, 0);
-}
-static void pipes_join(ArpHandle* h, cudaStream_t st, int np) {   // st continues after both pipes drain
-  for (int p = 0; p < np; ++p) {
-    cudaEventRecord(h->ev_join[p], h->pipe_stream[p]);
-    cudaStreamWaitEvent(st, h->ev_join[p], 0);
-  }
-}
-
 static int check_ready(ArpHandle* h, const void* ob, int64_t T, int64_t stride, cudaStream_t st) {
   if (!h) return ARP_ERR_INVALID;
   if (T < 0 || (T > 0 && !ob)) return fail(h, ARP_ERR_INVALID, "bad frame buffer / T");
@@ -1382,18 +1284,12 @@ extern "C" int arp_compute_reward(ArpHandle* h, const uint8_t* ob_dev, int64_t T
   ARP_TRY(check_ready(h, ob_dev, T, row_stride_bytes, st));
   if (h->goal) return fail(h, ARP_ERR_INVALID, "goal-conditioned heads need episode boundaries: use arp_label");
   const int64_t B = h->cfg.max_batch;
-  const int np = active_pipes(h, (T + B - 1) / B);
-  if (np > 1) pipes_fork(h, st, np);
-  int64_t ci = 0;
-  for (int64_t t0 = 0; t0 < T; t0 += B, ++ci) {
+  for (int64_t t0 = 0; t0 < T; t0 += B) {
     const int64_t n = std::min(B, T - t0);
-    const int p = np > 1 ? (int)(ci % np) : 0;
-    cudaStream_t ps = np > 1 ? h->pipe_stream[p] : st;
-    ARP_TRY(encode_chunk(h, p, ob_dev + t0 * row_stride_bytes, n, row_stride_bytes, ps));
-    ARP_TRY(head_chunk(h, p, n, reward_dev ? reward_dev + t0 : nullptr,
-                       logits_dev ? logits_dev + t0 * h->n_text : nullptr, nullptr, ps));
+    ARP_TRY(encode_chunk(h, ob_dev + t0 * row_stride_bytes, n, row_stride_bytes, st));
+    ARP_TRY(head_chunk(h, n, reward_dev ? reward_dev + t0 : nullptr,
+                       logits_dev ? logits_dev + t0 * h->n_text : nullptr, nullptr, st));
   }
-  if (np > 1) pipes_join(h, st, np);
   return ARP_OK;
 }
 
@@ -1403,17 +1299,11 @@ extern "C" int arp_encode_image(ArpHandle* h, const uint8_t* ob_dev, int64_t T, 
   ARP_TRY(check_ready(h, ob_dev, T, row_stride_bytes, st));
   if (!feat_dev) return fail(h, ARP_ERR_INVALID, "null output");
   const int64_t B = h->cfg.max_batch;
-  const int np = active_pipes(h, (T + B - 1) / B);
-  if (np > 1) pipes_fork(h, st, np);
-  int64_t ci = 0;
-  for (int64_t t0 = 0; t0 < T; t0 += B, ++ci) {
+  for (int64_t t0 = 0; t0 < T; t0 += B) {
     const int64_t n = std::min(B, T - t0);
-    const int p = np > 1 ? (int)(ci % np) : 0;
-    cudaStream_t ps = np > 1 ? h->pipe_stream[p] : st;
-    ARP_TRY(encode_chunk(h, p, ob_dev + t0 * row_stride_bytes, n, row_stride_bytes, ps));
-    ARP_TRY(head_chunk(h, p, n, nullptr, nullptr, feat_dev + t0 * h->feat_dim, ps));
+    ARP_TRY(encode_chunk(h, ob_dev + t0 * row_stride_bytes, n, row_stride_bytes, st));
+    ARP_TRY(head_chunk(h, n, nullptr, nullptr, feat_dev + t0 * h->feat_dim, st));
   }
-  if (np > 1) pipes_join(h, st, np);
   if (h->adapter && T > 0) {
     l2_normalize_rows_kernel<<<(unsigned)((T + 7) / 8), 256, 0, st>>>(feat_dev, h->feat_dim, T);
     h->launches++;
@@ -1436,8 +1326,8 @@ extern "C" int arp_encode_taps_chw(ArpHandle* h, const float* chw_dev, int64_t T
     const int64_t n = std::min(B, T - t0);
     h->cur_chw = chw_dev + t0 * img;
     h->cur_taps32 = taps_dev ? taps_dev + t0 * tw : nullptr;
-    rc = encode_chunk(h, 0, nullptr, n, 0, st);
-    if (rc == ARP_OK && feat_dev) rc = head_chunk(h, 0, n, nullptr, nullptr, feat_dev + t0 * h->feat_dim, st);
+    rc = encode_chunk(h, nullptr, n, 0, st);
+    if (rc == ARP_OK && feat_dev) rc = head_chunk(h, n, nullptr, nullptr, feat_dev + t0 * h->feat_dim, st);
   }
   h->cur_chw = nullptr;
   h->cur_taps32 = nullptr;
@@ -1506,18 +1396,12 @@ static int label_device(ArpHandle* h, const uint8_t* ob_dev, int64_t T, int64_t 
   float* r = reward ? reward : tmp.r;
   float* g = rtg ? rtg : tmp.g;
   const int64_t B = h->cfg.max_batch;
-  const int np = active_pipes(h, (T + B - 1) / B);
-  if (np > 1) pipes_fork(h, st, np);
-  int64_t ci = 0;
-  for (int64_t t0 = 0; t0 < T; t0 += B, ++ci) {
+  for (int64_t t0 = 0; t0 < T; t0 += B) {
     const int64_t n = std::min(B, T - t0);
-    const int p = np > 1 ? (int)(ci % np) : 0;
-    cudaStream_t ps = np > 1 ? h->pipe_stream[p] : st;
-    ARP_TRY(encode_chunk(h, p, ob_dev + t0 * stride, n, stride, ps));
-    if (!h->goal) ARP_TRY(head_chunk(h, p, n, r + t0, nullptr, nullptr, ps));
-    else ARP_TRY(head_chunk(h, p, n, nullptr, nullptr, tmp.feats + t0 * h->feat_dim, ps));
+    ARP_TRY(encode_chunk(h, ob_dev + t0 * stride, n, stride, st));
+    if (!h->goal) ARP_TRY(head_chunk(h, n, r + t0, nullptr, nullptr, st));
+    else ARP_TRY(head_chunk(h, n, nullptr, nullptr, tmp.feats + t0 * h->feat_dim, st));
   }
-  if (np > 1) pipes_join(h, st, np);
   if (h->goal) ARP_TRY(goal_rewards(h, tmp, T, ep_off, n_eps, r, st));
   return scan_launch(h, r, T, ep_off, n_eps, F, 1.0f, g, rs, gs, st);
 }
@@ -1562,13 +1446,10 @@ extern "C" int arp_label_host(ArpHandle* h, const uint8_t* ob_host, int64_t T, i
   ARP_CUDA(h, cudaMemcpyAsync(d_off, ep_offsets_host, (size_t)(n_eps + 1) * 8, cudaMemcpyHostToDevice, st));
   // double-buffered: chunk i+1's frames (only the scored image of each row) cross PCIe while chunk i is encoded
   const int64_t nchunks = (T + B - 1) / B;
-  const int np = active_pipes(h, nchunks);
-  if (np > 1) pipes_fork(h, st, np);
   int rc = ARP_OK;
   for (int64_t ci = 0; ci < nchunks && rc == ARP_OK; ++ci) {
     const int buf = (int)(ci & 1);
-    const int p = np > 1 ? buf : 0;
-    cudaStream_t ps = np > 1 ? h->pipe_stream[p] : st;
+    cudaStream_t ps = st;
     const int64_t t0 = ci * B, n = std::min(B, T - t0);
     if (ci >= 2) cudaStreamWaitEvent(h->copy_stream, h->ev_consumed[buf], 0);
     cudaError_t e = cudaMemcpy2DAsync(h->stage_dev[buf], frame_bytes, ob_host + t0 * row_stride_bytes,
@@ -1577,12 +1458,11 @@ extern "C" int arp_label_host(ArpHandle* h, const uint8_t* ob_host, int64_t T, i
     if (e != cudaSuccess) { rc = fail(h, ARP_ERR_CUDA, "H2D frames failed: %s", cudaGetErrorString(e)); break; }
     cudaEventRecord(h->ev_copied[buf], h->copy_stream);
     cudaStreamWaitEvent(ps, h->ev_copied[buf], 0);
-    if ((rc = encode_chunk(h, p, h->stage_dev[buf], n, (int64_t)frame_bytes, ps)) != ARP_OK) break;
-    if (!h->goal) rc = head_chunk(h, p, n, d_r + t0, nullptr, nullptr, ps);
-    else rc = head_chunk(h, p, n, nullptr, nullptr, tmp.feats + t0 * h->feat_dim, ps);
+    if ((rc = encode_chunk(h, h->stage_dev[buf], n, (int64_t)frame_bytes, ps)) != ARP_OK) break;
+    if (!h->goal) rc = head_chunk(h, n, d_r + t0, nullptr, nullptr, ps);
+    else rc = head_chunk(h, n, nullptr, nullptr, tmp.feats + t0 * h->feat_dim, ps);
     cudaEventRecord(h->ev_consumed[buf], ps);
   }
-  if (np > 1) pipes_join(h, st, np);
   if (rc == ARP_OK && h->goal) rc = goal_rewards(h, tmp, T, d_off, n_eps, d_r, st);
   if (rc == ARP_OK) rc = scan_launch(h, d_r, T, d_off, n_eps, F, 1.0f, d_g, d_rs, d_gs, st);
   if (rc == ARP_OK) {
@@ -1594,7 +1474,7 @@ extern "C" int arp_label_host(ArpHandle* h, const uint8_t* ob_host, int64_t T, i
     if (e == cudaSuccess) e = cudaStreamSynchronize(st);
     if (e != cudaSuccess) rc = fail(h, ARP_ERR_CUDA, "label_host tail failed: %s", cudaGetErrorString(e));
   }
-  if (rc != ARP_OK) cudaDeviceSynchronize();   // error path: drain the pipes before the caller frees anything
+  if (rc != ARP_OK) cudaDeviceSynchronize();   // error path: drain the device before the caller frees anything
   cudaStreamSynchronize(h->copy_stream);
   cudaStreamSynchronize(st);
   return rc;
@@ -1712,8 +1592,8 @@ extern "C" int arp_online_reward(ArpHandle* h, const uint8_t* ob_host, int32_t n
   float* d_lg = d_r + c.max_batch;
   float* d_f = d_lg + (size_t)c.max_batch * HEAD_MAX_TEXT;
   auto run = [&]() -> int {
-    ARP_TRY(encode_chunk(h, 0, h->stage_dev[0], n, (int64_t)frame_bytes, st));
-    ARP_TRY(head_chunk(h, 0, n, text_head ? d_r : nullptr, text_head ? d_lg : nullptr, d_f, st));
+    ARP_TRY(encode_chunk(h, h->stage_dev[0], n, (int64_t)frame_bytes, st));
+    ARP_TRY(head_chunk(h, n, text_head ? d_r : nullptr, text_head ? d_lg : nullptr, d_f, st));
     if (h->adapter) {
       l2_normalize_rows_kernel<<<(unsigned)((n + 7) / 8), 256, 0, st>>>(d_f, h->feat_dim, n);
       h->launches++;
@@ -1762,7 +1642,7 @@ extern "C" int arp_decode_only(ArpHandle* h, const uint8_t* ob_dev, int64_t T, i
 }
 
 extern "C" int arp_gemm_bf16(ArpHandle* h, const void* a_dev, const void* w_dev, void* out_dev, int32_t out_dtype,
-                             int64_t M, int32_t N, int32_t K, const float* bias_dev, const float* resid_dev,
+                             int64_t M, int32_t N, int32_t K, const float* bias_dev, const void* resid_dev,
                              int32_t act, void* stream) {
   if (!h || !a_dev || !w_dev || !out_dev) return fail(h, ARP_ERR_INVALID, "null argument");
   if (act < 0 || act > 2 || (out_dtype != ARP_F32 && out_dtype != ARP_OP_DTYPE)) return fail(h, ARP_ERR_INVALID, "bad act / out_dtype");
@@ -1770,6 +1650,36 @@ extern "C" int arp_gemm_bf16(ArpHandle* h, const void* a_dev, const void* w_dev,
   return launch_gemm(h, static_cast<const bf16*>(a_dev), M, static_cast<const bf16*>(w_dev), out_dev,
                      out_dtype == ARP_F32, act, M, N, K, N, bias_dev, resid_dev, N, nullptr, 0,
                      static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int arp_ln_gemm(ArpHandle* h, const void* x_dev, const float* gamma_dev, const float* beta_dev,
+                           const float* w_f32_dev, const float* bias_dev, void* out_dev, int64_t M, int32_t N,
+                           int32_t act, void* stream) {
+  if (!h || !x_dev || !gamma_dev || !beta_dev || !w_f32_dev || !bias_dev || !out_dev) return fail(h, ARP_ERR_INVALID, "null argument");
+  if (act != ACT_NONE && act != ACT_QUICKGELU) return fail(h, ARP_ERR_INVALID, "bad act");
+  if (M < 1 || N < 256 || N % 256) return fail(h, ARP_ERR_INVALID, "bad M / N");
+  ARP_CUDA(h, cudaSetDevice(h->cfg.device));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int K = 768;
+  uint8_t* tmp = nullptr;
+  const size_t b_w = (size_t)N * K * sizeof(bf16), b_v = (size_t)N * 4, b_s = (size_t)M * sizeof(float2);
+  auto al = [](size_t b) { return (b + 255) & ~static_cast<size_t>(255); };
+  ARP_CUDA(h, cudaMalloc((void**)&tmp, al(b_w) + 2 * al(b_v) + al(b_s)));
+  bf16* wf = reinterpret_cast<bf16*>(tmp);
+  float* svec = reinterpret_cast<float*>(tmp + al(b_w));
+  float* cvec = reinterpret_cast<float*>(tmp + al(b_w) + al(b_v));
+  float2* stats = reinterpret_cast<float2*>(tmp + al(b_w) + 2 * al(b_v));
+  fold_ln_weights_kernel<<<(N + 7) / 8, 256, 0, st>>>(w_f32_dev, gamma_dev, beta_dev, bias_dev, wf, svec, cvec, N, K);
+  h->launches++;
+  int rc = launch_row_moments(h, static_cast<const bf16*>(x_dev), stats, M, st);
+  const LnFoldArgs f{stats, svec, cvec};
+  if (rc == ARP_OK)
+    rc = launch_gemm(h, static_cast<const bf16*>(x_dev), M, wf, out_dev, false, act, M, N, K, N, nullptr, nullptr, 0,
+                     nullptr, 0, st, &f);
+  cudaStreamSynchronize(st);
+  h->tmaps.clear();          // descriptors of the freed temporaries must not be served from the cache
+  cudaFree(tmp);
+  return rc;
 }
 
 extern "C" int arp_layernorm_bf16(ArpHandle* h, const float* x_dev, const float* gamma_dev, const float* beta_dev,

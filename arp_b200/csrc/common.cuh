@@ -55,13 +55,14 @@ __device__ __forceinline__ float warp_max(float v) {
 }
 
 // ----------------------------------------------------------------------------
-// The 16-bit OPERAND format of every contraction (GEMM A / W, Q K V, attention output, MLP hidden): bf16 by default,
-// fp16 with -DARP_OP_FP16=1. tcgen05 kind::f16 runs both at the same rate with fp32 accumulation; fp16 carries three more
-// mantissa bits (tools/precision_study.py: max |dcos| 4.5e-5 against 3.8e-4) at the range the reference's own CUDA path
-// uses (clip.load keeps fp16 weights). Everything below names the format only through these.
+// The 16-bit OPERAND format of every contraction (GEMM A / W, Q K V, attention output, MLP hidden) and of the residual
+// stream: fp16 by default, bf16 with -DARP_OP_FP16=0. tcgen05 kind::f16 runs both at the same rate with fp32
+// accumulation; fp16 carries three more mantissa bits (tools/precision_study.py: max |dcos| 4.5e-5 against 3.8e-4) at the
+// range the reference's own CUDA path uses (clip.load keeps fp16 weights and activations). Everything below names the
+// format only through these ("bf16" in older identifiers reads "the operand format").
 // ----------------------------------------------------------------------------
 #ifndef ARP_OP_FP16
-#define ARP_OP_FP16 0
+#define ARP_OP_FP16 1
 #endif
 #if ARP_OP_FP16
 using op_t = __half;

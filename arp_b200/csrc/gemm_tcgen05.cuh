@@ -1,17 +1,25 @@
-// Persistent warp-specialised bf16 GEMM on the 5th-gen tensor cores:
-//   C[M,N] = epilogue( A[M,K] · W[N,K]^T )        (A, W bf16 K-major; fp32 accumulate in TMEM)
+// Persistent warp-specialised 16-bit GEMM on the 5th-gen tensor cores:
+//   C[M,N] = epilogue( A[M,K] · W[N,K]^T )        (A, W in the operand format op_t, K-major; fp32 accumulate in TMEM)
 //
-// This is the one dense-contraction kernel behind every linear layer on the
-// reward-labeling path (SURVEY.md §2 K2,K4,K6,K7,K8,K10; reference call sites:
-// openai/CLIP VisionTransformer / ResidualAttentionBlock as invoked from
+// The one dense-contraction kernel behind every linear layer on the reward-labeling path (SURVEY.md §2
+// K2,K4,K6,K7,K8,K10; reference call sites: openai/CLIP VisionTransformer / ResidualAttentionBlock as invoked from
 // arp_dt/label_reward.py:141 and finetune_module/clip_multiscale_adapter.py:135-151).
 //
-// Structure (one CTA per SM, 192 threads):
-//   warp 0      TMA producer     cp.async.bulk.tensor A[128x64], W[256x64] tiles, SW128, 4-stage mbarrier ring
-//   warp 1      MMA issuer       tcgen05.mma.cta_group::1.kind::f16, M=128 N=256 K=16, one elected lane
-//   warps 2..5  epilogue         tcgen05.ld 32x32b.x32 -> bias / periodic row table / residual / activation -> HBM
-// Two 256-column accumulator stages in TMEM (all 512 columns) let the epilogue
-// of tile i drain while tile i+1 is being multiplied.
+//   * CTA pairs (CG = 2): tcgen05.mma.cta_group::2 with M = 256 across the two SMs of a cluster, each CTA staging
+//     its own 128 A rows and half of the W tile — halves shared-memory and L2 traffic for the B operand.
+//   * warp roles (320 threads): 0 = TMA producer (6-stage mbarrier ring), 1 = MMA issuer + TMEM owner,
+//     2..9 = epilogue (warp w reads TMEM lane quarter w%4; warps 2-5 take accumulator columns 0-127, 6-9 columns
+//     128-255). Two 256-column accumulator stages in TMEM: tile i drains while tile i+1 is multiplied.
+//   * the epilogue never issues an uncoalesced global access: 32x128-byte sub-tiles go TMEM -> registers (bias /
+//     periodic row table / LayerNorm fold / activation) -> 128B-swizzled shared memory -> TMA store, or
+//   * G2_REDUCE: the residual stream is updated by TMA reduce-add (cp.reduce.async.bulk.tensor .add, performed at
+//     L2): x += tile without ever reading x into the SM. Works on the fp32 stream (precision mode 2, and the
+//     class-token rows of the pruned last block) and on the 16-bit stream of the default path
+//     (x = fl16(x + fl16(acc + bias)) — the same two roundings the reference's own fp16 CUDA route performs).
+//   * G2_LNFOLD: LayerNorm applied algebraically. A is the RAW residual stream, W' = W·diag(gamma), and
+//       LN(x) W^T + b = rstd_r · acc − rstd_r·mean_r · svec_n + cvec_n,   svec = W'·1,  cvec = W·beta + b,
+//     with (rstd_r, −mean_r·rstd_r) read per row from `ln_stats` (row_moments kernels, layernorm.cuh). No
+//     normalised copy of x is ever written: LayerNorm costs one float2 per row.
 #pragma once
 
 #include "common.cuh"
@@ -19,70 +27,74 @@
 namespace arp {
 
 enum GemmAct : int { ACT_NONE = 0, ACT_QUICKGELU = 1, ACT_RELU = 2 };
+enum G2Mode : int { G2_STORE = 0, G2_REDUCE = 1, G2_LNFOLD = 2 };
 
 struct GemmArgs {
   int M, N, K;
-  void* out;            // [M, ldo] bf16 or fp32
-  int ldo;              // elements
-  const float* bias;    // [N] or nullptr
-  const float* resid;   // fp32 [M, ldr] or nullptr; may alias out (in-place residual stream)
-  int ldr;
-  const float* rowtab;  // fp32 [period, N] added to row (row % period), or nullptr (pos-emb + cls)
+  void* out;               // [M, ldo] op_t or fp32 (addressed through tmap_out; kept for diagnostics)
+  int ldo;                 // elements
+  const float* bias;       // [N] or nullptr
+  const float* rowtab;     // fp32 [period, N] added to row (row % period), or nullptr (pos-emb + cls)
   int period;
-  // ---- LayerNorm fused behind the residual GEMM (gemm2 MODE 1 only; all null = off) ----
-  // After a CTA's TMA reduce-adds of a tile have completed it bumps ln_cnt[row block of 128]; the CTA that brings the
-  // count to N/256 (every column tile of those rows is in) normalises the 128 rows right there — they are still in
-  // L2 — and writes ln_out (bf16 [M, N]) = LN(out rows; ln_gamma, ln_beta). Replaces a standalone LayerNorm kernel
-  // that re-read the whole fp32 residual stream from HBM.
-  const float* ln_gamma;
-  const float* ln_beta;
-  op_t* ln_out;
-  int* ln_cnt;          // [ceil(M/128)] zeroed before the launch
-  int reverse;          // gemm2: walk the tiles from the last row block to the first (snake order across kernels,
-                        // so a kernel starts on the rows its predecessor wrote last — still in L2)
-  // ---- LayerNorm fold (gemm2 MODE 2 / 3) ----
-  // MODE 2 (residual + LN statistics): x = resid + acc + bias is written to `out` (fp32, may alias resid), a bf16
-  //   copy to `xb` [M, N], and per-row partial moments (sum, sum of squares over each 128-column span) to
-  //   `stats_out` [M, 2*N/128]. Every partial is written by exactly one warp: no atomics, deterministic.
-  // MODE 3 (LN applied algebraically): A was the RAW bf16 residual stream and W' = W*diag(gamma), so
-  //   LN(x) W^T + bias = rstd_r * (acc - mean_r * svec_n) + cvec_n with svec = W' 1, cvec = W beta + bias;
-  //   mean_r / rstd_r come from `stats_in` [M, 2*stats_nh] (moments over K = 128*stats_nh columns).
-  op_t* xb;
-  float* stats_out;
-  const float* stats_in;
-  int stats_nh;
-  const float* svec;
-  const float* cvec;
-  float eps;
+  int reverse;             // walk the tiles from the last row block to the first (snake order across kernels, so a
+                           // kernel starts on the rows its predecessor wrote last — still in L2)
+  const float2* ln_stats;  // G2_LNFOLD: [M] (rstd, -mean*rstd) of the rows of A
+  const float* svec;       // G2_LNFOLD: [N]
+  const float* cvec;       // G2_LNFOLD: [N]
 };
 
 constexpr int GEMM_BM = 128;
 constexpr int GEMM_BN = 256;
-constexpr int GEMM_BK = 64;  // 64 bf16 = one 128-byte swizzle atom
-constexpr int GEMM_STAGES = 4;
+constexpr int GEMM_BK = 64;  // 64 x 16-bit = one 128-byte swizzle atom
 constexpr int GEMM_A_BYTES = GEMM_BM * GEMM_BK * 2;  // 16 KB
-constexpr int GEMM_B_BYTES = GEMM_BN * GEMM_BK * 2;  // 32 KB
-constexpr int GEMM_STAGE_BYTES = GEMM_A_BYTES + GEMM_B_BYTES;
-constexpr int GEMM_THREADS = 192;
-constexpr int GEMM_SMEM_BYTES = GEMM_STAGES * GEMM_STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
 
-template <typename OutT, int ACT>
-__global__ void __launch_bounds__(GEMM_THREADS, 1)
-gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
-                         const GemmArgs args) {
+// QuickGELU x*sigmoid(1.702x) with ONE MUFU op: sigmoid(z) = 0.5 + 0.5*tanh(z/2)  ->  h + h*tanh(0.851x), h = x/2.
+// tanh.approx.f32 has ~2^-11 relative error, at the rounding of the 16-bit store that follows.
+__device__ __forceinline__ float quick_gelu(float x) {
+  float t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(0.851f * x));
+  const float h = 0.5f * x;
+  return fmaf(h, t, h);
+}
+
+constexpr int G2_THREADS = 320;
+constexpr int G2_EPI_WARPS = 8;
+constexpr int G2_STAGE_UNIT = 32 * 128;  // one staging buffer: 32 rows x 128 B
+constexpr int G2_STAGING_BYTES = G2_EPI_WARPS * G2_STAGE_UNIT;
+
+template <int CG>
+struct G2Cfg {
+  static constexpr int B_ROWS = GEMM_BN / CG;                       // W rows staged per CTA
+  static constexpr int STAGE_BYTES = GEMM_A_BYTES + B_ROWS * GEMM_BK * 2;
+  static constexpr int STAGES = CG == 1 ? 3 : 6;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + G2_STAGING_BYTES + 1024 + 256;
+};
+
+template <typename OutT, int ACT, int CG, int MODE>
+__global__ void __launch_bounds__(G2_THREADS, 1)
+gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                    const __grid_constant__ CUtensorMap tmap_out, const GemmArgs args) {
+  using Cfg = G2Cfg<CG>;
+  constexpr int STAGES = Cfg::STAGES;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + GEMM_STAGES * GEMM_STAGE_BYTES);
-  uint64_t* full_bar = bars;                       // [STAGES]  TMA -> MMA
-  uint64_t* empty_bar = bars + GEMM_STAGES;        // [STAGES]  MMA -> TMA
-  uint64_t* tfull_bar = bars + 2 * GEMM_STAGES;    // [2]       MMA -> epilogue
-  uint64_t* tempty_bar = tfull_bar + 2;            // [2]       epilogue -> MMA
+  uint8_t* staging = smem + STAGES * Cfg::STAGE_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(staging + G2_STAGING_BYTES);
+  uint64_t* full_bar = bars;
+  uint64_t* empty_bar = bars + STAGES;
+  uint64_t* tfull_bar = bars + 2 * STAGES;
+  uint64_t* tempty_bar = tfull_bar + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
 
-  const int warp = threadIdx.x >> 5;
+  // warp index through a shuffle: provably warp-uniform, so the MMA / TMA issue paths keep their descriptors in
+  // uniform registers (back-to-back UTCHMMA instead of an ELECT / R2UR.BROADCAST loop before every instruction)
+  const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0);
   const int lane = threadIdx.x & 31;
+  const uint32_t rank = CG == 2 ? cluster_ctarank() : 0;
+  const int cluster_id = blockIdx.x / CG;
+  const int num_clusters = gridDim.x / CG;
 
-  const int num_m = (args.M + GEMM_BM - 1) / GEMM_BM;
+  const int num_m = (args.M + GEMM_BM * CG - 1) / (GEMM_BM * CG);
   const int num_n = args.N / GEMM_BN;
   const int num_tiles = num_m * num_n;
   const int num_kb = args.K / GEMM_BK;
@@ -90,152 +102,215 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_a);
     tma_prefetch_desc(&tmap_b);
+    tma_prefetch_desc(&tmap_out);
   }
   if (warp == 1 && lane == 0) {
-    for (int i = 0; i < GEMM_STAGES; ++i) {
+    for (int i = 0; i < STAGES; ++i) {
       mbar_init(&full_bar[i], 1);
       mbar_init(&empty_bar[i], 1);
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull_bar[i], 1);
-      mbar_init(&tempty_bar[i], 128);
+      mbar_init(&tempty_bar[i], G2_EPI_WARPS * CG);
     }
     fence_mbar_init();
   }
-  if (warp == 2) tmem_alloc<512>(tmem_slot);
+  if (warp == 1) {
+    if (CG == 1) tmem_alloc<512>(tmem_slot); else tmem_alloc_cg2<512>(tmem_slot);
+  }
   tc_fence_before();
-  __syncthreads();
+  if (CG == 2) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
 
   if (warp == 0) {
-    // ===================== TMA producer =====================
-    int stage = 0;
-    uint32_t phase = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      const int m_blk = tile / num_n, n_blk = tile % num_n;
-      for (int kb = 0; kb < num_kb; ++kb) {
-        mbar_wait(&empty_bar[stage], phase ^ 1);
-        if (lane == 0) {
-          uint8_t* sa = smem + stage * GEMM_STAGE_BYTES;
+    // ===================== TMA producer (every CTA loads its own A rows and its share of W) =====================
+    // One elected thread runs the whole loop (no per-iteration ELECT / __syncwarp; the other lanes park at the final
+    // barrier and cost no issue slots).
+    if (elect_one()) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+        const int tile_o = args.reverse ? num_tiles - 1 - tile : tile;
+        const int m_blk = tile_o / num_n, n_blk = tile_o % num_n;
+        const int a_row = (m_blk * CG + rank) * GEMM_BM;
+        const int b_row = n_blk * GEMM_BN + rank * Cfg::B_ROWS;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
           uint8_t* sb = sa + GEMM_A_BYTES;
-          mbar_arrive_expect_tx(&full_bar[stage], GEMM_STAGE_BYTES);
-          tma_load_2d(sa, &tmap_a, &full_bar[stage], kb * GEMM_BK, m_blk * GEMM_BM);
-          tma_load_2d(sb, &tmap_b, &full_bar[stage], kb * GEMM_BK, n_blk * GEMM_BN);
+          if (CG == 1) {
+            mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
+            tma_load_2d(sa, &tmap_a, &full_bar[stage], kb * GEMM_BK, a_row);
+            tma_load_2d(sb, &tmap_b, &full_bar[stage], kb * GEMM_BK, b_row);
+          } else {
+            // both CTAs' bytes are credited to the leader's barrier, which the leader arms for 2x the bytes
+            if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * Cfg::STAGE_BYTES);
+            const uint32_t leader_bar = mapa_u32(smem_u32(&full_bar[stage]), 0);
+            tma_load_2d_cg2(sa, &tmap_a, leader_bar, kb * GEMM_BK, a_row);
+            tma_load_2d_cg2(sb, &tmap_b, leader_bar, kb * GEMM_BK, b_row);
+          }
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
-        __syncwarp();
-        if (++stage == GEMM_STAGES) { stage = 0; phase ^= 1; }
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    constexpr uint32_t idesc = umma_idesc_bf16(GEMM_BM, GEMM_BN);
-    int stage = 0;
-    uint32_t phase = 0;
-    int acc = 0;
-    uint32_t acc_phase = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
-      tc_fence_after();
-      const uint32_t d_tmem = tmem_base + acc * GEMM_BN;
-      for (int kb = 0; kb < num_kb; ++kb) {
-        mbar_wait(&full_bar[stage], phase);
+    // ===================== MMA issuer (leader CTA of the pair only) =====================
+    if (rank == 0 && elect_one()) {   // a single thread waits, issues and commits
+      constexpr uint32_t idesc = umma_idesc_bf16(GEMM_BM * CG, GEMM_BN);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+        mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
         tc_fence_after();
-        if (lane == 0) {
-          const uint32_t sa = smem_u32(smem + stage * GEMM_STAGE_BYTES);
+        const uint32_t d_tmem = tmem_base + acc * GEMM_BN;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE_BYTES);
           const uint64_t da = umma_desc_kmajor_sw128(sa);
           const uint64_t db = umma_desc_kmajor_sw128(sa + GEMM_A_BYTES);
 #pragma unroll
           for (int k = 0; k < GEMM_BK / 16; ++k) {
-            // advance 16 elements (32 B) along K inside the swizzle atom: +2 in the >>4 address field
-            umma_bf16_ss(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+            if (CG == 1) umma_bf16_ss(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+            else umma_bf16_ss_cg2(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
           }
-          umma_commit(&empty_bar[stage]);  // smem slot reusable once these MMAs retire
-          if (kb == num_kb - 1) umma_commit(&tfull_bar[acc]);
+          if (CG == 1) {
+            umma_commit(&empty_bar[stage]);
+            if (kb == num_kb - 1) umma_commit(&tfull_bar[acc]);
+          } else {
+            umma_commit_cg2(&empty_bar[stage], 0b11);
+            if (kb == num_kb - 1) umma_commit_cg2(&tfull_bar[acc], 0b11);
+          }
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
-        __syncwarp();
-        if (++stage == GEMM_STAGES) { stage = 0; phase ^= 1; }
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
-      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
   } else {
-    // ===================== epilogue (warps 2..5) =====================
-    const int quarter = warp & 3;  // TMEM lane quarter this warp may read
+    // ===================== epilogue (warps 2..9) =====================
+    const int ew = warp - 2;
+    const int quarter = warp & 3;   // TMEM lane quarter this warp may touch
+    const int half = ew >> 2;       // accumulator column half
+    uint8_t* sbuf = staging + ew * G2_STAGE_UNIT;
+    constexpr int UNIT_COLS = sizeof(OutT) == 4 ? 32 : 64;   // 128 B per row
+    constexpr int UNITS = 128 / UNIT_COLS;
+    const uint32_t tempty_leader0 = CG == 2 ? mapa_u32(smem_u32(&tempty_bar[0]), 0) : 0;
+    const uint32_t tempty_leader1 = CG == 2 ? mapa_u32(smem_u32(&tempty_bar[1]), 0) : 0;
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      const int m_blk = tile / num_n, n_blk = tile % num_n;
+    const int sw = lane & 7;
+    for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+      const int tile_o = args.reverse ? num_tiles - 1 - tile : tile;
+      const int m_blk = tile_o / num_n, n_blk = tile_o % num_n;
+      const int row0 = (m_blk * CG + rank) * GEMM_BM + quarter * 32;
+      const int row = row0 + lane;
+      float ln_rstd = 1.f, ln_rm = 0.f;        // G2_LNFOLD: the row's 1/std and -mean/std (in flight under the MMAs)
+      if (MODE == G2_LNFOLD && row < args.M) {
+        const float2 p = __ldg(args.ln_stats + row);
+        ln_rstd = p.x;
+        ln_rm = p.y;
+      }
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
-      const int row = m_blk * GEMM_BM + quarter * 32 + lane;
-      const bool row_ok = row < args.M;
-      const uint32_t taddr = tmem_base + acc * GEMM_BN + (static_cast<uint32_t>(quarter * 32) << 16);
+      const uint32_t taddr = tmem_base + acc * GEMM_BN + half * 128 + (static_cast<uint32_t>(quarter * 32) << 16);
       const float* tab_row =
           args.rowtab ? args.rowtab + static_cast<size_t>(row % args.period) * args.N : nullptr;
-      const float* res_row = args.resid ? args.resid + static_cast<size_t>(row) * args.ldr : nullptr;
-      OutT* out_row = reinterpret_cast<OutT*>(args.out) + static_cast<size_t>(row) * args.ldo;
 #pragma unroll 1
-      for (int c = 0; c < GEMM_BN / 32; ++c) {
-        uint32_t r[32];
-        tmem_ld_32x32(taddr + c * 32, r);
-        tmem_ld_wait();
-        const int n0 = n_blk * GEMM_BN + c * 32;
-        if (row_ok) {
-          float v[32];
+      for (int u = 0; u < UNITS; ++u) {
+        const int n0 = n_blk * GEMM_BN + half * 128 + u * UNIT_COLS;
+        float v[UNIT_COLS];
+        {
+          uint32_t r[32];
+          tmem_ld_32x32(taddr + u * UNIT_COLS, r);
+          if (UNIT_COLS == 64) {
+            uint32_t r2[32];
+            tmem_ld_32x32(taddr + u * UNIT_COLS + 32, r2);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[(UNIT_COLS == 64 ? 32 : 0) + j] = __uint_as_float(r2[j]);
+          } else {
+            tmem_ld_wait();
+          }
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-          if (args.bias) {
-#pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              const float4 b = __ldg(reinterpret_cast<const float4*>(args.bias + n0 + j));
-              v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
-            }
-          }
-          if (tab_row) {
-#pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              const float4 b = __ldg(reinterpret_cast<const float4*>(tab_row + n0 + j));
-              v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
-            }
-          }
-          if (ACT == ACT_QUICKGELU) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = __fdividef(v[j], 1.0f + __expf(-1.702f * v[j]));
-          } else if (ACT == ACT_RELU) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.0f);
-          }
-          if (res_row) {
-#pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              const float4 b = *reinterpret_cast<const float4*>(res_row + n0 + j);
-              v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
-            }
-          }
-          if (sizeof(OutT) == 4) {
-            float4* o = reinterpret_cast<float4*>(reinterpret_cast<float*>(out_row) + n0);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) o[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-          } else {
-            uint4* o = reinterpret_cast<uint4*>(reinterpret_cast<op_t*>(out_row) + n0);
-#pragma unroll
-            for (int j = 0; j < 4; ++j)
-              o[j] = make_uint4(pack_op(v[8 * j], v[8 * j + 1]), pack_op(v[8 * j + 2], v[8 * j + 3]),
-                                pack_op(v[8 * j + 4], v[8 * j + 5]), pack_op(v[8 * j + 6], v[8 * j + 7]));
+        }
+        if (u == UNITS - 1) {
+          // all of this warp's accumulator columns are in registers: hand the TMEM stage back to the MMA warp
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) {
+            if (CG == 1) mbar_arrive_relaxed(&tempty_bar[acc]);
+            else mbar_arrive_cluster_relaxed(acc ? tempty_leader1 : tempty_leader0);
           }
         }
+        if (MODE == G2_LNFOLD) {
+#pragma unroll
+          for (int j = 0; j < UNIT_COLS; j += 4) {
+            const float4 sv = __ldg(reinterpret_cast<const float4*>(args.svec + n0 + j));
+            const float4 cv = __ldg(reinterpret_cast<const float4*>(args.cvec + n0 + j));
+            v[j] = fmaf(ln_rstd, v[j], fmaf(ln_rm, sv.x, cv.x));
+            v[j + 1] = fmaf(ln_rstd, v[j + 1], fmaf(ln_rm, sv.y, cv.y));
+            v[j + 2] = fmaf(ln_rstd, v[j + 2], fmaf(ln_rm, sv.z, cv.z));
+            v[j + 3] = fmaf(ln_rstd, v[j + 3], fmaf(ln_rm, sv.w, cv.w));
+          }
+        } else if (args.bias) {
+#pragma unroll
+          for (int j = 0; j < UNIT_COLS; j += 4) {
+            const float4 b = __ldg(reinterpret_cast<const float4*>(args.bias + n0 + j));
+            v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
+          }
+        }
+        if (tab_row) {
+#pragma unroll
+          for (int j = 0; j < UNIT_COLS; j += 4) {
+            const float4 b = __ldg(reinterpret_cast<const float4*>(tab_row + n0 + j));
+            v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
+          }
+        }
+        if (ACT == ACT_QUICKGELU) {
+#pragma unroll
+          for (int j = 0; j < UNIT_COLS; ++j) v[j] = quick_gelu(v[j]);
+        } else if (ACT == ACT_RELU) {
+#pragma unroll
+          for (int j = 0; j < UNIT_COLS; ++j) v[j] = fmaxf(v[j], 0.0f);
+        }
+        // the staging buffer was last read by the TMA store of the previous unit
+        if (lane == 0) tma_store_wait_read<0>();
+        __syncwarp();
+        uint4* srow = reinterpret_cast<uint4*>(sbuf + lane * 128);
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          uint4 q;
+          if (sizeof(OutT) == 4) {
+            q = make_uint4(__float_as_uint(v[4 * c]), __float_as_uint(v[4 * c + 1]), __float_as_uint(v[4 * c + 2]),
+                           __float_as_uint(v[4 * c + 3]));
+          } else {
+            q = make_uint4(pack_op(v[8 * c], v[8 * c + 1]), pack_op(v[8 * c + 2], v[8 * c + 3]),
+                           pack_op(v[8 * c + 4], v[8 * c + 5]), pack_op(v[8 * c + 6], v[8 * c + 7]));
+          }
+          srow[c ^ sw] = q;   // 128B swizzle: 16-byte chunk index XOR (row & 7)
+        }
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+          if (MODE == G2_REDUCE) tma_reduce_add_2d(&tmap_out, sbuf, n0, row0);
+          else tma_store_2d(&tmap_out, sbuf, n0, row0);
+          tma_store_commit();
+        }
       }
-      tc_fence_before();
-      mbar_arrive(&tempty_bar[acc]);
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
+    if (lane == 0) tma_store_wait_all<0>();
   }
 
   tc_fence_before();
-  __syncthreads();
-  if (warp == 2) {
+  if (CG == 2) cluster_sync_all(); else __syncthreads();
+  if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc<512>(tmem_base);
+    if (CG == 1) tmem_dealloc<512>(tmem_base); else tmem_dealloc_cg2<512>(tmem_base);
   }
 }
 

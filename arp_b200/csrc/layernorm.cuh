@@ -48,56 +48,6 @@ __device__ __forceinline__ void ln_row(const float* __restrict__ x, const float*
   }
 }
 
-// NB rows per warp at once, read with ld.global.cg: all NB*W/128 row loads are issued before the first reduction, so a
-// lone warp (the fused LayerNorm in the residual GEMM's epilogue has only 8 per SM) keeps NB rows of L2 latency in
-// flight. Same arithmetic, in the same order, as ln_row. rows [row0, row0+NB) clipped to M; y = bf16 [M, W].
-template <int W, int NB>
-__device__ __forceinline__ void ln_rows_cg_bf16(const float* __restrict__ x, int ldx, const float* __restrict__ gamma,
-                                                const float* __restrict__ beta, float eps, op_t* __restrict__ y,
-                                                int row0, int M) {
-  constexpr int KV = W / 128;
-  const int lane = threadIdx.x & 31;
-  float4 v[NB][KV];
-#pragma unroll
-  for (int r = 0; r < NB; ++r) {
-    const int row = min(row0 + r, M - 1);
-#pragma unroll
-    for (int i = 0; i < KV; ++i) v[r][i] = __ldcg(reinterpret_cast<const float4*>(x + static_cast<size_t>(row) * ldx) + i * 32 + lane);
-  }
-  float mean[NB], rstd[NB];
-#pragma unroll
-  for (int r = 0; r < NB; ++r) {
-    float s = 0.f;
-#pragma unroll
-    for (int i = 0; i < KV; ++i) s += (v[r][i].x + v[r][i].y) + (v[r][i].z + v[r][i].w);
-    mean[r] = warp_sum(s) * (1.0f / W);
-  }
-#pragma unroll
-  for (int r = 0; r < NB; ++r) {
-    float q = 0.f;
-#pragma unroll
-    for (int i = 0; i < KV; ++i) {
-      const float a = v[r][i].x - mean[r], b = v[r][i].y - mean[r], c = v[r][i].z - mean[r], d = v[r][i].w - mean[r];
-      q += (a * a + b * b) + (c * c + d * d);
-    }
-    rstd[r] = rsqrtf(warp_sum(q) * (1.0f / W) + eps);
-  }
-#pragma unroll
-  for (int i = 0; i < KV; ++i) {
-    const float4 g = __ldg(reinterpret_cast<const float4*>(gamma) + i * 32 + lane);
-    const float4 b = __ldg(reinterpret_cast<const float4*>(beta) + i * 32 + lane);
-#pragma unroll
-    for (int r = 0; r < NB; ++r) {
-      if (row0 + r < M) {
-        const float o0 = (v[r][i].x - mean[r]) * rstd[r] * g.x + b.x, o1 = (v[r][i].y - mean[r]) * rstd[r] * g.y + b.y;
-        const float o2 = (v[r][i].z - mean[r]) * rstd[r] * g.z + b.z, o3 = (v[r][i].w - mean[r]) * rstd[r] * g.w + b.w;
-        reinterpret_cast<uint2*>(y + static_cast<size_t>(row0 + r) * W)[i * 32 + lane] =
-            make_uint2(pack_op(o0, o1), pack_op(o2, o3));
-      }
-    }
-  }
-}
-
 // y(bf16)[M,W] = LN(x fp32 [M,W])                 (ln_1 / ln_2 feeding the QKV and c_fc GEMMs)
 template <int W>
 __global__ void __launch_bounds__(256)
@@ -131,29 +81,72 @@ layernorm_f32_inplace_kernel(float* __restrict__ x, const float* __restrict__ ga
   for (int i = 0; i < RowRegs<W>::kVec; ++i) reinterpret_cast<float4*>(xr)[i * 32 + lane] = r.v[i];
 }
 
-// ln_pre for the LayerNorm-folded pipeline: x = LN(x) in place (fp32), plus what the first resblock's folded
-// LN needs — a bf16 copy of the new x and per-row partial moments (sum, sum of squares) over each 128-column
-// span, in the same [M, 2*W/128] layout the residual GEMM epilogue writes (gemm2 MODE 2).
+// ---- 16-bit residual stream (the default path): LayerNorm is never materialised. The consumer GEMM multiplies the RAW
+// stream by gamma-folded weights and applies (rstd, -mean*rstd) per row in its epilogue (gemm_tcgen05.cuh G2_LNFOLD);
+// these kernels produce that float2 per row. Moments are taken of the ROUNDED 16-bit values — exactly what the tensor
+// core multiplies — two-pass (mean, then centred squares) with the row in registers.
+template <int W>
+__device__ __forceinline__ float2 row_stats_from_regs(const float (&v)[W / 32], float eps) {
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < W / 32; ++i) s += v[i];
+  const float mean = warp_sum(s) * (1.0f / W);
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < W / 32; ++i) {
+    const float d = v[i] - mean;
+    q = fmaf(d, d, q);
+  }
+  const float rstd = rsqrtf(warp_sum(q) * (1.0f / W) + eps);
+  return make_float2(rstd, -mean * rstd);
+}
+
+// stats[row] = (rstd, -mean*rstd) of x[row, :]   (x = 16-bit residual stream [M, W]); one warp per row, 16-byte loads
 template <int W>
 __global__ void __launch_bounds__(256)
-layernorm_pre_fold_kernel(float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
-                          op_t* __restrict__ xb, float* __restrict__ stats, int M, float eps) {
+row_moments_kernel(const op_t* __restrict__ x, float2* __restrict__ stats, int M, float eps, int reverse) {
+  static_assert(W % 256 == 0, "row width must be a multiple of 256");
+  int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= M) return;
+  if (reverse) row = M - 1 - row;
+  const int lane = threadIdx.x & 31;
+  const uint4* src = reinterpret_cast<const uint4*>(x + static_cast<size_t>(row) * W);
+  float v[W / 32];
+#pragma unroll
+  for (int i = 0; i < W / 256; ++i) {
+    const uint4 u = src[i * 32 + lane];
+    const op2_t* h2 = reinterpret_cast<const op2_t*>(&u);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      v[i * 8 + 2 * e] = op_to_float(h2[e].x);
+      v[i * 8 + 2 * e + 1] = op_to_float(h2[e].y);
+    }
+  }
+  const float2 st = row_stats_from_regs<W>(v, eps);
+  if (lane == 0) stats[row] = st;
+}
+
+// ln_pre of the 16-bit path: x16 = fl16(LN(x0 fp32)) and the first block's ln_1 statistics of x16.
+template <int W>
+__global__ void __launch_bounds__(256)
+layernorm_pre_r16_kernel(const float* __restrict__ x0, const float* __restrict__ gamma, const float* __restrict__ beta,
+                         op_t* __restrict__ x16, float2* __restrict__ stats, int M, float eps) {
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= M) return;
   const int lane = threadIdx.x & 31;
   RowRegs<W> r;
-  float* xr = x + static_cast<size_t>(row) * W;
-  ln_row<W>(xr, gamma, beta, eps, r);
-  uint2* ob = reinterpret_cast<uint2*>(xb + static_cast<size_t>(row) * W);
-  float2* st = reinterpret_cast<float2*>(stats) + static_cast<size_t>(row) * (W / 128);
+  ln_row<W>(x0 + static_cast<size_t>(row) * W, gamma, beta, eps, r);
+  uint2* out = reinterpret_cast<uint2*>(x16 + static_cast<size_t>(row) * W);
+  float v[W / 32];
 #pragma unroll
-  for (int i = 0; i < RowRegs<W>::kVec; ++i) {      // float4 i of lane l is column (i*32 + l)*4: span i = columns [128i, 128i+128)
-    reinterpret_cast<float4*>(xr)[i * 32 + lane] = r.v[i];
-    ob[i * 32 + lane] = make_uint2(pack_op(r.v[i].x, r.v[i].y), pack_op(r.v[i].z, r.v[i].w));
-    const float a = warp_sum((r.v[i].x + r.v[i].y) + (r.v[i].z + r.v[i].w));
-    const float b = warp_sum((r.v[i].x * r.v[i].x + r.v[i].y * r.v[i].y) + (r.v[i].z * r.v[i].z + r.v[i].w * r.v[i].w));
-    if (lane == 0) st[i] = make_float2(a, b);
+  for (int i = 0; i < RowRegs<W>::kVec; ++i) {
+    const op2_t a = floats_to_op2(r.v[i].x, r.v[i].y), b = floats_to_op2(r.v[i].z, r.v[i].w);
+    out[i * 32 + lane] = make_uint2(*reinterpret_cast<const uint32_t*>(&a), *reinterpret_cast<const uint32_t*>(&b));
+    v[4 * i] = op_to_float(a.x); v[4 * i + 1] = op_to_float(a.y);
+    v[4 * i + 2] = op_to_float(b.x); v[4 * i + 3] = op_to_float(b.y);
   }
+  const float2 st = row_stats_from_regs<W>(v, eps);
+  if (lane == 0) stats[row] = st;
 }
 
 // Weight preparation for the folded LayerNorm (run once per weight load), one warp per output row n:
@@ -185,33 +178,42 @@ fold_ln_weights_kernel(const float* __restrict__ Wt, const float* __restrict__ g
 // taps(bf16)[B, ld_taps] columns [layer*W, (layer+1)*W) = x[b*tokens + 0, :]
 // The CLS row of every resblock output; replaces the reference's forward hooks
 // (finetune_module/utils.py:6-18, clip_multiscale_adapter.py:138-143).
-template <int W>
+// four consecutive elements of a residual-stream row (fp32 or 16-bit) as floats
+__device__ __forceinline__ float4 load4_as_float(const float* p) { return *reinterpret_cast<const float4*>(p); }
+__device__ __forceinline__ float4 load4_as_float(const op_t* p) {
+  const uint2 u = *reinterpret_cast<const uint2*>(p);
+  const op2_t a = *reinterpret_cast<const op2_t*>(&u.x), b = *reinterpret_cast<const op2_t*>(&u.y);
+  return make_float4(op_to_float(a.x), op_to_float(a.y), op_to_float(b.x), op_to_float(b.y));
+}
+
+template <int W, typename XT>
 __global__ void __launch_bounds__(256)
-gather_cls_bf16_kernel(const float* __restrict__ x, op_t* __restrict__ taps, int B, int tokens,
+gather_cls_bf16_kernel(const XT* __restrict__ x, op_t* __restrict__ taps, int B, int tokens,
                        int ld_taps, int col0) {
   const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (b >= B) return;
   const int lane = threadIdx.x & 31;
-  const float4* src = reinterpret_cast<const float4*>(x + static_cast<size_t>(b) * tokens * W);
+  const XT* src = x + static_cast<size_t>(b) * tokens * W;
   uint2* dst = reinterpret_cast<uint2*>(taps + static_cast<size_t>(b) * ld_taps + col0);
 #pragma unroll
   for (int i = 0; i < W / 128; ++i) {
-    const float4 v = src[i * 32 + lane];
+    const float4 v = load4_as_float(src + (i * 32 + lane) * 4);
     dst[i * 32 + lane] = make_uint2(pack_op(v.x, v.y), pack_op(v.z, v.w));
   }
 }
 
-// xcls fp32 [B, W] = x[b*tokens, :]  — the class-token rows of the residual stream, compacted (last-layer pruning)
-template <int W>
+// dst fp32 [B, ld_dst] columns [col0, col0+W) = x[b*tokens, :]  — the class-token rows of the residual stream (fp32 or
+// 16-bit), compacted: the pruned last block and the heads (ld_dst = W), the fine-tuning taps (ld_dst = layers*W)
+template <int W, typename XT>
 __global__ void __launch_bounds__(256)
-gather_cls_rows_f32_kernel(const float* __restrict__ x, float* __restrict__ xcls, int B, int tokens) {
+gather_cls_rows_f32_kernel(const XT* __restrict__ x, float* __restrict__ dst, int B, int tokens, int ld_dst, int col0) {
   const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (b >= B) return;
   const int lane = threadIdx.x & 31;
-  const float4* src = reinterpret_cast<const float4*>(x + static_cast<size_t>(b) * tokens * W);
-  float4* dst = reinterpret_cast<float4*>(xcls + static_cast<size_t>(b) * W);
+  const XT* src = x + static_cast<size_t>(b) * tokens * W;
+  float4* out = reinterpret_cast<float4*>(dst + static_cast<size_t>(b) * ld_dst + col0);
 #pragma unroll
-  for (int i = 0; i < W / 128; ++i) dst[i * 32 + lane] = src[i * 32 + lane];
+  for (int i = 0; i < W / 128; ++i) out[i * 32 + lane] = load4_as_float(src + (i * 32 + lane) * 4);
 }
 
 // Attention for the CLASS-TOKEN query only (last resblock): one warp per (frame, head).

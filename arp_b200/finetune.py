@@ -56,7 +56,7 @@ class FrozenClip(nn.Module):
     `clip_model.`), has no `nn.Parameter`s (so `for p in model.clip_model.parameters(): p.requires_grad = False`
     is a no-op and the optimizer never sees CLIP), and evaluates the vision tower through the native library."""
 
-    def __init__(self, state_dict: dict, arch: str = "ViT-B/16", max_batch: int = 256, precision: str = "bf16"):
+    def __init__(self, state_dict: dict, arch: str = "ViT-B/16", max_batch: int = 256, precision: str = "16bit"):
         super().__init__()
         self.arch = arch
         self.patch, self.vision_width, self.vision_layers, self.embed_dim, self.text_width, self.text_layers = ARCH[arch][:6]
@@ -111,7 +111,8 @@ class FrozenClip(nn.Module):
                                "inputs to a CUDA device (there is no CPU fallback)")
         idx = device.index if device.index is not None else torch.cuda.current_device()
         if self._engine is None or self._engine.cfg.device != idx:
-            prec = {"bf16": capi.PREC_BF16, "fp32": capi.PREC_F32}[self._precision]
+            prec = {"16bit": capi.PREC_16BIT, "bf16": capi.PREC_16BIT, "fp16": capi.PREC_16BIT, "fp32resid": capi.PREC_F32RESID,
+                    "fp32": capi.PREC_F32}[self._precision]
             self._engine = capi.Engine(device=idx, patch=self.patch, in_h=224, in_w=224, preprocess=capi.PRE_BILINEAR,
                                        head=capi.HEAD_CLIP, max_batch=self._max_batch, layers=self.vision_layers,
                                        width=self.vision_width, heads=self.vision_width // 64,
@@ -163,7 +164,7 @@ class CLIPMultiscaleAdapter(nn.Module):
                  action_dim: int = 15, num_layers: int = 2, device: torch.device = None,
                  use_discrete_action: bool = False, use_vip_loss: bool = False, use_id_loss: bool = False,
                  lambda_id: float = 0.1, goal_conditioned: bool = False, *, clip_state_dict: dict = None,
-                 arch: str = "ViT-B/16", augmentation=None, max_batch: int = 256, precision: str = "bf16",
+                 arch: str = "ViT-B/16", augmentation=None, max_batch: int = 256, precision: str = "16bit",
                  init: str = "orthogonal"):
         super().__init__()
         self.model_path = model_path

@@ -23,9 +23,15 @@ Keyword-only extensions (all optional; defaults reproduce the reference):
     reduce           "first" (reference behaviour) or "mean" (envs/vl_reward.py semantics).
     max_batch        frames per device chunk.      slab_frames  frames per host slab.
     device           CUDA ordinal (default: LOCAL_RANK or 0).
-    precision        "bf16" (tensor-core product path) or "fp32" (verification path: every weight, activation and
-                     contraction in fp32, what the reference's CPU route computes; ~50x slower).
+    precision        "16bit" (default; "bf16"/"fp16" are accepted aliases): the tensor-core product path — 16-bit operands
+                     in the library's operand format (fp16 by default, the reference's own CUDA format), 16-bit residual
+                     stream, LayerNorm folded into the GEMMs. "fp32resid": same tensor-core kernels with an fp32 residual
+                     stream and standalone LayerNorm (~2x closer to fp32, ~10 % slower). "fp32": verification path, every
+                     weight, activation and contraction in fp32 (what the reference's CPU route computes; ~50x slower).
     distributed      shard episodes over torch.distributed ranks (default: on when a process group exists).
+    tokenizer        None: openai/CLIP's clip.tokenize (label_reward.py:136) — if the package is missing the call REFUSES
+                     unless ARP_ALLOW_STANDIN_TOKENIZER=1; "standin": the deterministic stand-in (random-init experiments
+                     only); or a callable(list[str]) -> int tensor [n, 77].
 """
 from __future__ import annotations
 
@@ -40,7 +46,7 @@ from .instructions import get_clip_instruct, get_clip_special_instruct
 from .sharding import gather_rows, partition_episodes
 from .store import open_store
 from .text_tower import adapter_text_embedding, clip_text_embedding
-from .tokenizer import tokenize
+from .tokenizer import resolve as resolve_tokenizer
 from .weights import load_checkpoint
 
 
@@ -106,6 +112,10 @@ def _resolve_clip_weights(clip_state_dict, arch: str) -> dict:
             "label_reward.py:126)") from e
 
 
+PRECISIONS = {"16bit": capi.PREC_16BIT, "bf16": capi.PREC_16BIT, "fp16": capi.PREC_16BIT,
+              "fp32resid": capi.PREC_F32RESID, "fp32": capi.PREC_F32}
+
+
 class RewardLabeler:
     """Model + cached instruction embedding on one GPU; label() scores slabs of episodes.
 
@@ -114,10 +124,10 @@ class RewardLabeler:
 
     def __init__(self, model_type: str, text, frame_hw: tuple[int, int], *, model_ckpt_dir=None,
                  clip_state_dict=None, arch: str = "ViT-B/16", use_crop: bool = False, reduce: str = "first",
-                 max_batch: int = 1024, device: int | None = None, precision: str = "bf16"):
+                 max_batch: int = 1024, device: int | None = None, precision: str = "16bit", tokenizer=None):
         head, pre = _head_for(model_type)
-        if precision not in ("bf16", "fp32"):
-            raise ValueError(f"precision must be 'bf16' or 'fp32', got {precision!r}")
+        if precision not in PRECISIONS:
+            raise ValueError(f"precision must be one of {sorted(PRECISIONS)}, got {precision!r}")
         adapter = head in (capi.HEAD_ADAPTER, capi.HEAD_ADAPTER_ENSEMBLE, capi.HEAD_ADAPTER_GOAL)
         if adapter:
             assert model_ckpt_dir is not None, "specify model_ckpt_dir"  # label_reward.py:174
@@ -129,7 +139,7 @@ class RewardLabeler:
                                   use_crop=bool(use_crop), preprocess=pre, head=head,
                                   reduce=capi.REDUCE_MEAN if reduce == "mean" else capi.REDUCE_FIRST,
                                   max_batch=max_batch,
-                                  precision=capi.PREC_F32 if precision == "fp32" else capi.PREC_BF16)
+                                  precision=PRECISIONS[precision])
         dev = self.engine.device
         if adapter:
             sd = load_checkpoint(model_ckpt_dir) if not isinstance(model_ckpt_dir, dict) else model_ckpt_dir
@@ -146,7 +156,7 @@ class RewardLabeler:
         self.goal = self.engine.goal
         if not self.goal:
             texts = list(text) if isinstance(text, (list, tuple)) else [text]
-            tokens = tokenize(texts)
+            tokens = resolve_tokenizer(tokenizer)(texts)
             if adapter:
                 emb, scale = adapter_text_embedding(sd, tokens, dev, ensemble=head == capi.HEAD_ADAPTER_ENSEMBLE)
             else:
@@ -233,7 +243,8 @@ def label_reward(
     slab_frames=16384,
     device=None,
     distributed=None,
-    precision="bf16",
+    precision="16bit",
+    tokenizer=None,
 ):
     image_keys = image_keys.split(", ")
     if data_path is None:
@@ -250,56 +261,80 @@ def label_reward(
     rank = dist.get_rank() if distributed else 0
     world = dist.get_world_size() if distributed else 1
 
-    g = open_store(data_path, "a" if rank == 0 else "r")
+    # Every rank READS through its own read-only handle; rank 0 reopens the container for writing only after all
+    # readers have closed (HDF5 file locking refuses a writer next to readers, and a reader next to the writer).
+    g = open_store(data_path, "r")
+    labeler = None
+    failure = None
+    results = {}
     try:
         len_data, num_frames, g_traj_idx = episode_index(g)  # num_frames comes from the file (Q4)
         n_eps = len(g_traj_idx) - 1
         off = np.minimum(np.asarray(g_traj_idx, dtype=np.int64), len_data)  # min(idx[i+1], len_data) (:267)
-        H, W = g[image_keys[0]].shape[-3:-1]
-        if use_crop:
-            print(f"image_size: {g[image_keys[0]].shape[-2]}")  # label_reward.py:104-105
-
-        labeler = RewardLabeler(model_type, text, (int(H), int(W)), model_ckpt_dir=model_ckpt_dir,
-                                clip_state_dict=clip_state_dict, arch=arch, use_crop=use_crop, reduce=reduce,
-                                max_batch=max_batch, device=device, precision=precision)
+        shards = partition_episodes(off, world)
+        e_lo, e_hi = shards[rank]
         target_keys = [f"{model_type}_reward", f"{model_type}_pos_rtg"]
         if inst_type != "none":
             target_keys = [f"{x}_{inst_type}" for x in target_keys]
-
-        shards = partition_episodes(off, world)
-        e_lo, e_hi = shards[rank]
-        for img_key in image_keys:
-            ds = g[img_key]
-            side = g.get(img_key + SIDECAR_SUFFIX)
-            if side is not None and (side.shape[0] != ds.shape[0] or tuple(side.shape[1:]) != tuple(ds.shape[2:])):
-                side = None                      # stale or foreign sidecar: fall back to the stacked dataset
-            parts_r, parts_g = [], []
-            for s_lo, s_hi in _slabs(off, e_lo, e_hi, slab_frames):
-                lo, hi = int(off[s_lo]), int(off[s_hi])
-                if hi <= lo:
-                    continue
-                r, _, rs, gs = labeler.label_slab(_rows_array(ds, lo, hi, side), off[s_lo:s_hi + 1] - lo, num_frames)
-                if labeler.goal:
-                    rs, gs = _goal_float64(r, off[s_lo:s_hi + 1] - lo, num_frames)
-                parts_r.append(rs)
-                parts_g.append(gs)
-            empty = np.zeros((0, num_frames), np.float64 if labeler.goal else np.float32)
-            rs = np.concatenate(parts_r) if parts_r else empty
-            gs = np.concatenate(parts_g) if parts_g else empty
-            if distributed:
-                rows = [int(off[b] - off[a]) for a, b in shards]
-                backend = dist.get_backend()
-                dev = labeler.engine.device if backend == "nccl" else torch.device("cpu")
-                both = torch.from_numpy(np.stack([rs, gs], axis=1)).to(dev)  # [n, 2, F]: one collective
+        try:
+            H, W = g[image_keys[0]].shape[-3:-1]
+            if use_crop:
+                print(f"image_size: {g[image_keys[0]].shape[-2]}")  # label_reward.py:104-105
+            labeler = RewardLabeler(model_type, text, (int(H), int(W)), model_ckpt_dir=model_ckpt_dir,
+                                    clip_state_dict=clip_state_dict, arch=arch, use_crop=use_crop, reduce=reduce,
+                                    max_batch=max_batch, device=device, precision=precision, tokenizer=tokenizer)
+            for img_key in image_keys:
+                ds = g[img_key]
+                side = g.get(img_key + SIDECAR_SUFFIX)
+                if side is not None and (side.shape[0] != ds.shape[0] or tuple(side.shape[1:]) != tuple(ds.shape[2:])):
+                    side = None                      # stale or foreign sidecar: fall back to the stacked dataset
+                parts_r, parts_g = [], []
+                for s_lo, s_hi in _slabs(off, e_lo, e_hi, slab_frames):
+                    lo, hi = int(off[s_lo]), int(off[s_hi])
+                    if hi <= lo:
+                        continue
+                    r, _, rs, gs = labeler.label_slab(_rows_array(ds, lo, hi, side), off[s_lo:s_hi + 1] - lo, num_frames)
+                    if labeler.goal:
+                        rs, gs = _goal_float64(r, off[s_lo:s_hi + 1] - lo, num_frames)
+                    parts_r.append(rs)
+                    parts_g.append(gs)
+                empty = np.zeros((0, num_frames), np.float64 if labeler.goal else np.float32)
+                results[img_key] = (np.concatenate(parts_r) if parts_r else empty,
+                                    np.concatenate(parts_g) if parts_g else empty)
+        except Exception as e:  # noqa: BLE001 — reported to every rank below, then re-raised
+            failure = e
+        if distributed:
+            # a rank that failed must not leave the others waiting in the gather: agree on success first
+            backend = dist.get_backend()
+            cdev = torch.device("cuda", torch.cuda.current_device()) if backend == "nccl" else torch.device("cpu")
+            flag = torch.tensor([0 if failure is None else 1], device=cdev)
+            dist.all_reduce(flag, op=dist.ReduceOp.MAX)
+            if int(flag) and failure is None:
+                failure = RuntimeError("label_reward failed on another rank; nothing was written")
+        if failure is not None:
+            raise failure
+        if distributed:
+            rows = [int(off[b] - off[a]) for a, b in shards]
+            for img_key in image_keys:
+                rs, gs = results[img_key]
+                both = torch.from_numpy(np.stack([rs, gs], axis=1)).to(cdev)  # [n, 2, F]: the path's one collective
                 full = gather_rows(both, rows, dst=0)
                 if rank == 0:
                     full = full.cpu().numpy()
-                    rs, gs = np.ascontiguousarray(full[:, 0]), np.ascontiguousarray(full[:, 1])
-            if rank == 0:
-                _write_labels(g, img_key, target_keys, (rs, gs), off, n_eps, len_data, num_frames)
-        labeler.close()
+                    results[img_key] = (np.ascontiguousarray(full[:, 0]), np.ascontiguousarray(full[:, 1]))
     finally:
+        if labeler is not None:
+            labeler.close()
         g.close()
+    if distributed:
+        dist.barrier()                                   # every reader has closed
+    if rank == 0:
+        g = open_store(data_path, "a")
+        try:
+            for img_key in image_keys:
+                _write_labels(g, img_key, target_keys, results[img_key], off, n_eps, len_data, num_frames)
+        finally:
+            g.close()
     if distributed:
         dist.barrier()
 
@@ -322,20 +357,21 @@ def _goal_float64(r: np.ndarray, ep_off: np.ndarray, num_frames: int):
 
 
 def _write_labels(g, img_key, target_keys, data, off, n_eps, len_data, num_frames):
-    """label_reward.py:260-289: create on the first episode (gzip, chunks (1,F), maxshape (len_data,F)) and
-    append per episode — equivalently one dataset holding rows [0, off[-1]); when the key already exists the
-    reference assigns in place by row index (:288-289)."""
-    labeled = int(off[n_eps]) if n_eps > 0 else 0
+    """label_reward.py:260-289. `data` rows are the labeled rows [off[0], off[n_eps]) in order. When the key does not
+    exist the reference creates the dataset from the first episode (gzip, chunks (1,F), maxshape (len_data,F)) and
+    APPENDS every later episode (:273-286) — one dataset of off[n_eps]-off[0] rows, whatever off[0] is (it is non-zero
+    only in the "time" layout, :84-87). When the key exists it assigns in place at the true row indices (:288-289)."""
+    if n_eps <= 0:
+        return
+    first, last = int(off[0]), int(off[n_eps])
     for _key, arr in zip(target_keys, data):
         key = f"{img_key}_{_key}"
-        if n_eps == 0:
-            continue
+        arr = arr[:last - first]
         existing = g.get(key)
         if not existing:
-            g.create_dataset(key, compression="gzip", chunks=(1, num_frames), maxshape=(len_data, num_frames),
-                             data=arr[:labeled])
+            g.create_dataset(key, compression="gzip", chunks=(1, num_frames), maxshape=(len_data, num_frames), data=arr)
         else:
-            existing[0:labeled] = arr[:labeled]
+            existing[first:last] = arr
 
 
 def main():
@@ -359,7 +395,8 @@ def main():
     parser.add_argument("--arch", type=str, default="ViT-B/16")
     parser.add_argument("--reduce", type=str, default="first", choices=["first", "mean"])
     parser.add_argument("--max_batch", type=int, default=1024)
-    parser.add_argument("--precision", type=str, default="bf16", choices=["bf16", "fp32"])
+    parser.add_argument("--precision", type=str, default="16bit", choices=sorted(PRECISIONS))
+    parser.add_argument("--tokenizer", type=str, default=None, choices=["clip", "standin"])
     args = parser.parse_args()
 
     env_name = f"{args.env_name}" if args.env_type == "none" else f"{args.env_name}_{args.env_type}"
@@ -380,7 +417,7 @@ def main():
         start_level=args.start_level, num_demonstrations=args.num_demonstrations, num_frames=args.num_frames,
         base_path=args.base_path, model_type=args.model_type, model_ckpt_dir=args.model_ckpt_dir,
         use_crop=args.use_crop, inst_type=args.inst_type, arch=args.arch, reduce=args.reduce,
-        max_batch=args.max_batch, precision=args.precision,
+        max_batch=args.max_batch, precision=args.precision, tokenizer=args.tokenizer,
     )
 
 

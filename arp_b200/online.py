@@ -26,7 +26,7 @@ import torch
 from . import capi
 from .label_reward import _resolve_clip_weights, center_crop
 from .text_tower import adapter_text_embedding, clip_text_embedding
-from .tokenizer import tokenize
+from .tokenizer import resolve as resolve_tokenizer
 from .weights import load_checkpoint
 
 
@@ -36,7 +36,7 @@ class OnlineClip:
     changes the resize tables) and text embeddings are cached per instruction."""
 
     def __init__(self, vl_type: str = "clip", *, vl_checkpoint=None, clip_state_dict=None, arch: str = "ViT-B/16",
-                 device: int | None = None, max_batch: int = 2, precision: str = "bf16"):
+                 device: int | None = None, max_batch: int = 2, precision: str = "16bit", tokenizer=None):
         if vl_type not in ("clip", "clip_goal_conditioned", "clip_ft", "clip_ft_goal_conditioned"):
             raise ValueError(vl_type)                                         # rollout_procgen.py:145
         self.vl_type, self.arch = vl_type, arch
@@ -44,6 +44,7 @@ class OnlineClip:
         self.goal = vl_type.endswith("goal_conditioned")
         self.device_index = int(os.environ.get("LOCAL_RANK", "0")) if device is None else device
         self.max_batch, self.precision = max_batch, precision
+        self._tokenize = resolve_tokenizer(tokenizer)   # refuses the stand-in unless opted in (tokenizer.py)
         if self.adapter:
             assert vl_checkpoint, "You have to specifiy vl_checkpoint."     # main_procgen.py:585
             sd = load_checkpoint(vl_checkpoint) if not isinstance(vl_checkpoint, dict) else vl_checkpoint
@@ -69,7 +70,7 @@ class OnlineClip:
             # clip.load's preprocess for every vl_type (main_procgen.py:570,572): PIL bicubic, not the adapter's bilinear
             e = capi.Engine(device=self.device_index, patch=32 if self.arch.endswith("/32") else 16, in_h=h, in_w=w,
                             preprocess=capi.PRE_PIL_BICUBIC, head=self._head(), max_batch=self.max_batch,
-                            precision=capi.PREC_F32 if self.precision == "fp32" else capi.PREC_BF16)
+                            precision={"fp32": capi.PREC_F32, "fp32resid": capi.PREC_F32RESID}.get(self.precision, capi.PREC_16BIT))
             missing = e.load_state_dict(self.sd, strict=False)
             if missing:
                 raise RuntimeError(f"checkpoint lacks {len(missing)} tensors, e.g. {missing[:3]}")
@@ -80,7 +81,7 @@ class OnlineClip:
         texts = tuple(pos_text) if isinstance(pos_text, (list, tuple)) else (pos_text,)
         if self._engine_text.get(key_hw) != texts:
             if texts not in self._text_cache:
-                tokens = tokenize(list(texts))
+                tokens = self._tokenize(list(texts))
                 self._text_cache[texts] = (adapter_text_embedding(self.sd, tokens, e.device, ensemble=False)
                                            if self.adapter else clip_text_embedding(self.sd, tokens, e.device))
             emb, scale = self._text_cache[texts]

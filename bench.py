@@ -47,6 +47,8 @@ def parse():
     ap.add_argument("--num-frames", type=int, default=8)
     ap.add_argument("--max-batch", type=int, default=1024)
     ap.add_argument("--cpu-sample-frames", type=int, default=400)
+    ap.add_argument("--precision", default="16bit", choices=["16bit", "fp32resid"],
+                    help="tensor-core mode: 16-bit residual stream + folded LayerNorm (default) or fp32 residual stream")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
@@ -166,7 +168,7 @@ def workload_config(args, frames_per_rank: int) -> dict:
     return {"workload": f"CLIP ViT-B/16 model_type=clip labeling of {args.episodes} synthetic CoinRun-shaped episodes "
                         f"at {args.size}x{args.size} (BASELINE configs[1]), random-init weights",
             "episodes_per_gpu": args.episodes, "frames_per_gpu": frames_per_rank, "frame": [args.size, args.size, 3],
-            "num_frames": args.num_frames, "max_batch": args.max_batch, "parallelism": f"episode-sharded x{args.gpus}",
+            "num_frames": args.num_frames, "max_batch": args.max_batch, "precision": args.precision, "parallelism": f"episode-sharded x{args.gpus}",
             "cache": "inputs (14 GB/GPU at the default size) far exceed the 126 MB L2; no flush needed"}
 
 
@@ -183,7 +185,8 @@ def main():
     from arp_b200.build import build
     from arp_b200.sharding import gather_rows
     from arp_b200.text_tower import clip_text_embedding
-    from arp_b200.tokenizer import tokenize
+    from arp_b200.tokenizer import tokenize as _tokenize
+    tokenize = lambda t: _tokenize(t, standin=True)   # noqa: E731 — random-init weights: the deterministic stand-in ids
     from arp_b200.weights import random_clip_state_dict
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -200,7 +203,8 @@ def main():
     F = args.num_frames
     off_np = episode_offsets(args.episodes, seed=1 + rank)
     T = int(off_np[-1])
-    eng = capi.Engine(device=local, patch=16, in_h=args.size, in_w=args.size, max_batch=args.max_batch)
+    eng = capi.Engine(device=local, patch=16, in_h=args.size, in_w=args.size, max_batch=args.max_batch,
+                      precision=capi.PREC_F32RESID if args.precision == "fp32resid" else capi.PREC_16BIT)
     sd = random_clip_state_dict("ViT-B/16", seed=0, device="cpu")   # CPU generator: same weights as the CPU arm
     eng.load_state_dict(sd)
     emb, scale = clip_text_embedding(sd, tokenize([TEXT]), dev)

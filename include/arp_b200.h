@@ -21,7 +21,7 @@
 extern "C" {
 #endif
 
-#define ARP_B200_ABI_VERSION 4   /* 3: + arp_encode_taps_chw, 4: + arp_operand_dtype (both additive) */
+#define ARP_B200_ABI_VERSION 5   /* 3: + arp_encode_taps_chw, 4: + arp_operand_dtype, 5: + ARP_PREC_F32RESID, arp_ln_gemm */
 
 #if defined(__GNUC__)
 #define ARP_API __attribute__((visibility("default")))
@@ -53,11 +53,17 @@ typedef enum ArpHead {
 typedef enum ArpReduce { ARP_REDUCE_FIRST = 0, ARP_REDUCE_MEAN = 1 } ArpReduce;
 
 typedef enum ArpDType { ARP_F32 = 0, ARP_BF16 = 1, ARP_F16 = 2 } ArpDType;
-/* Arithmetic of the model path. BF16 = tcgen05 tensor cores, bf16 operands, fp32 accumulate and fp32 residual
- * stream (the product path). F32 = verification path: every weight, activation and contraction in fp32 on the
- * FMA pipe — what clip.load(...).float() computes on the reference's CPU route (label_reward.py:126-141); used
- * to check the restated algorithm at the 1e-5 bar, ~50x slower. */
-typedef enum ArpPrecision { ARP_PREC_BF16 = 0, ARP_PREC_F32 = 1 } ArpPrecision;
+/* Arithmetic of the model path.
+ * ARP_PREC_BF16 (0; the name is historical — read "16-bit tensor-core path"): the product path. tcgen05 tensor cores,
+ *   16-bit operands in the build's operand format (arp_operand_dtype(): fp16 by default, the format the reference's own
+ *   CUDA route runs CLIP in, clip.load label_reward.py:126), fp32 accumulation, 16-bit residual stream updated by TMA
+ *   reduce-add, LayerNorm folded algebraically into the QKV / c_fc GEMM epilogues from fp32 row moments.
+ * ARP_PREC_F32RESID (2): same tensor-core GEMMs and attention with an fp32 residual stream and standalone fp32 LayerNorm
+ *   kernels (round 1's pipeline): ~2x closer to fp32, ~10 % slower.
+ * ARP_PREC_F32 (1): verification path — every weight, activation and contraction in fp32 on the FMA pipe, what
+ *   clip.load(...).float() computes on the reference's CPU route (label_reward.py:126-141); used to check the restated
+ *   algorithm at the 1e-5 bar, ~50x slower. */
+typedef enum ArpPrecision { ARP_PREC_BF16 = 0, ARP_PREC_F32 = 1, ARP_PREC_F32RESID = 2 } ArpPrecision;
 
 typedef struct ArpHandle ArpHandle;
 
@@ -86,9 +92,9 @@ ARP_API int arp_create(const ArpConfig* cfg, ArpHandle** out);
 ARP_API void arp_destroy(ArpHandle* h);
 ARP_API const char* arp_last_error(const ArpHandle* h); /* h may be NULL: last error of arp_create */
 ARP_API int arp_abi_version(void);
-/* ArpDType of the 16-bit operand format this build runs its contractions in: ARP_BF16 (default build) or ARP_F16
- * (-DARP_OP_FP16=1; the reference's own CUDA path keeps CLIP in fp16, clip.load). The "bf16" buffers of the test hooks
- * below (arp_gemm_bf16, arp_layernorm_bf16, arp_attention) are in THIS format. */
+/* ArpDType of the 16-bit operand format this build runs its contractions in: ARP_F16 (default build; the reference's
+ * own CUDA path keeps CLIP in fp16, clip.load) or ARP_BF16 (-DARP_OP_FP16=0). The "bf16" buffers of the test hooks
+ * below (arp_gemm_bf16, arp_ln_gemm, arp_layernorm_bf16, arp_attention) are in THIS format. */
 ARP_API int arp_operand_dtype(void);
 
 /* ------------------------------------------------------------------------------------------------
@@ -194,10 +200,17 @@ ARP_API int arp_scan_only(ArpHandle* h, const float* reward_dev, int64_t T, cons
                   int32_t num_frames, float gamma, float* rtg_dev, float* reward_stacked_dev,
                   float* rtg_stacked_dev, void* stream);
 /* C[M,N] = act(A[M,K] W[N,K]^T + bias) (+ resid): the tcgen05 GEMM behind every linear layer.
- * A, W in the operand format (arp_operand_dtype) on the device; out in that format (out_dtype = it) or fp32; act 0 none, 1 QuickGELU, 2 ReLU;
- * bias / resid fp32 or NULL; N % 256 == 0, K % 64 == 0. */
+ * A, W in the operand format (arp_operand_dtype) on the device; out in that format (out_dtype = it) or fp32; act 0 none,
+ * 1 QuickGELU, 2 ReLU; bias fp32 or NULL; resid NULL or a buffer of out's dtype (may alias out_dev: the residual
+ * stream is then updated in place by TMA reduce-add, fp32 or 16-bit); N % 256 == 0, K % 64 == 0. */
 ARP_API int arp_gemm_bf16(ArpHandle* h, const void* a_dev, const void* w_dev, void* out_dev, int32_t out_dtype, int64_t M,
-                  int32_t N, int32_t K, const float* bias_dev, const float* resid_dev, int32_t act, void* stream);
+                  int32_t N, int32_t K, const float* bias_dev, const void* resid_dev, int32_t act, void* stream);
+/* out[M,N] = act(LayerNorm(x; gamma, beta) W^T + bias) with the LayerNorm FOLDED into the GEMM as on the default path
+ * (ln_1 -> in_proj, ln_2 -> c_fc; openai/CLIP ResidualAttentionBlock): x [M,768] in the operand format is multiplied raw
+ * by gamma-folded weights and the epilogue applies the row's (rstd, -mean*rstd). w fp32 [N,768], gamma / beta [768],
+ * bias [N] fp32 DEVICE; out in the operand format; act 0 none, 1 QuickGELU. Allocates its temporaries per call: test seam. */
+ARP_API int arp_ln_gemm(ArpHandle* h, const void* x_dev, const float* gamma_dev, const float* beta_dev, const float* w_f32_dev,
+                const float* bias_dev, void* out_dev, int64_t M, int32_t N, int32_t act, void* stream);
 /* y = LayerNorm(x) over 768-wide rows, fp32 in, bf16 out */
 ARP_API int arp_layernorm_bf16(ArpHandle* h, const float* x_dev, const float* gamma_dev, const float* beta_dev, void* y_dev,
                        int64_t M, void* stream);

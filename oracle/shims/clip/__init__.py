@@ -33,6 +33,7 @@ import torch
 from torch import nn
 
 __all__ = ["available_models", "load", "tokenize", "CLIP"]
+__arp_oracle_shim__ = True   # arp_b200.tokenizer must never mistake this stand-in package for openai/CLIP
 
 _ARCH = {
     # name: (embed_dim, image_resolution, vision_layers, vision_width, vision_patch,

@@ -20,6 +20,7 @@ sys.path.insert(0, str(ROOT / "oracle" / "shims"))
 TOL_COS_ABS = 5e-4          # absolute error of the cosine similarity, bf16 pipeline
 TOL_REWARD_REL_TO_MAX = 2e-2   # max|Δr| / max|r_ref| at random init (reported, loose)
 TOL_REWARD_REL_CORRELATED = 1e-3  # north_star's 1e-3 relative, on the well-conditioned correlated-text case
+TOL_REWARD_REL_OPERATING_POINT = 1e-3   # north_star's 1e-3, per frame, at cos 0.15-0.35 and scale 100 (default build)
 LOGIT_SCALE_RANDOM_INIT = 1.0 / 0.07
 # fp32 verification path (precision="fp32") against the fp32 reference — north_star's 1e-5:
 TOL_F32_REL = 1e-5          # max|Δr| / max|r_ref| per golden, and per-frame relative on the correlated-text case

@@ -1,9 +1,12 @@
+import os
 import sys
 from pathlib import Path
 
 import pytest
 
 ROOT = Path(__file__).resolve().parents[1]
+# random-init parity experiments: both sides tokenize with the same deterministic stand-in (arp_b200/tokenizer.py)
+os.environ.setdefault("ARP_ALLOW_STANDIN_TOKENIZER", "1")
 for p in (str(ROOT), str(ROOT / "tests")):
     if p not in sys.path:
         sys.path.insert(0, p)

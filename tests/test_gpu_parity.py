@@ -8,7 +8,7 @@ import pytest
 import torch
 
 from _util import (LOGIT_SCALE_RANDOM_INIT, TOL_COS_ABS, TOL_F32_COS_ABS, TOL_F32_REL, TOL_REWARD_REL_CORRELATED,
-                   TOL_REWARD_REL_TO_MAX, golden_names, load_golden, rebuild_inputs)
+                   TOL_REWARD_REL_OPERATING_POINT, TOL_REWARD_REL_TO_MAX, golden_names, load_golden, rebuild_inputs)
 
 pytestmark = pytest.mark.gpu
 
@@ -46,8 +46,11 @@ def relerr(a, b):
     (197 * 64, 768, 3072, 0, True, True, torch.float32),     # c_proj + residual
     (100, 13312, 6656, 2, True, False, torch.bfloat16),      # adapter fc1 + ReLU
     (100, 6144, 9216, 0, False, False, torch.float32),       # adapter intermediate linear
+    (197 * 64, 768, 768, 0, True, True, torch.bfloat16),     # out_proj accumulating into the 16-bit residual stream
+    (197 * 64 + 5, 768, 3072, 0, True, True, torch.bfloat16),  # c_proj likewise, ragged M
 ])
 def test_gemm_vs_torch(eng, M, N, K, act, bias, resid, out_dtype):
+    from arp_b200 import capi as capi_mod
     dev = eng.device
     g = torch.Generator(device=dev).manual_seed(M + N + K)
     a = (torch.randn(M, K, device=dev, generator=g) * 0.5).bfloat16()
@@ -63,7 +66,10 @@ def test_gemm_vs_torch(eng, M, N, K, act, bias, resid, out_dtype):
     elif act == 2:
         ref = torch.relu(ref)
     if resid:
-        ref = ref + r
+        if out_dtype != torch.float32:       # 16-bit stream: x = fl16(x16 + fl16(acc + bias)), x16 = fl16(resid)
+            ref = ref.to(capi_mod.operand_dtype()).float() + r.to(capi_mod.operand_dtype()).float()
+        else:
+            ref = ref + r
     assert torch.isfinite(out.float()).all()
     assert relerr(out, ref) < (1e-2 if out_dtype == torch.bfloat16 else 3e-5)   # bf16 output rounding / fp32 accumulate
 
@@ -82,6 +88,51 @@ def test_gemm_residual_in_place(eng):
                                       C.c_void_p(x.data_ptr()), 0, 300, 768, 768, None, C.c_void_p(x.data_ptr()), 0,
                                       C.c_void_p(torch.cuda.current_stream().cuda_stream)))
     assert relerr(x, ref) < 3e-5
+
+
+def test_gemm_16bit_residual_in_place(eng):
+    """Default path: the 16-bit residual stream is updated in place by a 16-bit TMA reduce-add."""
+    dev = eng.device
+    from arp_b200 import capi as _capi
+    op = _capi.operand_dtype()
+    a = torch.randn(1000, 3072, device=dev).to(op)
+    w = (torch.randn(768, 3072, device=dev) * 0.02).to(op)
+    b = torch.randn(768, device=dev)
+    x = torch.randn(1000, 768, device=dev).to(op)
+    delta = (a.float() @ w.float().t() + b).to(op).float()
+    ref = (x.float() + delta).to(op)
+    import ctypes as C
+    eng._check(eng._lib.arp_gemm_bf16(eng._h, C.c_void_p(a.data_ptr()), C.c_void_p(w.data_ptr()),
+                                      C.c_void_p(x.data_ptr()), _capi._TORCH_DT[op], 1000, 768, 3072,
+                                      C.c_void_p(b.data_ptr()), C.c_void_p(x.data_ptr()), 0,
+                                      C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+    # identical up to the fp32 summation order of acc ahead of the two 16-bit roundings: the rounded increment may differ
+    # by one ulp of ITS magnitude, and the sum's rounding by one more of the result's
+    ulp = 2.0 ** (-10 if op == torch.float16 else -7)
+    scale = torch.maximum(ref.float().abs(), delta.abs()).clamp_min(1.0)
+    assert float(((x.float() - ref.float()).abs() / scale).max()) <= 2 * ulp
+    assert float((x.float() - ref.float()).abs().mean()) < 1e-2 * ulp          # and almost every element is identical
+
+
+@pytest.mark.parametrize("M,N,act", [(197 * 8, 2304, 0), (1003, 3072, 1), (1, 256, 0)])
+def test_layernorm_folded_gemm_vs_torch(eng, M, N, act):
+    """act(LN(x) W^T + b) with LayerNorm applied algebraically in the GEMM epilogue (row moments + gamma-folded
+    weights) against torch fp32 LayerNorm -> linear on the same 16-bit x."""
+    dev = eng.device
+    from arp_b200 import capi as _capi
+    g = torch.Generator(device=dev).manual_seed(M + N)
+    x = (torch.randn(M, 768, device=dev, generator=g) * 2.0 + 0.7).to(_capi.operand_dtype())   # mean / std = 0.35
+    x[:, 5] += 20.0                                                                           # an outlier channel
+    gamma = 1.0 + 0.2 * torch.randn(768, device=dev, generator=g)
+    beta = 0.1 * torch.randn(768, device=dev, generator=g)
+    w = torch.randn(N, 768, device=dev, generator=g) * 0.03
+    b = torch.randn(N, device=dev, generator=g) * 0.1
+    out = eng.ln_gemm(x, gamma, beta, w, b, act=act)
+    ref = torch.nn.functional.layer_norm(x.float(), (768,), gamma, beta, 1e-5) @ w.t() + b
+    if act == 1:
+        ref = ref * torch.sigmoid(1.702 * ref)
+    assert torch.isfinite(out.float()).all()
+    assert relerr(out, ref) < 1e-2       # 16-bit operands (gamma-folded W rounded once) and 16-bit output
 
 
 def test_layernorm_vs_torch(eng):
@@ -205,19 +256,22 @@ def _run_product(tmp_path, meta, data, clip_sd, adapter_sd, **kw):
                  model_type=meta["model_type"], model_ckpt_dir=str(ckpt) if ckpt else None,
                  use_crop=meta.get("use_crop", False), inst_type=meta.get("inst_type", "none"),
                  clip_state_dict=clip_sd, arch=meta["arch"], max_batch=kw.get("max_batch", 64), env_type="none",
-                 precision=kw.get("precision", "bf16"))
+                 precision=kw.get("precision", "16bit"))
     s = NpyStore(path, "r")
     out = {k: np.array(s[k][:]) for k in s.keys() if k.startswith("ob_")}
     s.close()
     return out
 
 
+@pytest.mark.parametrize("precision", ["16bit", "fp32resid"])
 @pytest.mark.parametrize("name", golden_names())
-def test_label_reward_matches_reference_golden(tmp_path, name):
+def test_label_reward_matches_reference_golden(tmp_path, name, precision):
+    """Both tensor-core modes (default: 16-bit residual stream + folded LayerNorm; fp32resid: fp32 stream + LayerNorm
+    kernels) against what the unmodified reference wrote."""
     from oracle import port
     meta, gold = load_golden(name)
     data, clip_sd, adapter_sd = rebuild_inputs(meta)
-    out = _run_product(tmp_path, meta, data, clip_sd, adapter_sd)
+    out = _run_product(tmp_path, meta, data, clip_sd, adapter_sd, precision=precision)
     assert sorted(out) == sorted(gold), "dataset keys must be the reference's"
     F = data["done"].shape[1]
     idx = port.episode_index(data["done"][:, -1])
@@ -417,6 +471,53 @@ def test_correlated_text_reward_relative_tolerance(capi):
         e.close()
         rel = np.abs(r - ref) / np.abs(ref)
         assert rel.max() <= tol, f"precision {precision}: max relative reward error {rel.max():.2e}"
+
+
+@pytest.fixture(scope="module")
+def operating_point_case():
+    """16 structured 256x256 frames, the fp32 oracle's unit image features f̂ (ViT-B/16), and for every frame a unit
+    vector n̂ ⟂ f̂ — the text embeddings of the operating-point test are built from these at fixed angles."""
+    from oracle import port
+    from arp_b200.synth import structured_frames
+    model = port.clip_shim.build("ViT-B/16", 0)
+    rng = np.random.default_rng(11)
+    ob = structured_frames(16, 256, rng)[:, None]
+    tf = port.transform_pil(False, 256)
+    with torch.no_grad():
+        f = model.encode_image(torch.stack([tf(im) for im in ob[:, 0]])).double()
+    fn = f / f.norm(dim=1, keepdim=True)
+    g = torch.Generator().manual_seed(3)
+    n = torch.randn(fn.shape, generator=g, dtype=torch.float64)
+    n = n - (n * fn).sum(1, keepdim=True) * fn
+    n = n / n.norm(dim=1, keepdim=True)
+    return model.state_dict(), ob, fn, n
+
+
+@pytest.mark.parametrize("c", [0.15, 0.25, 0.35])
+def test_reward_relative_tolerance_at_pretrained_operating_point(capi, operating_point_case, c):
+    """north_star's tolerance where it is hard: per-frame |Δr| / |r| <= 1e-3 for the DEFAULT 16-bit build and <= 1e-5
+    for precision="fp32", with the image/text cosine at c in {0.15, 0.25, 0.35} and scale 100 (= pretrained
+    logit_scale.exp()) — the range pretrained CLIP rewards live in (label_reward.py:141-145). Frame i is scored
+    against its own text t_i = c·f̂_i + sqrt(1-c²)·n̂_i (n̂_i ⟂ f̂_i), so the reference reward is exactly 100·c and the
+    angular error of the image feature enters at first order (unlike the mean-feature case above, cos ≈ 0.9)."""
+    sd, ob, fn, n = operating_point_case
+    t = (c * fn + (1.0 - c * c) ** 0.5 * n).float()
+    scale = 100.0
+    ref = scale * (fn.float() * t).sum(1).numpy()
+    assert np.allclose(ref, scale * c, rtol=1e-5)
+    worst = {}
+    for precision, tol in ((capi.PREC_16BIT, TOL_REWARD_REL_OPERATING_POINT),
+                           (capi.PREC_F32RESID, TOL_REWARD_REL_OPERATING_POINT), (capi.PREC_F32, TOL_F32_REL)):
+        e = capi.Engine(device=0, patch=16, in_h=256, in_w=256, max_batch=16, precision=precision)
+        e.load_state_dict(sd)
+        e.set_text(t, scale)
+        _, lg = e.compute_reward(torch.from_numpy(ob).cuda(), want_logits=True)
+        e.close()
+        r = np.diagonal(lg.cpu().numpy())                 # frame i against text i
+        worst[precision] = float((np.abs(r - ref) / np.abs(ref)).max())
+        print(f"operating point c={c} precision={precision} operand={capi.operand_dtype()}: "
+              f"max |dr|/|r| = {worst[precision]:.3e}")
+        assert worst[precision] <= tol, f"c={c} precision {precision}: max relative reward error {worst[precision]:.2e}"
 
 
 def test_device_and_host_entry_points_agree(capi):

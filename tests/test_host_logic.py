@@ -195,3 +195,46 @@ def test_slabs_properties(lens, budget, data):
     assert all(a < b for a, b in slabs) and all(a[1] == b[0] for a, b in zip(slabs, slabs[1:]))
     for a, b in slabs:
         assert off[b] - off[a] <= budget or b == a + 1
+
+
+def test_tokenizer_refuses_the_standin_unless_opted_in(monkeypatch):
+    """VERDICT r1 #7 / ADVICE: with openai/CLIP's tokenizer missing, real weights + stand-in ids would give garbage
+    rewards silently. The stand-in must be an explicit choice (tokenizer="standin" or ARP_ALLOW_STANDIN_TOKENIZER=1)."""
+    import sys
+    from arp_b200 import tokenizer as tk
+    shims = str(Path(__file__).resolve().parents[1] / "oracle" / "shims")
+    if shims not in sys.path:
+        sys.path.insert(0, shims)
+    import clip as shim                                    # the oracle's stand-in package must not count as the real one
+    assert getattr(shim, "__arp_oracle_shim__", False) and tk._real_tokenizer() is None
+    monkeypatch.delenv("ARP_ALLOW_STANDIN_TOKENIZER", raising=False)
+    with pytest.raises(tk.TokenizerUnavailable):
+        tk.tokenize(["the goal is to collect the coin."])
+    with pytest.raises(tk.TokenizerUnavailable):
+        tk.resolve(None)(["x"])
+    with pytest.raises(tk.TokenizerUnavailable):
+        tk.resolve("clip")(["x"])
+    t = tk.resolve("standin")(["a b", "c"])
+    assert t.shape == (2, 77) and int(t[0, 0]) == tk.SOT and int(t[0].max()) == tk.EOT
+    assert torch.equal(tk.resolve(lambda texts: torch.ones(len(texts), 77, dtype=torch.int32))(["q"]),
+                       torch.ones(1, 77, dtype=torch.int32))
+    monkeypatch.setenv("ARP_ALLOW_STANDIN_TOKENIZER", "1")
+    assert torch.equal(tk.tokenize(["a b", "c"]), t)
+    with pytest.raises(ValueError):
+        tk.resolve("bpe")
+
+
+def test_label_reward_refuses_without_a_tokenizer(tmp_path, monkeypatch):
+    """The drop-in itself: a CLIP state_dict that is NOT flagged as an experiment + no `clip` package -> refuse before
+    any frame is scored (the text embedding is built first)."""
+    from arp_b200 import capi, tokenizer as tk
+    from arp_b200.label_reward import RewardLabeler
+    monkeypatch.delenv("ARP_ALLOW_STANDIN_TOKENIZER", raising=False)
+
+    class FakeEngine:                                       # no GPU here: stop right after construction
+        device, goal = torch.device("cpu"), False
+        def __init__(self, **kw): pass
+        def load_state_dict(self, sd, strict=False): return []
+    monkeypatch.setattr(capi, "Engine", FakeEngine)
+    with pytest.raises(tk.TokenizerUnavailable):
+        RewardLabeler("clip", "the goal is to collect the coin.", (64, 64), clip_state_dict={"visual.proj": torch.zeros(1)})

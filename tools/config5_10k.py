@@ -50,7 +50,7 @@ for e in range(e_lo, e_hi):
 sd = random_clip_state_dict("ViT-B/16", seed=0, device="cpu")
 eng = capi.Engine(device=local, patch=16, in_h=SIZE, in_w=SIZE, max_batch=512)
 eng.load_state_dict(sd)
-emb, scale = clip_text_embedding(sd, tokenize(["the goal is to collect the coin."]), dev)
+emb, scale = clip_text_embedding(sd, tokenize(["the goal is to collect the coin."], standin=True), dev)
 eng.set_text(emb, scale)
 off_local = torch.from_numpy(off[e_lo:e_hi + 1] - lo).to(dev)
 rows = [int(off[b] - off[a]) for a, b in shards]
