@@ -24,7 +24,7 @@ NVCC_FLAGS = [
     "-shared", "-Xcompiler", "-fPIC",
     "-Xcompiler", "-fvisibility=hidden",
     "--expt-relaxed-constexpr",
-    "-cudart", "static",
+    "-cudart", "static", "-Xcompiler", "-pthread",
 ]
 
 

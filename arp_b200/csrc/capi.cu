@@ -5,12 +5,16 @@
 #include <cuda.h>
 #include <cuda_runtime.h>
 
+#include <atomic>
 #include <cmath>
+#include <condition_variable>
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
 #include <map>
+#include <mutex>
 #include <string>
+#include <thread>
 #include <tuple>
 #include <vector>
 
@@ -169,6 +173,9 @@ struct ArpHandle {
   size_t scratch_bytes[2] = {0, 0};
   uint8_t* stage_dev[2] = {nullptr, nullptr};
   size_t stage_bytes = 0;
+  uint8_t* pin_ring = nullptr;     // pinned staging ring for pageable callers of arp_label_host (STG_SLOTS x STG_SUB frames)
+  size_t pin_bytes = 0;
+  cudaEvent_t ev_slot[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   cudaStream_t copy_stream = nullptr, own_stream = nullptr;
   cudaEvent_t ev_copied[2] = {nullptr, nullptr}, ev_consumed[2] = {nullptr, nullptr};
 
@@ -470,6 +477,8 @@ extern "C" void arp_destroy(ArpHandle* h) {
     if (h->ev_copied[i]) cudaEventDestroy(h->ev_copied[i]);
     if (h->ev_consumed[i]) cudaEventDestroy(h->ev_consumed[i]);
   }
+  if (h->pin_ring) cudaFreeHost(h->pin_ring);
+  for (cudaEvent_t e : h->ev_slot) if (e) cudaEventDestroy(e);
   for (auto& kv : h->online_graphs) if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
   for (auto& r : h->prof) { cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); }
   for (cudaEvent_t e : h->event_pool) cudaEventDestroy(e);
@@ -1419,6 +1428,75 @@ static int ensure_stage(ArpHandle* h) {
   return ARP_OK;
 }
 
+// ---- host staging (arp_label_host on pageable memory) -------------------------------------------------------------
+// The drop-in hands the library a pointer into a memory-mapped dataset (label_reward.py:268 `g[img_key][traj, -1]`): the
+// rows are pageable, file-backed, and only the last stacked frame of each row is wanted. cudaMemcpy from such memory is
+// a synchronous driver-side bounce copy; instead a few worker threads gather sub-chunks of frames (page faults and all)
+// into a ring of pinned slots while the main thread turns finished slots into asynchronous H2D copies, so that disk /
+// page-cache reads, PCIe and the GPU all run concurrently and one call can cover a whole shard.
+constexpr int STG_SLOTS = 8;       // pinned ring depth
+constexpr int STG_SUB = 64;        // frames per slot (12.6 MB at 256x256x3)
+constexpr int STG_WORKERS = 4;
+
+static bool host_ptr_is_pinned(const void* p) {
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+  return a.type == cudaMemoryTypeHost;   // pageable memory reports cudaMemoryTypeUnregistered
+}
+
+static int ensure_pinned_ring(ArpHandle* h, size_t frame_bytes) {
+  const size_t need = frame_bytes * STG_SUB * STG_SLOTS;
+  if (h->pin_bytes >= need) return ARP_OK;
+  if (h->pin_ring) { cudaFreeHost(h->pin_ring); h->pin_ring = nullptr; h->pin_bytes = 0; }
+  ARP_CUDA(h, cudaHostAlloc((void**)&h->pin_ring, need, cudaHostAllocDefault));
+  h->pin_bytes = need;
+  for (int i = 0; i < STG_SLOTS; ++i)
+    if (!h->ev_slot[i]) ARP_CUDA(h, cudaEventCreateWithFlags(&h->ev_slot[i], cudaEventDisableTiming));
+  return ARP_OK;
+}
+
+struct SubChunk { int64_t t0; int n; };   // rows [t0, t0+n) of the call, never straddling a device chunk
+
+// gathers sub-chunk after sub-chunk into the pinned ring; the main thread consumes them in order
+struct HostStager {
+  const uint8_t* src; int64_t stride; size_t frame_bytes; uint8_t* ring; cudaEvent_t* ev_slot; int device;
+  const std::vector<SubChunk>* subs;
+  std::atomic<int64_t> next{0}, issued{0};   // next task to start | sub-chunks whose H2D has been enqueued
+  std::atomic<bool> abort{false};
+  std::mutex mu; std::condition_variable cv;
+  std::vector<char> done;
+  std::vector<std::thread> threads;
+
+  void run() {
+    cudaSetDevice(device);
+    const int64_t n = (int64_t)subs->size();
+    for (;;) {
+      const int64_t j = next.fetch_add(1);
+      if (j >= n || abort.load()) return;
+      const int slot = (int)(j % STG_SLOTS);
+      if (j >= STG_SLOTS) {                      // the slot's previous tenant must have left for the device
+        while (issued.load(std::memory_order_acquire) < j - STG_SLOTS + 1) {
+          if (abort.load()) return;
+          std::this_thread::yield();
+        }
+        cudaEventSynchronize(ev_slot[slot]);
+      }
+      const SubChunk& sc = (*subs)[j];
+      uint8_t* dst = ring + (size_t)slot * STG_SUB * frame_bytes;
+      for (int f = 0; f < sc.n; ++f) memcpy(dst + (size_t)f * frame_bytes, src + (sc.t0 + f) * stride, frame_bytes);
+      { std::lock_guard<std::mutex> lk(mu); done[j] = 1; }
+      cv.notify_all();
+    }
+  }
+  void start() {
+    done.assign(subs->size(), 0);
+    const int nw = (int)std::min<size_t>(STG_WORKERS, subs->size());
+    for (int i = 0; i < nw; ++i) threads.emplace_back([this] { run(); });
+  }
+  void wait(int64_t j) { std::unique_lock<std::mutex> lk(mu); cv.wait(lk, [&] { return done[j] != 0; }); }
+  void stop() { abort.store(true); for (auto& t : threads) t.join(); threads.clear(); }
+};
+
 extern "C" int arp_label_host(ArpHandle* h, const uint8_t* ob_host, int64_t T, int64_t row_stride_bytes,
                               const int64_t* ep_offsets_host, int32_t n_eps, int32_t num_frames, float* reward_host,
                               float* rtg_host, float* reward_stacked_host, float* rtg_stacked_host) {
@@ -1444,25 +1522,52 @@ extern "C" int arp_label_host(ArpHandle* h, const uint8_t* ob_host, int64_t T, i
   float* d_rs = d_g + T;
   float* d_gs = d_rs + (size_t)T * F;
   ARP_CUDA(h, cudaMemcpyAsync(d_off, ep_offsets_host, (size_t)(n_eps + 1) * 8, cudaMemcpyHostToDevice, st));
-  // double-buffered: chunk i+1's frames (only the scored image of each row) cross PCIe while chunk i is encoded
   const int64_t nchunks = (T + B - 1) / B;
+  // pinned (or registered) caller memory goes to the device directly, one strided 2-D copy per chunk; pageable memory is
+  // gathered through the pinned ring by worker threads
+  const bool staged = !host_ptr_is_pinned(ob_host);
+  std::vector<SubChunk> subs;
+  HostStager stager;
+  if (staged) {
+    ARP_TRY(ensure_pinned_ring(h, frame_bytes));
+    for (int64_t ci = 0; ci < nchunks; ++ci) {
+      const int64_t t0 = ci * B, n = std::min(B, T - t0);
+      for (int64_t s0 = 0; s0 < n; s0 += STG_SUB) subs.push_back(SubChunk{t0 + s0, (int)std::min<int64_t>(STG_SUB, n - s0)});
+    }
+    stager.src = ob_host; stager.stride = row_stride_bytes; stager.frame_bytes = frame_bytes; stager.ring = h->pin_ring;
+    stager.ev_slot = h->ev_slot; stager.device = c.device; stager.subs = &subs;
+    stager.start();
+  }
+  // double-buffered: chunk i+1's frames (only the scored image of each row) cross PCIe while chunk i is encoded
   int rc = ARP_OK;
+  int64_t sub_j = 0;
   for (int64_t ci = 0; ci < nchunks && rc == ARP_OK; ++ci) {
     const int buf = (int)(ci & 1);
-    cudaStream_t ps = st;
     const int64_t t0 = ci * B, n = std::min(B, T - t0);
     if (ci >= 2) cudaStreamWaitEvent(h->copy_stream, h->ev_consumed[buf], 0);
-    cudaError_t e = cudaMemcpy2DAsync(h->stage_dev[buf], frame_bytes, ob_host + t0 * row_stride_bytes,
-                                      (size_t)row_stride_bytes, frame_bytes, (size_t)n, cudaMemcpyHostToDevice,
-                                      h->copy_stream);
+    cudaError_t e = cudaSuccess;
+    if (!staged) {
+      e = cudaMemcpy2DAsync(h->stage_dev[buf], frame_bytes, ob_host + t0 * row_stride_bytes, (size_t)row_stride_bytes,
+                            frame_bytes, (size_t)n, cudaMemcpyHostToDevice, h->copy_stream);
+    } else {
+      for (int64_t s0 = 0; s0 < n && e == cudaSuccess; s0 += STG_SUB, ++sub_j) {
+        stager.wait(sub_j);
+        const int slot = (int)(sub_j % STG_SLOTS);
+        e = cudaMemcpyAsync(h->stage_dev[buf] + (size_t)s0 * frame_bytes, h->pin_ring + (size_t)slot * STG_SUB * frame_bytes,
+                            (size_t)subs[sub_j].n * frame_bytes, cudaMemcpyHostToDevice, h->copy_stream);
+        if (e == cudaSuccess) e = cudaEventRecord(h->ev_slot[slot], h->copy_stream);
+        stager.issued.store(sub_j + 1, std::memory_order_release);
+      }
+    }
     if (e != cudaSuccess) { rc = fail(h, ARP_ERR_CUDA, "H2D frames failed: %s", cudaGetErrorString(e)); break; }
     cudaEventRecord(h->ev_copied[buf], h->copy_stream);
-    cudaStreamWaitEvent(ps, h->ev_copied[buf], 0);
-    if ((rc = encode_chunk(h, h->stage_dev[buf], n, (int64_t)frame_bytes, ps)) != ARP_OK) break;
-    if (!h->goal) rc = head_chunk(h, n, d_r + t0, nullptr, nullptr, ps);
-    else rc = head_chunk(h, n, nullptr, nullptr, tmp.feats + t0 * h->feat_dim, ps);
-    cudaEventRecord(h->ev_consumed[buf], ps);
+    cudaStreamWaitEvent(st, h->ev_copied[buf], 0);
+    if ((rc = encode_chunk(h, h->stage_dev[buf], n, (int64_t)frame_bytes, st)) != ARP_OK) break;
+    if (!h->goal) rc = head_chunk(h, n, d_r + t0, nullptr, nullptr, st);
+    else rc = head_chunk(h, n, nullptr, nullptr, tmp.feats + t0 * h->feat_dim, st);
+    cudaEventRecord(h->ev_consumed[buf], st);
   }
+  if (staged) stager.stop();
   if (rc == ARP_OK && h->goal) rc = goal_rewards(h, tmp, T, d_off, n_eps, d_r, st);
   if (rc == ARP_OK) rc = scan_launch(h, d_r, T, d_off, n_eps, F, 1.0f, d_g, d_rs, d_gs, st);
   if (rc == ARP_OK) {

@@ -136,9 +136,11 @@ ARP_API int arp_label(ArpHandle* h, const uint8_t* ob_dev, int64_t T, int64_t ro
               const int64_t* ep_offsets_dev, int32_t n_eps, int32_t num_frames, float* reward_dev, float* rtg_dev,
               float* reward_stacked_dev, float* rtg_stacked_dev, void* stream);
 
-/* Same contract with HOST buffers (pageable or pinned): frames are streamed to the device in chunks on
- * a copy stream, overlapped with compute, and the four outputs are copied back. This is the call a
- * drop-in label_reward() makes per image key; it synchronises before returning. */
+/* Same contract with HOST buffers: frames are streamed to the device in chunks on a copy stream, overlapped with
+ * compute, and the four outputs are copied back. Pinned (cudaHostAlloc / cudaHostRegister) frames are copied directly;
+ * pageable ones — e.g. a pointer into the memory-mapped dataset itself — are gathered by a few internal worker threads
+ * through a ring of pinned slots, so page-cache reads, PCIe and the GPU overlap and ONE call can cover a whole shard.
+ * This is the call a drop-in label_reward() makes per image key; it synchronises before returning. */
 ARP_API int arp_label_host(ArpHandle* h, const uint8_t* ob_host, int64_t T, int64_t row_stride_bytes,
                    const int64_t* ep_offsets_host, int32_t n_eps, int32_t num_frames, float* reward_host,
                    float* rtg_host, float* reward_stacked_host, float* rtg_stacked_host);
