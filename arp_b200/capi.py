@@ -32,7 +32,7 @@ EXPORTS = (
     "arp_set_text", "arp_label", "arp_label_host", "arp_compute_reward", "arp_encode_image", "arp_decode_only",
     "arp_scan_only", "arp_gemm_bf16", "arp_layernorm_bf16", "arp_attention", "arp_launch_count",
     "arp_profile_begin", "arp_profile_end", "arp_online_reward", "arp_preprocess_rtgs",
-    "arp_quantile_f32", "arp_encode_taps_chw", "arp_operand_dtype", "arp_ln_gemm",
+    "arp_quantile_f32", "arp_encode_taps_chw", "arp_operand_dtype", "arp_ln_gemm", "arp_resid_gemm_stats",
 )
 PROFILE_CLASSES = ("gemm", "attention", "layernorm", "decode", "head", "scan", "other")
 
@@ -93,6 +93,7 @@ def load_library() -> C.CDLL:
     lib.arp_scan_only.argtypes = [vp, vp, i64, vp, i32, i32, f32, vp, vp, vp, vp]
     lib.arp_gemm_bf16.argtypes = [vp, vp, vp, vp, i32, i64, i32, i32, vp, vp, i32, vp]
     lib.arp_ln_gemm.argtypes = [vp, vp, vp, vp, vp, vp, vp, i64, i32, i32, vp]
+    lib.arp_resid_gemm_stats.argtypes = [vp, vp, vp, vp, vp, vp, i64, i32, i32, vp]
     lib.arp_layernorm_bf16.argtypes = [vp, vp, vp, vp, vp, i64, vp]
     lib.arp_attention.argtypes = [vp, vp, vp, i32, i32, vp]
     lib.arp_launch_count.argtypes = [vp]
@@ -364,6 +365,20 @@ class Engine:
                                             DT_F32 if out_dtype == torch.float32 else _TORCH_DT[op], M, N, K, _ptr(bias),
                                             _ptr(resid), act, _stream_ptr(self.device)))
         return out
+
+    def resid_gemm_stats(self, a: torch.Tensor, w: torch.Tensor, bias: torch.Tensor, x: torch.Tensor):
+        """Test hook: x (16-bit, updated IN PLACE) += a w^T + bias in the GEMM epilogue; returns stats [M,2] =
+        (rstd, -mean*rstd) of the updated rows."""
+        op = operand_dtype()
+        assert x.dtype == op and x.is_contiguous() and x.device == self.device
+        a, w = a.to(op).contiguous(), w.to(op).contiguous()
+        bias = bias.to(self.device, torch.float32).contiguous()
+        M, K = a.shape
+        N = w.shape[0]
+        stats = torch.empty(M, 2, device=self.device, dtype=torch.float32)
+        self._check(self._lib.arp_resid_gemm_stats(self._h, _ptr(a), _ptr(w), _ptr(bias), _ptr(x), _ptr(stats), M, N, K,
+                                                   _stream_ptr(self.device)))
+        return stats
 
     def ln_gemm(self, x: torch.Tensor, gamma, beta, w: torch.Tensor, bias: torch.Tensor, act: int = ACT_NONE) -> torch.Tensor:
         """Test hook: act(LayerNorm(x) W^T + bias) with the LayerNorm folded into the GEMM (default-path ln_1/ln_2).

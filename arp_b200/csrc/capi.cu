@@ -6,6 +6,7 @@
 #include <cuda_runtime.h>
 
 #include <atomic>
+#include <chrono>
 #include <cmath>
 #include <condition_variable>
 #include <cstdarg>
@@ -112,6 +113,12 @@ struct ArpHandle {
   // epilogues from per-row moments — no LayerNorm kernels, no normalised copy, no fp32 read-modify-write.
   // false (ARP_PREC_F32RESID): fp32 x, standalone LayerNorm kernels writing a 16-bit copy (round 1's pipeline).
   bool resid16 = true;
+  // Row statistics of the 16-bit stream. true (default): x is updated by 16-bit TMA reduce-add and a small kernel re-reads
+  // it for (rstd, -mean*rstd). false (ARP_FUSED_STATS=1, measurement switch): the residual GEMM adds in registers and
+  // emits the statistics itself (gemm_tcgen05.cuh G2_RESID_STATS) — correct, but measured SLOWER on B200 (out_proj 208 ->
+  // 265 us, c_proj 712 -> 860 us at 1024 frames against 2 x 52 us of statistics kernels saved): the row-per-lane loads of
+  // x cost ~50 us of LSU time and the row-block-major tile order it needs makes c_proj re-read A from DRAM.
+  bool stats_kernel = true;
   // Snake order: consecutive kernels of a chunk walk the rows in opposite directions, so each starts on what its
   // predecessor wrote last (the tail of a 150-600 MB activation is still in the 126 MB L2). ARP_SNAKE=0 disables.
   bool snake = true;
@@ -518,6 +525,7 @@ extern "C" int arp_create(const ArpConfig* cfg, ArpHandle** out) {
   h->resid16 = cfg->precision == ARP_PREC_BF16;
   if (const char* e = getenv("ARP_SNAKE")) h->snake = atoi(e) != 0;            // measurement switches, both exact:
   if (const char* e = getenv("ARP_PRUNE_LAST")) h->prune_last = atoi(e) != 0;  // kernel order / last-block pruning
+  if (const char* e = getenv("ARP_FUSED_STATS")) h->stats_kernel = atoi(e) == 0;
   h->grid = DEC_OUT / cfg->patch;
   h->tokens = h->grid * h->grid + 1;
   h->kp = 3 * cfg->patch * cfg->patch;
@@ -606,7 +614,7 @@ extern "C" int arp_create(const ArpConfig* cfg, ArpHandle** out) {
   G2_ATTR(bf16, ACT_NONE, G2_STORE) G2_ATTR(bf16, ACT_QUICKGELU, G2_STORE) G2_ATTR(bf16, ACT_RELU, G2_STORE)
   G2_ATTR(float, ACT_NONE, G2_STORE) G2_ATTR(float, ACT_QUICKGELU, G2_STORE) G2_ATTR(float, ACT_RELU, G2_STORE)
   G2_ATTR(float, ACT_NONE, G2_REDUCE) G2_ATTR(bf16, ACT_NONE, G2_REDUCE)
-  G2_ATTR(bf16, ACT_NONE, G2_LNFOLD) G2_ATTR(bf16, ACT_QUICKGELU, G2_LNFOLD)
+  G2_ATTR(bf16, ACT_NONE, G2_LNFOLD) G2_ATTR(bf16, ACT_QUICKGELU, G2_LNFOLD) G2_ATTR(bf16, ACT_NONE, G2_RESID_STATS)
 #undef G2_ATTR
   CREATE_TRY(set_smem(h, attention_tc_kernel<197>, AtcCfg<197>::SMEM_BYTES));
   CREATE_TRY(set_smem(h, attention_tc_kernel<50>, AtcCfg<50>::SMEM_BYTES));
@@ -802,7 +810,8 @@ struct LnFoldArgs { const float2* stats; const float* svec; const float* cvec; }
 // computed and dropped by the clipped store).
 static int launch_gemm(ArpHandle* h, const bf16* a, int64_t a_rows_alloc, const bf16* w, void* out, bool out_f32,
                        int act, int64_t M, int N, int K, int ldo, const float* bias, const void* resid, int ldr,
-                       const float* rowtab, int period, cudaStream_t st, const LnFoldArgs* fold = nullptr) {
+                       const float* rowtab, int period, cudaStream_t st, const LnFoldArgs* fold = nullptr,
+                       float2* stats_out = nullptr) {
   if (M <= 0) return ARP_OK;
   if (N % GEMM_BN || K % GEMM_BK) return fail(h, ARP_ERR_INVALID, "GEMM needs N %% 256 == 0 and K %% 64 == 0 (N=%d K=%d)", N, K);
   if (M > 0x7fffffff / 2) return fail(h, ARP_ERR_INVALID, "GEMM M too large");
@@ -819,6 +828,12 @@ static int launch_gemm(ArpHandle* h, const bf16* a, int64_t a_rows_alloc, const 
       return fail(h, ARP_ERR_INVALID, "bad LayerNorm-folded GEMM");
     g.ln_stats = fold->stats; g.svec = fold->svec; g.cvec = fold->cvec; g.bias = nullptr;   // cvec carries the bias
   }
+  // stats_out: the 16-bit in-place residual update done in registers, emitting the updated rows' LayerNorm statistics
+  const bool resid_stats = stats_out != nullptr;
+  if (resid_stats) {
+    if (!reduce || resid != out || out_f32 || ldr != ldo || rowtab || !bias) return fail(h, ARP_ERR_INVALID, "bad residual+statistics GEMM");
+    g.resid = static_cast<const bf16*>(resid); g.ldr = ldr; g.stats_out = stats_out; g.eps = 1e-5f;
+  }
   if (reduce) {
     if (act != ACT_NONE) return fail(h, ARP_ERR_INVALID, "the residual epilogue takes no activation");
     if (resid != out)  // out-of-place residual (test hook only): seed the output, then accumulate into it
@@ -829,8 +844,10 @@ static int launch_gemm(ArpHandle* h, const bf16* a, int64_t a_rows_alloc, const 
   ARP_TRY(get_tmap(h, a, (uint64_t)a_rows_alloc, (uint64_t)K, (uint64_t)K, GEMM_BM, &ta));
   ARP_TRY(get_tmap(h, w, (uint64_t)N, (uint64_t)K, (uint64_t)K, GEMM_BN / cg, &tb));
   ARP_TRY(get_tmap(h, out, (uint64_t)M, (uint64_t)N, (uint64_t)ldo, 32, &to, out_f32 ? 32 : 64, out_f32 ? 4 : 2));
-  const int tiles = (int)((M + GEMM_BM * cg - 1) / (GEMM_BM * cg)) * (N / GEMM_BN);
-  const int grid = std::min(tiles * cg, kNumSMs / cg * cg);
+  const int row_blocks = (int)((M + GEMM_BM * cg - 1) / (GEMM_BM * cg));
+  const int tiles = row_blocks * (N / GEMM_BN);
+  // resid_stats: a cluster owns whole row blocks (all column tiles), so the grid is bounded by the row blocks
+  const int grid = std::min((resid_stats ? row_blocks : tiles) * cg, kNumSMs / cg * cg);
   const int smem = G2Cfg<cg>::SMEM_BYTES;
   ProfScope prof(h, PC_GEMM, 2.0 * (double)M * N * K,
                  (double)M * K * 2 + (double)N * K * 2 + (double)M * N * osz * (reduce ? 2 : 1), st);
@@ -839,6 +856,8 @@ static int launch_gemm(ArpHandle* h, const bf16* a, int64_t a_rows_alloc, const 
   if (fold) {
     if (act == ACT_NONE) G2_LAUNCH(bf16, ACT_NONE, G2_LNFOLD);
     else G2_LAUNCH(bf16, ACT_QUICKGELU, G2_LNFOLD);
+  } else if (resid_stats) {
+    G2_LAUNCH(bf16, ACT_NONE, G2_RESID_STATS);
   } else if (reduce) {
     if (out_f32) G2_LAUNCH(float, ACT_NONE, G2_REDUCE);
     else G2_LAUNCH(bf16, ACT_NONE, G2_REDUCE);
@@ -1026,13 +1045,15 @@ static int encode_blocks_r16(ArpHandle* h, int64_t n, cudaStream_t st) {
     ARP_TRY(launch_gemm(h, ws.x16, Mcap, L.w_qkv_fold, ws.qkv, false, ACT_NONE, M, 3 * W, W, 3 * W, nullptr, nullptr, 0,
                         nullptr, 0, st, &f_qkv));
     ARP_TRY(launch_attention(h, ws.qkv, ws.attn, (int)n, h->tokens, st, Mcap));
-    ARP_TRY(launch_gemm(h, ws.attn, Mcap, L.w_out, ws.x16, false, ACT_NONE, M, W, W, W, L.b_out, ws.x16, W, nullptr, 0, st));
-    ARP_TRY(launch_row_moments(h, ws.x16, ws.stats, M, st));
+    // x += out_proj(attn) in place; the epilogue also leaves ln_2's row statistics in ws.stats
+    ARP_TRY(launch_gemm(h, ws.attn, Mcap, L.w_out, ws.x16, false, ACT_NONE, M, W, W, W, L.b_out, ws.x16, W, nullptr, 0, st,
+                        nullptr, h->stats_kernel ? nullptr : ws.stats));
+    if (h->stats_kernel) ARP_TRY(launch_row_moments(h, ws.x16, ws.stats, M, st));
     ARP_TRY(launch_gemm(h, ws.x16, Mcap, L.w_fc_fold, ws.hid, false, ACT_QUICKGELU, M, 4 * W, W, 4 * W, nullptr, nullptr,
                         0, nullptr, 0, st, &f_fc));
     ARP_TRY(launch_gemm(h, ws.hid, Mcap, L.w_proj, ws.x16, false, ACT_NONE, M, W, 4 * W, W, L.b_proj, ws.x16, W, nullptr,
-                        0, st));
-    if (l + 1 < c.layers) ARP_TRY(launch_row_moments(h, ws.x16, ws.stats, M, st));
+                        0, st, nullptr, h->stats_kernel ? nullptr : ws.stats));   // ... and the next block's ln_1 statistics
+    if (h->stats_kernel && l + 1 < c.layers) ARP_TRY(launch_row_moments(h, ws.x16, ws.stats, M, st));
     gather_taps(h, ws.x16, n, l, st);
   }
   if (!ws.cls_compact) {   // prune_last off: hand the heads compact fp32 class-token rows all the same
@@ -1490,10 +1511,19 @@ struct HostStager {
   }
   void start() {
     done.assign(subs->size(), 0);
-    const int nw = (int)std::min<size_t>(STG_WORKERS, subs->size());
+    int want = STG_WORKERS;
+    if (const char* e = getenv("ARP_STAGER_THREADS")) want = std::max(1, std::min(STG_SLOTS, atoi(e)));
+    const int nw = (int)std::min<size_t>(want, subs->size());
     for (int i = 0; i < nw; ++i) threads.emplace_back([this] { run(); });
   }
-  void wait(int64_t j) { std::unique_lock<std::mutex> lk(mu); cv.wait(lk, [&] { return done[j] != 0; }); }
+  double waited_s = 0.0;       // time the consumer spent waiting for the workers (ARP_STAGER_DEBUG prints it)
+  void wait(int64_t j) {
+    std::unique_lock<std::mutex> lk(mu);
+    if (done[j]) return;
+    const auto t0 = std::chrono::steady_clock::now();
+    cv.wait(lk, [&] { return done[j] != 0; });
+    waited_s += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+  }
   void stop() { abort.store(true); for (auto& t : threads) t.join(); threads.clear(); }
 };
 
@@ -1567,7 +1597,12 @@ extern "C" int arp_label_host(ArpHandle* h, const uint8_t* ob_host, int64_t T, i
     else rc = head_chunk(h, n, nullptr, nullptr, tmp.feats + t0 * h->feat_dim, st);
     cudaEventRecord(h->ev_consumed[buf], st);
   }
-  if (staged) stager.stop();
+  if (staged) {
+    stager.stop();
+    if (getenv("ARP_STAGER_DEBUG"))
+      fprintf(stderr, "arp_label_host: %lld frames staged in %zu sub-chunks, consumer waited %.3f s for the gather threads\n",
+              (long long)T, subs.size(), stager.waited_s);
+  }
   if (rc == ARP_OK && h->goal) rc = goal_rewards(h, tmp, T, d_off, n_eps, d_r, st);
   if (rc == ARP_OK) rc = scan_launch(h, d_r, T, d_off, n_eps, F, 1.0f, d_g, d_rs, d_gs, st);
   if (rc == ARP_OK) {
@@ -1755,6 +1790,15 @@ extern "C" int arp_gemm_bf16(ArpHandle* h, const void* a_dev, const void* w_dev,
   return launch_gemm(h, static_cast<const bf16*>(a_dev), M, static_cast<const bf16*>(w_dev), out_dev,
                      out_dtype == ARP_F32, act, M, N, K, N, bias_dev, resid_dev, N, nullptr, 0,
                      static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int arp_resid_gemm_stats(ArpHandle* h, const void* a_dev, const void* w_dev, const float* bias_dev, void* x_dev,
+                                    float* stats_dev, int64_t M, int32_t N, int32_t K, void* stream) {
+  if (!h || !a_dev || !w_dev || !bias_dev || !x_dev || !stats_dev) return fail(h, ARP_ERR_INVALID, "null argument");
+  ARP_CUDA(h, cudaSetDevice(h->cfg.device));
+  return launch_gemm(h, static_cast<const bf16*>(a_dev), M, static_cast<const bf16*>(w_dev), x_dev, false, ACT_NONE, M, N, K,
+                     N, bias_dev, x_dev, N, nullptr, 0, static_cast<cudaStream_t>(stream), nullptr,
+                     reinterpret_cast<float2*>(stats_dev));
 }
 
 extern "C" int arp_ln_gemm(ArpHandle* h, const void* x_dev, const float* gamma_dev, const float* beta_dev,

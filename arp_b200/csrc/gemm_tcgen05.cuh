@@ -16,6 +16,13 @@
 //     L2): x += tile without ever reading x into the SM. Works on the fp32 stream (precision mode 2, and the
 //     class-token rows of the pruned last block) and on the 16-bit stream of the default path
 //     (x = fl16(x + fl16(acc + bias)) — the same two roundings the reference's own fp16 CUDA route performs).
+//   * G2_RESID_STATS: the 16-bit residual update of the default path, x = fl16(x + acc + bias) with ONE rounding, done in
+//     registers: every lane prefetches its row's x values (16-byte loads issued before the accumulator is waited for),
+//     adds, stores through the same staging / TMA path — and accumulates the row's mean and centred second moment of
+//     the ROUNDED values on the way (two-pass per 64-column unit, Chan's merge across units). Each cluster owns whole
+//     row blocks (all N/256 column tiles back to back), so after the last column tile the two warps that share a row
+//     combine their halves and write (rstd, -mean*rstd) — the LayerNorm the next GEMM folds in. No moments kernel, no
+//     second pass over x.
 //   * G2_LNFOLD: LayerNorm applied algebraically. A is the RAW residual stream, W' = W·diag(gamma), and
 //       LN(x) W^T + b = rstd_r · acc − rstd_r·mean_r · svec_n + cvec_n,   svec = W'·1,  cvec = W·beta + b,
 //     with (rstd_r, −mean_r·rstd_r) read per row from `ln_stats` (row_moments kernels, layernorm.cuh). No
@@ -27,7 +34,7 @@
 namespace arp {
 
 enum GemmAct : int { ACT_NONE = 0, ACT_QUICKGELU = 1, ACT_RELU = 2 };
-enum G2Mode : int { G2_STORE = 0, G2_REDUCE = 1, G2_LNFOLD = 2 };
+enum G2Mode : int { G2_STORE = 0, G2_REDUCE = 1, G2_LNFOLD = 2, G2_RESID_STATS = 3 };
 
 struct GemmArgs {
   int M, N, K;
@@ -41,6 +48,10 @@ struct GemmArgs {
   const float2* ln_stats;  // G2_LNFOLD: [M] (rstd, -mean*rstd) of the rows of A
   const float* svec;       // G2_LNFOLD: [N]
   const float* cvec;       // G2_LNFOLD: [N]
+  const op_t* resid;       // G2_RESID_STATS: the 16-bit residual stream [M, ldr] (aliases out: updated in place)
+  int ldr;
+  float2* stats_out;       // G2_RESID_STATS: [M] (rstd, -mean*rstd) of the updated rows
+  float eps;
 };
 
 constexpr int GEMM_BM = 128;
@@ -67,7 +78,7 @@ struct G2Cfg {
   static constexpr int B_ROWS = GEMM_BN / CG;                       // W rows staged per CTA
   static constexpr int STAGE_BYTES = GEMM_A_BYTES + B_ROWS * GEMM_BK * 2;
   static constexpr int STAGES = CG == 1 ? 3 : 6;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + G2_STAGING_BYTES + 1024 + 256;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + G2_STAGING_BYTES + 1024 + 256 + 1024;   // + row-stat exchange
 };
 
 template <typename OutT, int ACT, int CG, int MODE>
@@ -85,6 +96,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   uint64_t* tfull_bar = bars + 2 * STAGES;
   uint64_t* tempty_bar = tfull_bar + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  float2* stat_part = reinterpret_cast<float2*>(staging + G2_STAGING_BYTES + 256);   // [4 quarters][32 rows]
+  static_assert(MODE != G2_RESID_STATS || sizeof(OutT) == 2, "G2_RESID_STATS updates the 16-bit residual stream");
 
   // warp index through a shuffle: provably warp-uniform, so the MMA / TMA issue paths keep their descriptors in
   // uniform registers (back-to-back UTCHMMA instead of an ELECT / R2UR.BROADCAST loop before every instruction)
@@ -98,6 +111,24 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   const int num_n = args.N / GEMM_BN;
   const int num_tiles = num_m * num_n;
   const int num_kb = args.K / GEMM_BK;
+  // Iteration -> tile. Default: tiles go round-robin over the clusters in n-inner order (the clusters that share an A row
+  // block run in the same wave). G2_RESID_STATS: a cluster owns whole row blocks, all num_n column tiles back to back, so
+  // a row's statistics never leave the CTA that updates it.
+  const int my_tiles = MODE == G2_RESID_STATS
+                           ? (cluster_id < num_m ? (num_m - cluster_id + num_clusters - 1) / num_clusters * num_n : 0)
+                           : (cluster_id < num_tiles ? (num_tiles - cluster_id + num_clusters - 1) / num_clusters : 0);
+  auto tile_coords = [&](int it, int& m_blk, int& n_blk) {
+    if (MODE == G2_RESID_STATS) {
+      const int mb = cluster_id + (it / num_n) * num_clusters;
+      m_blk = args.reverse ? num_m - 1 - mb : mb;
+      n_blk = it % num_n;
+    } else {
+      const int tile = cluster_id + it * num_clusters;
+      const int tile_o = args.reverse ? num_tiles - 1 - tile : tile;
+      m_blk = tile_o / num_n;
+      n_blk = tile_o % num_n;
+    }
+  };
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_a);
@@ -130,9 +161,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     if (elect_one()) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
-        const int tile_o = args.reverse ? num_tiles - 1 - tile : tile;
-        const int m_blk = tile_o / num_n, n_blk = tile_o % num_n;
+      for (int it = 0; it < my_tiles; ++it) {
+        int m_blk, n_blk;
+        tile_coords(it, m_blk, n_blk);
         const int a_row = (m_blk * CG + rank) * GEMM_BM;
         const int b_row = n_blk * GEMM_BN + rank * Cfg::B_ROWS;
         for (int kb = 0; kb < num_kb; ++kb) {
@@ -162,7 +193,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+      for (int it = 0; it < my_tiles; ++it) {
         mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * GEMM_BN;
@@ -202,11 +233,35 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     int acc = 0;
     uint32_t acc_phase = 0;
     const int sw = lane & 7;
-    for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
-      const int tile_o = args.reverse ? num_tiles - 1 - tile : tile;
-      const int m_blk = tile_o / num_n, n_blk = tile_o % num_n;
+    float st_n = 0.f, st_mean = 0.f, st_m2 = 0.f;   // G2_RESID_STATS: running count / mean / centred 2nd moment of this lane's row
+    for (int it = 0; it < my_tiles; ++it) {
+      int m_blk, n_blk;
+      tile_coords(it, m_blk, n_blk);
       const int row0 = (m_blk * CG + rank) * GEMM_BM + quarter * 32;
       const int row = row0 + lane;
+      // G2_RESID_STATS: this lane's 128 residual values of the tile, requested before the accumulator is waited for
+      uint4 xo[MODE == G2_RESID_STATS ? 16 : 1];
+      if (MODE == G2_RESID_STATS) {
+        const uint4* xp = reinterpret_cast<const uint4*>(args.resid + static_cast<size_t>(row) * args.ldr + n_blk * GEMM_BN + half * 128);
+#ifdef ARP_DBG_NOLDG
+#pragma unroll
+        for (int c = 0; c < 16; ++c) xo[c] = make_uint4(0u, 0u, 0u, 0u);
+#else
+#pragma unroll
+        for (int c = 0; c < 16; ++c) xo[c] = row < args.M ? xp[c] : make_uint4(0u, 0u, 0u, 0u);
+#endif
+#ifndef ARP_DBG_NOPREFETCH
+        // the NEXT tile's residual values are pulled into L2 now, a whole tile period ahead: under a saturated HBM the
+        // loaded DRAM latency is several microseconds, more than this warp can cover between two of its own tiles
+        if (lane == 0 && it + 1 < my_tiles) {
+          int m2, n2;
+          tile_coords(it + 1, m2, n2);
+          const int r2 = (m2 * CG + rank) * GEMM_BM + quarter * 32, c2 = n2 * GEMM_BN + half * 128;
+          tma_prefetch_l2_2d(&tmap_out, c2, r2);
+          tma_prefetch_l2_2d(&tmap_out, c2 + 64, r2);
+        }
+#endif
+      }
       float ln_rstd = 1.f, ln_rm = 0.f;        // G2_LNFOLD: the row's 1/std and -mean/std (in flight under the MMAs)
       if (MODE == G2_LNFOLD && row < args.M) {
         const float2 p = __ldg(args.ln_stats + row);
@@ -218,9 +273,76 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       const uint32_t taddr = tmem_base + acc * GEMM_BN + half * 128 + (static_cast<uint32_t>(quarter * 32) << 16);
       const float* tab_row =
           args.rowtab ? args.rowtab + static_cast<size_t>(row % args.period) * args.N : nullptr;
-#pragma unroll 1
+#pragma unroll(MODE == G2_RESID_STATS ? UNITS : 1)
       for (int u = 0; u < UNITS; ++u) {
         const int n0 = n_blk * GEMM_BN + half * 128 + u * UNIT_COLS;
+        if (MODE == G2_RESID_STATS) {
+          // 64-column unit in two 32-column halves (register budget: 168 with ten warps per CTA):
+          //   x_new = fl16(x_old + acc + bias); statistics of the ROUNDED values — what is stored and what the next GEMM
+          //   multiplies — two-pass per half (they are all in registers), Chan's merge into the running (n, mean, M2)
+          if (lane == 0) tma_store_wait_read<0>();     // the staging buffer was last read by the previous unit's store
+          __syncwarp();
+          uint4* srow = reinterpret_cast<uint4*>(sbuf + lane * 128);
+#pragma unroll
+          for (int hh = 0; hh < 2; ++hh) {
+            uint32_t r[32];
+            tmem_ld_32x32(taddr + u * 64 + hh * 32, r);
+            tmem_ld_wait();
+            if (u == UNITS - 1 && hh == 1) {
+              tc_fence_before();
+              __syncwarp();
+              if (lane == 0) {
+                if (CG == 1) mbar_arrive_relaxed(&tempty_bar[acc]);
+                else mbar_arrive_cluster_relaxed(acc ? tempty_leader1 : tempty_leader0);
+              }
+            }
+            float y[32];
+            float s1 = 0.f;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+              const uint4 q = xo[u * 8 + hh * 4 + c];
+              const uint32_t w4[4] = {q.x, q.y, q.z, q.w};
+              const float4 b0 = __ldg(reinterpret_cast<const float4*>(args.bias + n0 + hh * 32 + 8 * c));
+              const float4 b1 = __ldg(reinterpret_cast<const float4*>(args.bias + n0 + hh * 32 + 8 * c + 4));
+              const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+              uint32_t pk[4];
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const op2_t xh = *reinterpret_cast<const op2_t*>(&w4[e]);
+                const op2_t yh = floats_to_op2(__uint_as_float(r[8 * c + 2 * e]) + bb[2 * e] + op_to_float(xh.x),
+                                               __uint_as_float(r[8 * c + 2 * e + 1]) + bb[2 * e + 1] + op_to_float(xh.y));
+                pk[e] = *reinterpret_cast<const uint32_t*>(&yh);
+                y[8 * c + 2 * e] = op_to_float(yh.x);
+                y[8 * c + 2 * e + 1] = op_to_float(yh.y);
+                s1 += y[8 * c + 2 * e] + y[8 * c + 2 * e + 1];
+              }
+              srow[(hh * 4 + c) ^ sw] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+            }
+#ifdef ARP_DBG_NOSTATS
+            st_mean += s1;
+            continue;
+#endif
+            const float mu = s1 * (1.0f / 32.0f);
+            float m2 = 0.f;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const float d = y[j] - mu;
+              m2 = fmaf(d, d, m2);
+            }
+            const float nt = st_n + 32.0f;
+            const float d = mu - st_mean, f = __fdividef(32.0f, nt);
+            st_mean = fmaf(d, f, st_mean);
+            st_m2 += fmaf(d * d, st_n * f, m2);
+            st_n = nt;
+          }
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_2d(&tmap_out, sbuf, n0, row0);
+            tma_store_commit();
+          }
+          continue;
+        }
         float v[UNIT_COLS];
         {
           uint32_t r[32];
@@ -300,6 +422,21 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
           else tma_store_2d(&tmap_out, sbuf, n0, row0);
           tma_store_commit();
         }
+      }
+      if (MODE == G2_RESID_STATS && n_blk == num_n - 1) {
+        // the row block is complete: the warp of the other column half holds the other N/2 columns of the same rows
+        if (half == 1) stat_part[quarter * 32 + lane] = make_float2(st_mean, st_m2);
+        named_bar_sync(1, G2_EPI_WARPS * 32);
+        if (half == 0) {
+          const float2 o = stat_part[quarter * 32 + lane];
+          const float d = o.x - st_mean;
+          const float mean = fmaf(d, 0.5f, st_mean);
+          const float var = (st_m2 + o.y + d * d * (0.5f * st_n)) / (2.0f * st_n);
+          const float rstd = rsqrtf(var + args.eps);
+          if (row < args.M) args.stats_out[row] = make_float2(rstd, -mean * rstd);
+        }
+        named_bar_sync(1, G2_EPI_WARPS * 32);     // stat_part is rewritten at the end of the next row block
+        st_n = st_mean = st_m2 = 0.f;
       }
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }

@@ -177,7 +177,17 @@ class CLIPMultiscaleAdapter(nn.Module):
         self.num_clip_layers = self.clip_model.text_layers                    # :59 (text tower depth; 12 = vision depth too)
         self.visual_dim = self.clip_model.vision_width
         self.text_dim = self.clip_model.text_width
-        self.augmentation = augmentation if augmentation is not None else (lambda x: x)
+        # The reference ALWAYS jitters training images: kornia ColorJitter(0.1, 0.2, 0.2, 0.03, same_on_batch=True, p=0.75)
+        # (clip_multiscale_adapter.py:24-36, :128-129). Same default here when kornia is importable; otherwise identity,
+        # and preprocess(train=True) warns once so that a fine-tuning run does not silently lose its augmentation.
+        self._augmentation_missing = False
+        if augmentation is None:
+            try:
+                from kornia.augmentation import ColorJitter  # type: ignore
+                augmentation = nn.Sequential(ColorJitter(0.1, 0.2, 0.2, 0.03, same_on_batch=True, p=0.75))
+            except Exception:  # noqa: BLE001 — kornia is the caller's dependency (not in this image)
+                augmentation, self._augmentation_missing = (lambda x: x), True
+        self.augmentation = augmentation
         self.device = device
         self.use_vip_loss, self.use_id_loss = use_vip_loss, use_id_loss
         L = self.num_clip_layers
@@ -214,6 +224,12 @@ class CLIPMultiscaleAdapter(nn.Module):
         if H != 224 and W != 224:                  # pinned torchvision 0.12: bilinear, align_corners=False, no antialias
             x = F.interpolate(x, size=(224, 224), mode="bilinear", align_corners=False, antialias=False)
         if train:
+            if self._augmentation_missing:
+                import warnings
+                warnings.warn("CLIPMultiscaleAdapter.preprocess(train=True): kornia is not importable, so the reference's "
+                              "ColorJitter augmentation is NOT applied; pass augmentation= explicitly (identity: "
+                              "augmentation=lambda x: x)", RuntimeWarning, stacklevel=2)
+                self._augmentation_missing = False
             with torch.no_grad():
                 x = self.augmentation(x)
         x = x / 255.0

@@ -261,6 +261,9 @@ def label_reward(
     rank = dist.get_rank() if distributed else 0
     world = dist.get_world_size() if distributed else 1
 
+    import time
+    _t = [("start", time.perf_counter())]
+    _mark = lambda name: _t.append((name, time.perf_counter()))  # noqa: E731 — ARP_TIMING=1 prints the phase breakdown
     # Every rank READS through its own read-only handle; rank 0 reopens the container for writing only after all
     # readers have closed (HDF5 file locking refuses a writer next to readers, and a reader next to the writer).
     g = open_store(data_path, "r")
@@ -276,6 +279,7 @@ def label_reward(
         target_keys = [f"{model_type}_reward", f"{model_type}_pos_rtg"]
         if inst_type != "none":
             target_keys = [f"{x}_{inst_type}" for x in target_keys]
+        _mark("open + episode index")
         try:
             H, W = g[image_keys[0]].shape[-3:-1]
             if use_crop:
@@ -283,24 +287,14 @@ def label_reward(
             labeler = RewardLabeler(model_type, text, (int(H), int(W)), model_ckpt_dir=model_ckpt_dir,
                                     clip_state_dict=clip_state_dict, arch=arch, use_crop=use_crop, reduce=reduce,
                                     max_batch=max_batch, device=device, precision=precision, tokenizer=tokenizer)
+            _mark("engine + weights + text tower")
             for img_key in image_keys:
                 ds = g[img_key]
                 side = g.get(img_key + SIDECAR_SUFFIX)
                 if side is not None and (side.shape[0] != ds.shape[0] or tuple(side.shape[1:]) != tuple(ds.shape[2:])):
                     side = None                      # stale or foreign sidecar: fall back to the stacked dataset
-                parts_r, parts_g = [], []
-                for s_lo, s_hi in _slabs(off, e_lo, e_hi, slab_frames):
-                    lo, hi = int(off[s_lo]), int(off[s_hi])
-                    if hi <= lo:
-                        continue
-                    r, _, rs, gs = labeler.label_slab(_rows_array(ds, lo, hi, side), off[s_lo:s_hi + 1] - lo, num_frames)
-                    if labeler.goal:
-                        rs, gs = _goal_float64(r, off[s_lo:s_hi + 1] - lo, num_frames)
-                    parts_r.append(rs)
-                    parts_g.append(gs)
-                empty = np.zeros((0, num_frames), np.float64 if labeler.goal else np.float32)
-                results[img_key] = (np.concatenate(parts_r) if parts_r else empty,
-                                    np.concatenate(parts_g) if parts_g else empty)
+                results[img_key] = _label_rows(labeler, ds, side, off, e_lo, e_hi, num_frames, slab_frames)
+            _mark("label (decode + encoder + head + scan, H2D / D2H)")
         except Exception as e:  # noqa: BLE001 — reported to every rank below, then re-raised
             failure = e
         if distributed:
@@ -326,6 +320,7 @@ def label_reward(
         if labeler is not None:
             labeler.close()
         g.close()
+    _mark("gather + close")
     if distributed:
         dist.barrier()                                   # every reader has closed
     if rank == 0:
@@ -335,8 +330,62 @@ def label_reward(
                 _write_labels(g, img_key, target_keys, results[img_key], off, n_eps, len_data, num_frames)
         finally:
             g.close()
+    _mark("write labels")
     if distributed:
         dist.barrier()
+    if os.environ.get("ARP_TIMING", "0") not in ("", "0") and rank == 0:
+        print("[arp_b200] label_reward phases: " + ", ".join(f"{b[0]} {b[1] - a[1]:.3f} s" for a, b in zip(_t[:-1], _t[1:]))
+              + f"; total {_t[-1][1] - _t[0][1]:.3f} s", flush=True)
+
+
+def _label_rows(labeler, ds, side, off, e_lo: int, e_hi: int, num_frames: int, slab_frames: int):
+    """(reward_stacked, rtg_stacked) for episodes [e_lo, e_hi). A memory-mapped container is handed to the library in ONE
+    call (a strided pointer into the file mapping; the native stager overlaps page-cache reads, PCIe and compute). A
+    container that has to be read through its API (h5py: chunked, gzip) is read slab by slab on a reader thread, one slab
+    ahead of the GPU."""
+    empty = np.zeros((0, num_frames), np.float64 if labeler.goal else np.float32)
+    lo_all, hi_all = int(off[e_lo]), int(off[e_hi])
+    if hi_all <= lo_all:
+        return empty, empty
+
+    def finish(r, rs, gs, rel_off):
+        return _goal_float64(r, rel_off, num_frames) if labeler.goal else (rs, gs)
+
+    src = side if side is not None else ds
+    arr = getattr(src, "array", None)
+    if arr is not None and arr.flags.c_contiguous:
+        rel = off[e_lo:e_hi + 1] - lo_all
+        r, _, rs, gs = labeler.label_slab(arr[lo_all:hi_all], rel, num_frames)
+        return finish(r, rs, gs, rel)
+
+    import threading
+    slabs = [(a, b) for a, b in _slabs(off, e_lo, e_hi, slab_frames) if off[b] > off[a]]
+    box = {}
+
+    def read(i):
+        a, b = slabs[i]
+        try:
+            box[i] = _rows_array(ds, int(off[a]), int(off[b]), side)
+        except Exception as e:  # noqa: BLE001 — re-raised on the consumer side
+            box[i] = e
+
+    parts_r, parts_g = [], []
+    th = threading.Thread(target=read, args=(0,))
+    th.start()
+    for i, (a, b) in enumerate(slabs):
+        th.join()
+        rows = box.pop(i)
+        if isinstance(rows, Exception):
+            raise rows
+        if i + 1 < len(slabs):
+            th = threading.Thread(target=read, args=(i + 1,))
+            th.start()
+        rel = off[a:b + 1] - off[a]
+        r, _, rs, gs = labeler.label_slab(rows, rel, num_frames)
+        rs, gs = finish(r, rs, gs, rel)
+        parts_r.append(rs)
+        parts_g.append(gs)
+    return (np.concatenate(parts_r) if parts_r else empty), (np.concatenate(parts_g) if parts_g else empty)
 
 
 def _goal_float64(r: np.ndarray, ep_off: np.ndarray, num_frames: int):

@@ -46,9 +46,17 @@ def reward_key(store, image_key: str, vl_type: str) -> str:
     raise KeyError(f"no reward dataset for {image_key!r} / {vl_type!r}")
 
 
+def _numpy_index_dtype(dtype=np.float32):
+    """The float type np.quantile computes its virtual index / gamma / lerp in for a `dtype` sample: numpy >= 2 casts q to
+    the sample's dtype (float32 here); numpy 1.x — the reference pins numpy==1.23.5 — keeps q a Python float, so the
+    index, gamma and the interpolation are float64 and the float32 result is the rounding of that. Parity is with the
+    numpy of the environment the loader runs in; `numpy_semantics` ("1" / "2") overrides the detection."""
+    return dtype if int(np.__version__.split(".")[0]) >= 2 else np.float64
+
+
 def linear_quantile_plan(n: int, q: float, dtype=np.float32):
     """Where np.quantile(x, q) (method 'linear') looks in the sorted sample: (k_lo, k_hi, gamma), with numpy's own
-    expressions and dtypes (numpy >= 2: q is cast to the array's float dtype, so the virtual index is computed in it)."""
+    expressions in the index dtype `dtype` (see _numpy_index_dtype)."""
     quant = np.asanyarray(q, dtype=dtype)
     virtual = np.asanyarray((n - 1) * quant)
     prev = np.floor(virtual)
@@ -62,12 +70,14 @@ def linear_quantile_plan(n: int, q: float, dtype=np.float32):
 
 
 def lerp_like_numpy(a, b, t):
-    """numpy.lib._function_base_impl._lerp for scalars: a + (b-a)*t, or b - (b-a)*(1-t) when t >= 0.5."""
-    a, b = np.float32(a), np.float32(b)
+    """numpy's _lerp for scalars: a + (b-a)*t, or b - (b-a)*(1-t) when t >= 0.5 — in t's dtype (float32 under numpy >= 2,
+    float64 under numpy 1.x where the float32 order statistics are promoted by the float64 gamma), rounded to float32."""
+    wt = np.asarray(t).dtype.type
+    a, b = wt(np.float32(a)), wt(np.float32(b))
     d = np.subtract(b, a)
     out = np.add(a, d * t)
     if t >= 0.5:
-        out = np.subtract(b, d * (1 - t), dtype=np.float32, casting="unsafe")
+        out = np.subtract(b, d * (1 - t), dtype=wt, casting="unsafe")
     return np.float32(out)
 
 
@@ -81,7 +91,7 @@ class RtgInfo:
 
 
 def preprocess_rtgs(rewards: dict, traj_idx, num_frames: int, env_name: str, use_normalize: bool,
-                    engine: "capi.Engine | None" = None, device: int = 0) -> RtgInfo:
+                    engine: "capi.Engine | None" = None, device: int = 0, numpy_semantics: "str | None" = None) -> RtgInfo:
     """rewards: image_key -> per-frame reward (float32 [T], i.e. column -1 of the reward dataset).
     traj_idx: the loader's h5_file_traj_idx ([0] + done indices + 1, data_procgen.py:118-121)."""
     own = engine is None
@@ -101,7 +111,8 @@ def preprocess_rtgs(rewards: dict, traj_idx, num_frames: int, env_name: str, use
         else:
             allv = torch.cat([v.reshape(-1) for v in stacks.values()]) if len(stacks) > 1 else next(iter(stacks.values()))
             n = allv.numel()
-            k_lo, k_hi, gamma = linear_quantile_plan(n, 0.9, np.float32)
+            idx_dtype = {None: _numpy_index_dtype(np.float32), "1": np.float64, "2": np.float32}[numpy_semantics]
+            k_lo, k_hi, gamma = linear_quantile_plan(n, 0.9, idx_dtype)
             lo, hi = engine.order_statistics(allv, k_lo, k_hi)
             rtg = lerp_like_numpy(lo, hi, gamma)                                # np.quantile(..., 0.9) (:173)
         return_to_go = rtg // 100 * 100

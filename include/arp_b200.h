@@ -21,7 +21,7 @@
 extern "C" {
 #endif
 
-#define ARP_B200_ABI_VERSION 5   /* 3: + arp_encode_taps_chw, 4: + arp_operand_dtype, 5: + ARP_PREC_F32RESID, arp_ln_gemm */
+#define ARP_B200_ABI_VERSION 5   /* 3: + arp_encode_taps_chw, 4: + arp_operand_dtype, 5: + ARP_PREC_F32RESID, arp_ln_gemm, arp_resid_gemm_stats */
 
 #if defined(__GNUC__)
 #define ARP_API __attribute__((visibility("default")))
@@ -207,6 +207,12 @@ ARP_API int arp_scan_only(ArpHandle* h, const float* reward_dev, int64_t T, cons
  * stream is then updated in place by TMA reduce-add, fp32 or 16-bit); N % 256 == 0, K % 64 == 0. */
 ARP_API int arp_gemm_bf16(ArpHandle* h, const void* a_dev, const void* w_dev, void* out_dev, int32_t out_dtype, int64_t M,
                   int32_t N, int32_t K, const float* bias_dev, const void* resid_dev, int32_t act, void* stream);
+/* The default path's residual update: x[M,N] (operand format, in place) = fl16(x + A[M,K] W[N,K]^T + bias) done in the
+ * GEMM epilogue's registers, which also writes stats[M][2] = (rstd, -mean*rstd) of every updated row (eps 1e-5, moments
+ * of the ROUNDED values over all N columns) — the LayerNorm statistics the next GEMM folds in (out_proj -> ln_2, c_proj ->
+ * next ln_1). N % 256 == 0, K % 64 == 0; fp32 stats on the device. Test seam. */
+ARP_API int arp_resid_gemm_stats(ArpHandle* h, const void* a_dev, const void* w_dev, const float* bias_dev, void* x_dev,
+                         float* stats_dev, int64_t M, int32_t N, int32_t K, void* stream);
 /* out[M,N] = act(LayerNorm(x; gamma, beta) W^T + bias) with the LayerNorm FOLDED into the GEMM as on the default path
  * (ln_1 -> in_proj, ln_2 -> c_fc; openai/CLIP ResidualAttentionBlock): x [M,768] in the operand format is multiplied raw
  * by gamma-folded weights and the epilogue applies the row's (rstd, -mean*rstd). w fp32 [N,768], gamma / beta [768],

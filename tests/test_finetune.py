@@ -57,7 +57,8 @@ def make_model(meta, sd, clip_sd, device=None, precision="bf16"):
     from arp_b200.finetune import CLIPMultiscaleAdapter
     m = CLIPMultiscaleAdapter(clip_state_dict=clip_sd, arch=meta["arch"], use_discrete_action=True, action_dim=15,
                               use_vip_loss=True, use_id_loss=True, goal_conditioned=meta["goal_conditioned"],
-                              init="normal", precision=precision)
+                              init="normal", precision=precision,
+                              augmentation=lambda x: x)    # the goldens were made with kornia's random jitter stubbed to identity
     res = m.load_state_dict(sd, strict=True)          # the reference's checkpoint format, every key accounted for
     assert not res.missing_keys and not res.unexpected_keys
     return m.to(device) if device is not None else m

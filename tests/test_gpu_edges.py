@@ -133,3 +133,29 @@ def test_non_square_frames_are_refused_loudly(capi):
     with pytest.raises(capi.ArpError) as ei:
         capi.Engine(device=0, patch=16, in_h=48, in_w=80, max_batch=4)
     assert ei.value.code == capi.ARP_ERR_INVALID and "non-square" in str(ei.value)
+
+
+def test_label_host_pageable_stager_equals_pinned(capi):
+    """arp_label_host gathers pageable (e.g. memory-mapped) frames through its pinned ring with worker threads and copies
+    pinned frames directly; both must give the bits of the device entry point. Ragged on purpose: max_batch 100 is not a
+    multiple of the 64-frame staging slot, T = 457 is not a multiple of max_batch, rows are strided (F = 3)."""
+    from arp_b200.weights import random_clip_state_dict
+    e = capi.Engine(device=0, patch=32, in_h=64, in_w=64, max_batch=100)
+    e.load_state_dict(random_clip_state_dict("ViT-B/32", 0, "cuda"))
+    e.set_text(torch.nn.functional.normalize(torch.randn(1, 512), dim=1), 14.3)
+    rng = np.random.default_rng(3)
+    lens = rng.integers(1, 60, size=16)
+    off = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
+    T = int(off[-1]) + 5
+    ob = rng.integers(0, 256, size=(T, 3, 64, 64, 3), dtype=np.uint8)
+    pageable = e.label_host(ob, off, 4)
+    pinned_t = torch.from_numpy(ob).pin_memory()
+    pinned = e.label_host(pinned_t, off, 4)
+    dev = [t.cpu().numpy() for t in e.label(torch.from_numpy(ob).cuda(), torch.from_numpy(off), 4)]
+    n = int(off[-1])
+    for a, b, c in zip(pageable, pinned, dev):
+        assert np.array_equal(a[:n], b[:n]) and np.array_equal(a[:n], c[:n])
+    # twice in a row (ring slots and their events are reused across calls)
+    again = e.label_host(ob, off, 4)
+    assert all(np.array_equal(a[:n], b[:n]) for a, b in zip(pageable, again))
+    e.close()

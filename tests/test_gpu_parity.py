@@ -114,6 +114,33 @@ def test_gemm_16bit_residual_in_place(eng):
     assert float((x.float() - ref.float()).abs().mean()) < 1e-2 * ulp          # and almost every element is identical
 
 
+@pytest.mark.parametrize("M,K", [(197 * 80, 768), (197 * 40 + 3, 3072), (1, 64), (300, 768)])
+def test_residual_gemm_with_row_statistics(eng, M, K):
+    """out_proj / c_proj of the default path: x = fl16(x + a w^T + b) in the epilogue's registers (one rounding), plus
+    the updated rows' LayerNorm statistics (rstd, -mean*rstd) — against torch on the same 16-bit inputs. M spans several
+    row blocks per cluster (persistent loop, all three column tiles of a row block in one CTA) and a ragged tail."""
+    dev = eng.device
+    from arp_b200 import capi as _capi
+    op = _capi.operand_dtype()
+    g = torch.Generator(device=dev).manual_seed(M + K)
+    a = (torch.randn(M, K, device=dev, generator=g) * 0.5).to(op)
+    w = (torch.randn(768, K, device=dev, generator=g) * 0.03).to(op)
+    b = torch.randn(768, device=dev, generator=g) * 0.1
+    x0 = (torch.randn(M, 768, device=dev, generator=g) * 1.5 + 0.3).to(op)
+    x0[:, 7] += 30.0                                                     # an outlier channel, as in trained ViTs
+    x = x0.clone()
+    stats = eng.resid_gemm_stats(a, w, b, x)
+    ref = (x0.float() + a.float() @ w.float().t() + b).to(op)
+    ulp = 2.0 ** (-10 if op == torch.float16 else -7)
+    err = (x.float() - ref.float()).abs() / ref.float().abs().clamp_min(1.0)
+    assert float(err.max()) <= ulp and float((err > 0).float().mean()) < 3e-2      # summation order only
+    xs = x.float()                                                       # statistics are of the STORED values
+    mean, var = xs.mean(1), xs.var(1, unbiased=False)
+    rstd = torch.rsqrt(var + 1e-5)
+    assert float(((stats[:, 0] - rstd).abs() / rstd).max()) < 2e-5
+    assert float((stats[:, 1] + mean * rstd).abs().max()) < 2e-5 * float((mean * rstd).abs().max().clamp_min(1.0))
+
+
 @pytest.mark.parametrize("M,N,act", [(197 * 8, 2304, 0), (1003, 3072, 1), (1, 256, 0)])
 def test_layernorm_folded_gemm_vs_torch(eng, M, N, act):
     """act(LN(x) W^T + b) with LayerNorm applied algebraically in the GEMM epilogue (row moments + gamma-folded

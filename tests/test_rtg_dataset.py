@@ -60,14 +60,25 @@ def test_compute_scale_table():
 
 def test_quantile_plan_and_lerp_match_numpy():
     """The host half of the quantile (rank selection + interpolation) equals np.quantile given exact order statistics."""
-    from arp_b200.rtg_dataset import lerp_like_numpy, linear_quantile_plan
+    from arp_b200.rtg_dataset import _numpy_index_dtype, lerp_like_numpy, linear_quantile_plan
     rng = np.random.default_rng(0)
     for n in [1, 2, 3, 10, 11, 101, 6496, 100_003, 1_000_000]:
         x = (rng.standard_normal(n) * 50).astype(np.float32)
         s = np.sort(x)
         for q in (0.9, 0.5, 0.0, 1.0, 0.123):
-            k_lo, k_hi, g = linear_quantile_plan(n, q, np.float32)
-            assert lerp_like_numpy(s[k_lo], s[k_hi], g) == np.quantile(x, q), (n, q)
+            k_lo, k_hi, g = linear_quantile_plan(n, q, _numpy_index_dtype(np.float32))
+            assert lerp_like_numpy(s[k_lo], s[k_hi], g) == np.quantile(x, q), (n, q)       # the INSTALLED numpy's rule
+            # numpy 1.x (the reference pins 1.23.5): virtual index, gamma and the lerp in float64 — restated from
+            # numpy/lib/function_base.py @ v1.23.5 (_compute_virtual_index, _get_gamma, _lerp), result cast to float32
+            v = (n - 1) * q
+            lo = min(max(int(np.floor(v)), 0), n - 1)
+            hi = min(lo + 1, n - 1)
+            gam = np.float64(v - np.floor(v)) if 0 <= v < n - 1 else np.float64(0.0)
+            a, b = np.float64(s[lo]), np.float64(s[hi])
+            want = a + (b - a) * gam if gam < 0.5 else b - (b - a) * (1 - gam)
+            k_lo, k_hi, g = linear_quantile_plan(n, q, np.float64)
+            assert (k_lo, k_hi) == (lo, hi) or s[k_lo] == s[lo]
+            assert lerp_like_numpy(s[k_lo], s[k_hi], g) == np.float32(want), (n, q)
 
 
 def test_reward_key_alias():

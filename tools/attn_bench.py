@@ -1,4 +1,4 @@
-"""Dev tool: correctness + timing of the attention kernels (ARP_ATTN_IMPL=1 mma.sync, 2 tcgen05)."""
+"""Dev tool: correctness + timing of the tcgen05 / TMEM attention kernel."""
 import os
 import sys
 from pathlib import Path
@@ -10,7 +10,7 @@ sys.path.insert(0, str(ROOT))
 from arp_b200 import capi  # noqa: E402
 
 dev = torch.device("cuda", 0)
-impls = [int(x) for x in (sys.argv[1] if len(sys.argv) > 1 else "1,2").split(",")]
+impls = [2]
 
 
 def ref_attn(qkv, B, L):
@@ -19,7 +19,6 @@ def ref_attn(qkv, B, L):
 
 
 for impl in impls:
-    os.environ["ARP_ATTN_IMPL"] = str(impl)
     eng = capi.Engine(device=0, max_batch=8)
     print(f"==== attention impl {impl}", flush=True)
     for B, L, scale in ((1, 197, 1.5), (5, 197, 1.5), (7, 50, 1.5), (3, 197, 4.0), (40, 197, 0.5)):
@@ -36,7 +35,7 @@ for impl in impls:
             err, ok, per_frame = str(e), False, []
         print(f"  {'ok ' if ok else 'BAD'} B={B} L={L} scale={scale}: relerr {err} {per_frame}", flush=True)
     B, L = 512, 197
-    qkv = (torch.randn(B * L, 2304, device=dev) * 1.5).bfloat16()
+    qkv = (torch.randn(B * L, 2304, device=dev) * 1.5).to(capi.operand_dtype())   # no conversion inside the timed loop
     for _ in range(3):
         eng.attention(qkv, B, L)
     torch.cuda.synchronize()

@@ -1,4 +1,4 @@
-"""Dev tool: correctness + timing of the GEMM implementations (ARP_GEMM_IMPL=1|2|3) on the hot shapes."""
+"""Dev tool: correctness + timing of the tcgen05 GEMM on the hot shapes."""
 import os
 import sys
 from pathlib import Path
@@ -10,7 +10,7 @@ sys.path.insert(0, str(ROOT))
 from arp_b200 import capi  # noqa: E402
 
 dev = torch.device("cuda", 0)
-impls = [int(x) for x in (sys.argv[1] if len(sys.argv) > 1 else "1,2,3").split(",")]
+impls = [3]   # one implementation ships: CTA pairs (cta_group::2)
 M_HOT = 197 * 512
 
 
@@ -47,7 +47,6 @@ HOT = [("qkv", 2304, 768, 0, torch.bfloat16, False), ("fc_gelu", 3072, 768, 1, t
        ("proj_res", 768, 3072, 0, torch.float32, True), ("out_res", 768, 768, 0, torch.float32, True)]
 
 for impl in impls:
-    os.environ["ARP_GEMM_IMPL"] = str(impl)
     eng = capi.Engine(device=0, max_batch=8)
     print(f"==== impl {impl}", flush=True)
     ok_all = True
