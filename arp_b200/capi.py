@@ -32,7 +32,7 @@ EXPORTS = (
     "arp_set_text", "arp_label", "arp_label_host", "arp_compute_reward", "arp_encode_image", "arp_decode_only",
     "arp_scan_only", "arp_gemm_bf16", "arp_layernorm_bf16", "arp_attention", "arp_launch_count",
     "arp_profile_begin", "arp_profile_end", "arp_online_reward", "arp_preprocess_rtgs",
-    "arp_quantile_f32", "arp_encode_taps_chw", "arp_operand_dtype", "arp_ln_gemm", "arp_resid_gemm_stats",
+    "arp_quantile_f32", "arp_encode_taps_chw", "arp_operand_dtype", "arp_ln_gemm", "arp_resid_gemm_stats", "arp_label_file", "arp_wants_weight",
 )
 PROFILE_CLASSES = ("gemm", "attention", "layernorm", "decode", "head", "scan", "other")
 
@@ -83,6 +83,8 @@ def load_library() -> C.CDLL:
     lib.arp_set_text.argtypes = [vp, vp, i32, i32, f32, vp]
     lib.arp_label.argtypes = [vp, vp, i64, i64, vp, i32, i32, vp, vp, vp, vp, vp]
     lib.arp_label_host.argtypes = [vp, vp, i64, i64, vp, i32, i32, vp, vp, vp, vp]
+    lib.arp_label_file.argtypes = [vp, i32, i64, i64, i64, vp, i32, i32, vp, vp, vp, vp]
+    lib.arp_wants_weight.argtypes = [vp, C.c_char_p]
     lib.arp_compute_reward.argtypes = [vp, vp, i64, i64, vp, vp, vp]
     lib.arp_online_reward.argtypes = [vp, vp, i32, vp, vp, vp]
     lib.arp_preprocess_rtgs.argtypes = [vp, vp, i64, vp, i32, i32, i32, vp, vp, vp, vp, vp]
@@ -192,8 +194,11 @@ class Engine:
     def load_state_dict(self, state_dict, strict: bool = False) -> list[str]:
         """Feed every tensor of a CLIP (or adapter) state_dict; returns the names still missing."""
         for k, v in state_dict.items():
-            if torch.is_tensor(v):
-                self.set_weight(k, v, strict=strict)
+            if not torch.is_tensor(v):
+                continue
+            if not strict and not self._lib.arp_wants_weight(self._h, k.encode()):
+                continue                      # text tower / bookkeeping entries: never copied to the device
+            self.set_weight(k, v, strict=strict)
         return self.missing_weights()
 
     def missing_weights(self) -> list[str]:
@@ -259,6 +264,19 @@ class Engine:
         self._check(self._lib.arp_label_host(self._h, C.c_void_p(p), T, stride, C.c_void_p(off.ctypes.data),
                                              off.size - 1, num_frames, hp(out[0]), hp(out[1]), hp(out[2]),
                                              hp(out[3])))
+        return out
+
+    def label_file(self, fd: int, file_offset: int, T: int, row_stride_bytes: int, ep_offsets: np.ndarray,
+                   num_frames: int, out=None):
+        """arp_label_file: like label_host, the scored frame of row t read from `fd` at file_offset + t*row_stride_bytes."""
+        off = np.ascontiguousarray(ep_offsets, dtype=np.int64)
+        if out is None:
+            out = (np.empty(T, np.float32), np.empty(T, np.float32), np.empty((T, num_frames), np.float32),
+                   np.empty((T, num_frames), np.float32))
+        hp = lambda a: C.c_void_p(a.ctypes.data)  # noqa: E731
+        self._check(self._lib.arp_label_file(self._h, int(fd), int(file_offset), int(T), int(row_stride_bytes),
+                                             C.c_void_p(off.ctypes.data), off.size - 1, num_frames, hp(out[0]), hp(out[1]),
+                                             hp(out[2]), hp(out[3])))
         return out
 
     def compute_reward(self, ob: torch.Tensor, want_logits: bool = False):

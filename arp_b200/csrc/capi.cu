@@ -19,6 +19,9 @@
 #include <tuple>
 #include <vector>
 
+#include <cerrno>
+#include <unistd.h>
+
 #include "../../include/arp_b200.h"
 #include "attention_tc.cuh"
 #include "decode.cuh"
@@ -321,14 +324,32 @@ static int build_decode_tables(ArpHandle* h) {
       h->crop_left = (c.in_w - cs) / 2;
     }
   }
-  if (h->src_h <= 0 || h->src_w <= 0 || h->crop_top < 0 || h->crop_top + h->src_h > c.in_h)
-    return fail(h, ARP_ERR_INVALID, "bad crop geometry for %dx%d", c.in_h, c.in_w);
+  if (h->src_h <= 0 || h->src_w <= 0 || h->crop_top < 0 || h->crop_top + h->src_h > c.in_h || h->crop_left < 0 ||
+      h->crop_left + h->src_w > c.in_w)
+    return fail(h, ARP_ERR_INVALID, "bad crop geometry for %dx%d (a crop larger than the frame would be zero-padded by "
+                "torchvision; not supported)", c.in_h, c.in_w);
   if (c.preprocess == ARP_PRE_PIL_BICUBIC) {
-    // Resize(224) scales the SHORTER side to 224 keeping aspect; the path only meets square frames.
-    if (h->src_h != h->src_w) return fail(h, ARP_ERR_INVALID, "non-square frames are not supported (%dx%d)", h->src_h, h->src_w);
+    // Resize(224) scales the SHORTER side to 224 and the longer one to int(224 * long / short) (torchvision
+    // _compute_resized_output_size), then CenterCrop(224) takes the window at int(round((dim - 224) / 2.0)) — only on the
+    // no-crop route (label_reward.py:113-114); the use_crop route resizes its square crop and has no second crop (:96-97).
+    // Both passes are separable and a crop is a window, so the tables are the full-size tables restricted to the window.
+    int out_w = DEC_OUT, out_h = DEC_OUT;
+    if (h->src_w > h->src_h) out_w = static_cast<int>(static_cast<long long>(DEC_OUT) * h->src_w / h->src_h);
+    else if (h->src_h > h->src_w) out_h = static_cast<int>(static_cast<long long>(DEC_OUT) * h->src_h / h->src_w);
+    const int win_left = static_cast<int>(std::nearbyint((out_w - DEC_OUT) / 2.0));
+    const int win_top = static_cast<int>(std::nearbyint((out_h - DEC_OUT) / 2.0));
     std::vector<int> xm, xc, xk, ym, yc, yk;
-    pil_bicubic_tables(h->src_w, DEC_OUT, xm, xc, xk, h->h_ksize);
-    pil_bicubic_tables(h->src_h, DEC_OUT, ym, yc, yk, h->v_ksize);
+    {
+      std::vector<int> fm, fc, fk;
+      pil_bicubic_tables(h->src_w, out_w, fm, fc, fk, h->h_ksize);
+      xm.assign(fm.begin() + win_left, fm.begin() + win_left + DEC_OUT);
+      xc.assign(fc.begin() + win_left, fc.begin() + win_left + DEC_OUT);
+      xk.assign(fk.begin() + (size_t)win_left * h->h_ksize, fk.begin() + (size_t)(win_left + DEC_OUT) * h->h_ksize);
+      pil_bicubic_tables(h->src_h, out_h, fm, fc, fk, h->v_ksize);
+      ym.assign(fm.begin() + win_top, fm.begin() + win_top + DEC_OUT);
+      yc.assign(fc.begin() + win_top, fc.begin() + win_top + DEC_OUT);
+      yk.assign(fk.begin() + (size_t)win_top * h->v_ksize, fk.begin() + (size_t)(win_top + DEC_OUT) * h->v_ksize);
+    }
     if (h->h_ksize > 64 || h->v_ksize > 64) return fail(h, ARP_ERR_INVALID, "downscale factor too large");
     h->max_rows = 0;
     for (int b = 0; b < DEC_OUT / DEC_BAND; ++b) {
@@ -1481,6 +1502,8 @@ struct SubChunk { int64_t t0; int n; };   // rows [t0, t0+n) of the call, never 
 // gathers sub-chunk after sub-chunk into the pinned ring; the main thread consumes them in order
 struct HostStager {
   const uint8_t* src; int64_t stride; size_t frame_bytes; uint8_t* ring; cudaEvent_t* ev_slot; int device;
+  int fd = -1; int64_t fd_base = 0;          // fd >= 0: rows are pread() from a file (no page-table traffic) instead of src
+  std::atomic<int> io_error{0};
   const std::vector<SubChunk>* subs;
   std::atomic<int64_t> next{0}, issued{0};   // next task to start | sub-chunks whose H2D has been enqueued
   std::atomic<bool> abort{false};
@@ -1504,7 +1527,19 @@ struct HostStager {
       }
       const SubChunk& sc = (*subs)[j];
       uint8_t* dst = ring + (size_t)slot * STG_SUB * frame_bytes;
-      for (int f = 0; f < sc.n; ++f) memcpy(dst + (size_t)f * frame_bytes, src + (sc.t0 + f) * stride, frame_bytes);
+      if (fd < 0) {
+        for (int f = 0; f < sc.n; ++f) memcpy(dst + (size_t)f * frame_bytes, src + (sc.t0 + f) * stride, frame_bytes);
+      } else {
+        for (int f = 0; f < sc.n && !io_error.load(); ++f) {
+          size_t got = 0;
+          while (got < frame_bytes) {
+            const ssize_t r = pread(fd, dst + (size_t)f * frame_bytes + got, frame_bytes - got,
+                                    (off_t)(fd_base + (sc.t0 + f) * stride + (int64_t)got));
+            if (r <= 0) { io_error.store(r == 0 ? -1 : errno); break; }
+            got += (size_t)r;
+          }
+        }
+      }
       { std::lock_guard<std::mutex> lk(mu); done[j] = 1; }
       cv.notify_all();
     }
@@ -1527,12 +1562,13 @@ struct HostStager {
   void stop() { abort.store(true); for (auto& t : threads) t.join(); threads.clear(); }
 };
 
-extern "C" int arp_label_host(ArpHandle* h, const uint8_t* ob_host, int64_t T, int64_t row_stride_bytes,
-                              const int64_t* ep_offsets_host, int32_t n_eps, int32_t num_frames, float* reward_host,
-                              float* rtg_host, float* reward_stacked_host, float* rtg_stacked_host) {
+static int label_host_impl(ArpHandle* h, const uint8_t* ob_host, int fd, int64_t fd_offset, int64_t T,
+                           int64_t row_stride_bytes, const int64_t* ep_offsets_host, int32_t n_eps, int32_t num_frames,
+                           float* reward_host, float* rtg_host, float* reward_stacked_host, float* rtg_stacked_host) {
   if (!h) return ARP_ERR_INVALID;
   cudaStream_t st = h->own_stream;
-  ARP_TRY(check_ready(h, ob_host, T, row_stride_bytes, st));
+  if (fd >= 0 && fd_offset < 0) return fail(h, ARP_ERR_INVALID, "bad file offset");
+  ARP_TRY(check_ready(h, fd >= 0 ? reinterpret_cast<const uint8_t*>(h) : ob_host, T, row_stride_bytes, st));
   if (!ep_offsets_host || n_eps < 0) return fail(h, ARP_ERR_INVALID, "bad episode offsets");
   if (num_frames < 1 || num_frames > 64) return fail(h, ARP_ERR_INVALID, "num_frames must be in [1,64]");
   if (T == 0) return ARP_OK;
@@ -1555,7 +1591,7 @@ extern "C" int arp_label_host(ArpHandle* h, const uint8_t* ob_host, int64_t T, i
   const int64_t nchunks = (T + B - 1) / B;
   // pinned (or registered) caller memory goes to the device directly, one strided 2-D copy per chunk; pageable memory is
   // gathered through the pinned ring by worker threads
-  const bool staged = !host_ptr_is_pinned(ob_host);
+  const bool staged = fd >= 0 || !host_ptr_is_pinned(ob_host);
   std::vector<SubChunk> subs;
   HostStager stager;
   if (staged) {
@@ -1566,6 +1602,7 @@ extern "C" int arp_label_host(ArpHandle* h, const uint8_t* ob_host, int64_t T, i
     }
     stager.src = ob_host; stager.stride = row_stride_bytes; stager.frame_bytes = frame_bytes; stager.ring = h->pin_ring;
     stager.ev_slot = h->ev_slot; stager.device = c.device; stager.subs = &subs;
+    stager.fd = fd; stager.fd_base = fd_offset;
     stager.start();
   }
   // double-buffered: chunk i+1's frames (only the scored image of each row) cross PCIe while chunk i is encoded
@@ -1599,6 +1636,9 @@ extern "C" int arp_label_host(ArpHandle* h, const uint8_t* ob_host, int64_t T, i
   }
   if (staged) {
     stager.stop();
+    if (rc == ARP_OK && stager.io_error.load())
+      rc = fail(h, ARP_ERR_INVALID, "reading frames from the file failed (%s)",
+                stager.io_error.load() < 0 ? "unexpected end of file" : strerror(stager.io_error.load()));
     if (getenv("ARP_STAGER_DEBUG"))
       fprintf(stderr, "arp_label_host: %lld frames staged in %zu sub-chunks, consumer waited %.3f s for the gather threads\n",
               (long long)T, subs.size(), stager.waited_s);
@@ -1618,6 +1658,28 @@ extern "C" int arp_label_host(ArpHandle* h, const uint8_t* ob_host, int64_t T, i
   cudaStreamSynchronize(h->copy_stream);
   cudaStreamSynchronize(st);
   return rc;
+}
+
+extern "C" int arp_label_host(ArpHandle* h, const uint8_t* ob_host, int64_t T, int64_t row_stride_bytes,
+                              const int64_t* ep_offsets_host, int32_t n_eps, int32_t num_frames, float* reward_host,
+                              float* rtg_host, float* reward_stacked_host, float* rtg_stacked_host) {
+  return label_host_impl(h, ob_host, -1, 0, T, row_stride_bytes, ep_offsets_host, n_eps, num_frames, reward_host, rtg_host,
+                         reward_stacked_host, rtg_stacked_host);
+}
+
+extern "C" int arp_label_file(ArpHandle* h, int32_t fd, int64_t file_offset, int64_t T, int64_t row_stride_bytes,
+                              const int64_t* ep_offsets_host, int32_t n_eps, int32_t num_frames, float* reward_host,
+                              float* rtg_host, float* reward_stacked_host, float* rtg_stacked_host) {
+  if (fd < 0) return fail(h, ARP_ERR_INVALID, "bad file descriptor");
+  return label_host_impl(h, nullptr, fd, file_offset, T, row_stride_bytes, ep_offsets_host, n_eps, num_frames, reward_host,
+                         rtg_host, reward_stacked_host, rtg_stacked_host);
+}
+
+extern "C" int arp_wants_weight(const ArpHandle* h, const char* name) {
+  if (!h || !name) return 0;
+  std::string key(name);
+  if (key.compare(0, 11, "clip_model.") == 0) key = key.substr(11);
+  return h->slots.find(key) != h->slots.end() ? 1 : 0;
 }
 
 // ------------------------------------------------------------------------------------------------

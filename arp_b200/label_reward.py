@@ -168,6 +168,10 @@ class RewardLabeler:
         Returns host (reward[T], rtg[T], reward_stacked[T,F], rtg_stacked[T,F])."""
         return self.engine.label_host(ob, ep_offsets, num_frames)
 
+    def label_file(self, fd: int, file_offset: int, T: int, row_stride_bytes: int, ep_offsets: np.ndarray, num_frames: int):
+        """Same, the scored frame of row t read by the library from `fd` at file_offset + t*row_stride_bytes."""
+        return self.engine.label_file(fd, file_offset, T, row_stride_bytes, ep_offsets, num_frames)
+
     def close(self):
         self.engine.close()
 
@@ -352,9 +356,22 @@ def _label_rows(labeler, ds, side, off, e_lo: int, e_hi: int, num_frames: int, s
         return _goal_float64(r, rel_off, num_frames) if labeler.goal else (rs, gs)
 
     src = side if side is not None else ds
+    rel = off[e_lo:e_hi + 1] - lo_all
+    fsrc = src.file_source() if hasattr(src, "file_source") and hasattr(labeler, "label_file") else None
+    if fsrc is not None:
+        # rows contiguous in a file: the library preads the scored frame of every row itself (arp_label_file)
+        path, base = fsrc
+        frame = int(np.prod(src.shape[-3:]))
+        stride = frame * (src.shape[1] if len(src.shape) == 5 else 1)
+        first = base + lo_all * stride + (stride - frame)            # last stacked frame of row lo_all
+        fd = os.open(path, os.O_RDONLY)
+        try:
+            r, _, rs, gs = labeler.label_file(fd, first, hi_all - lo_all, stride, rel, num_frames)
+        finally:
+            os.close(fd)
+        return finish(r, rs, gs, rel)
     arr = getattr(src, "array", None)
     if arr is not None and arr.flags.c_contiguous:
-        rel = off[e_lo:e_hi + 1] - lo_all
         r, _, rs, gs = labeler.label_slab(arr[lo_all:hi_all], rel, num_frames)
         return finish(r, rs, gs, rel)
 

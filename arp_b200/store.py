@@ -46,6 +46,14 @@ class NpyDataset:
         """The underlying (memory-mapped) ndarray, C-contiguous — lets the caller pass raw pointers."""
         return self._a
 
+    def file_source(self):
+        """(path, byte offset of element [0, ...]) when the rows sit contiguously in the backing file — lets the labeler
+        hand the FILE to the native library (pread into pinned memory) instead of touching the mapping page by page."""
+        off = getattr(self._a, "offset", None)
+        if off is None or not self._a.flags.c_contiguous:
+            return None
+        return self._path, int(off)
+
     def resize(self, size, axis=None):
         new_shape = list(self._a.shape)
         if axis is None:

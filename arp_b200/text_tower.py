@@ -32,11 +32,17 @@ def _count_layers(sd, prefix: str) -> int:
 @torch.no_grad()
 def encode_text(sd: dict, tokens: torch.Tensor, device, prefix: str = ""):
     """Returns (text_features [n, embed_dim] un-normalised, eot_taps [n_layers][n, width])."""
+    emb_w = sd[prefix + "token_embedding.weight"]
+    if emb_w.device.type == "cpu":          # 49408 x 512 table (101 MB): look the few rows up where the table lives
+        x0 = emb_w[tokens.to("cpu").long()].to(device).float()
+    else:
+        x0 = emb_w[tokens.to(emb_w.device).long()].to(device).float()
     sd = {k[len(prefix):]: v.to(device).float() for k, v in sd.items()
-          if k.startswith(prefix) and not k[len(prefix):].startswith("visual.") and torch.is_tensor(v)}
+          if k.startswith(prefix) and torch.is_tensor(v) and
+          k[len(prefix):].startswith(("transformer.", "positional_embedding", "ln_final.", "text_projection"))}
     tok = tokens.to(device).long()
     n, ctx = tok.shape
-    x = sd["token_embedding.weight"][tok] + sd["positional_embedding"][:ctx]
+    x = x0 + sd["positional_embedding"][:ctx]
     width = x.shape[-1]
     heads = width // 64
     dh = width // heads

@@ -21,7 +21,7 @@
 extern "C" {
 #endif
 
-#define ARP_B200_ABI_VERSION 5   /* 3: + arp_encode_taps_chw, 4: + arp_operand_dtype, 5: + ARP_PREC_F32RESID, arp_ln_gemm, arp_resid_gemm_stats */
+#define ARP_B200_ABI_VERSION 5   /* 3: + arp_encode_taps_chw, 4: + arp_operand_dtype, 5: + ARP_PREC_F32RESID, arp_ln_gemm, arp_resid_gemm_stats, arp_label_file, arp_wants_weight */
 
 #if defined(__GNUC__)
 #define ARP_API __attribute__((visibility("default")))
@@ -109,6 +109,8 @@ ARP_API int arp_operand_dtype(void);
  * ---------------------------------------------------------------------------------------------- */
 ARP_API int arp_set_weight(ArpHandle* h, const char* name, const void* data, int32_t dtype, const int64_t* shape,
                    int32_t ndim, void* stream);
+/* 1 if `name` is a tensor this handle stores (so a caller can skip uploading the text tower etc.), else 0 */
+ARP_API int arp_wants_weight(const ArpHandle* h, const char* name);
 /* number of weights still missing for the configured head (0 = ready) */
 ARP_API int arp_missing_weights(const ArpHandle* h, char* names_out, int64_t names_cap);
 
@@ -142,6 +144,15 @@ ARP_API int arp_label(ArpHandle* h, const uint8_t* ob_dev, int64_t T, int64_t ro
  * through a ring of pinned slots, so page-cache reads, PCIe and the GPU overlap and ONE call can cover a whole shard.
  * This is the call a drop-in label_reward() makes per image key; it synchronises before returning. */
 ARP_API int arp_label_host(ArpHandle* h, const uint8_t* ob_host, int64_t T, int64_t row_stride_bytes,
+                   const int64_t* ep_offsets_host, int32_t n_eps, int32_t num_frames, float* reward_host,
+                   float* rtg_host, float* reward_stacked_host, float* rtg_stacked_host);
+
+/* Same call with the frames read straight from a FILE: row t's scored image is the frame_bytes (= in_h*in_w*3) at
+ * file_offset + t*row_stride_bytes of the open descriptor `fd` — an .npy memory-map's backing file, or a contiguous
+ * (unchunked, uncompressed) HDF5 dataset at its data offset. The gather threads pread() into the pinned ring, which
+ * avoids the page-table work of touching tens of GB through a mapping (faults on the way in, a long munmap on the way out).
+ * replaces g[img_key][traj, -1] (label_reward.py:268) for containers whose rows sit contiguously in a file. */
+ARP_API int arp_label_file(ArpHandle* h, int32_t fd, int64_t file_offset, int64_t T, int64_t row_stride_bytes,
                    const int64_t* ep_offsets_host, int32_t n_eps, int32_t num_frames, float* reward_host,
                    float* rtg_host, float* reward_stacked_host, float* rtg_stacked_host);
 

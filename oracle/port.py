@@ -83,35 +83,44 @@ def pil_coeffs(in_size: int, out_size: int):
     return bounds, kk
 
 
-def pil_resize_bicubic(img: np.ndarray, out_size: int = 224) -> np.ndarray:
-    """uint8 [H,W,3] -> uint8 [out,out,3]: horizontal pass to uint8, then vertical pass to uint8."""
+def pil_resize_bicubic(img: np.ndarray, out_size=224) -> np.ndarray:
+    """uint8 [H,W,3] -> uint8 [out_h,out_w,3] (out_size: int = square, or (out_h, out_w)): horizontal pass to uint8, then
+    vertical pass to uint8 (ImagingResample)."""
     H, W, _ = img.shape
+    out_h, out_w = (out_size, out_size) if isinstance(out_size, int) else out_size
 
-    def one_pass(src: np.ndarray, in_size: int) -> np.ndarray:      # resample along axis 1
-        bounds, kk = pil_coeffs(in_size, out_size)
-        out = np.empty((src.shape[0], out_size, src.shape[2]), np.uint8)
+    def one_pass(src: np.ndarray, in_size: int, n_out: int) -> np.ndarray:      # resample along axis 1
+        bounds, kk = pil_coeffs(in_size, n_out)
+        out = np.empty((src.shape[0], n_out, src.shape[2]), np.uint8)
         s = src.astype(np.int64)
-        for xx in range(out_size):
+        for xx in range(n_out):
             xmin, n = bounds[xx]
             acc = (1 << (PRECISION_BITS - 1)) + np.tensordot(s[:, xmin:xmin + n, :], kk[xx, :n], axes=([1], [0]))
             out[:, xx, :] = np.clip(acc >> PRECISION_BITS, 0, 255)
         return out
 
-    tmp = one_pass(img, W) if W != out_size else img
-    if H != out_size:
-        tmp = one_pass(tmp.transpose(1, 0, 2), H).transpose(1, 0, 2)
+    tmp = one_pass(img, W, out_w) if W != out_w else img
+    if H != out_h:
+        tmp = one_pass(tmp.transpose(1, 0, 2), H, out_h).transpose(1, 0, 2)
     return np.ascontiguousarray(tmp)
 
 
 def transform_restated(img: np.ndarray, use_crop: bool = False) -> np.ndarray:
-    """The reference `_transform` (label_reward.py:92-121) without PIL: fp32 [3,224,224]."""
+    """The reference `_transform` (label_reward.py:92-121) without PIL: fp32 [3,224,224]. Non-square frames: Resize(224)
+    takes the shorter side to 224 and the longer to int(224 * long / short); CenterCrop(224) (no-crop route only) takes
+    the window at int(round((dim - 224) / 2.0))."""
     if use_crop:
         cs = img.shape[-2] // 2                                     # CenterCrop(image_size // 2), :96,:104
         top = int(round((img.shape[0] - cs) / 2.0))
         left = int(round((img.shape[1] - cs) / 2.0))
         img = img[top:top + cs, left:left + cs]
-    u8 = pil_resize_bicubic(img, 224)
-    x = torch.from_numpy(u8).permute(2, 0, 1).to(torch.float32).div(255)      # ToTensor
+    H, W = img.shape[:2]
+    out_h, out_w = (224, int(224 * W / H)) if W >= H else (int(224 * H / W), 224)
+    u8 = pil_resize_bicubic(img, (out_h, out_w))
+    if not use_crop:
+        top, left = int(round((out_h - 224) / 2.0)), int(round((out_w - 224) / 2.0))
+        u8 = u8[top:top + 224, left:left + 224]
+    x = torch.from_numpy(np.ascontiguousarray(u8)).permute(2, 0, 1).to(torch.float32).div(255)      # ToTensor
     mean = torch.tensor(CLIP_MEAN, dtype=torch.float32).view(3, 1, 1)
     std = torch.tensor(CLIP_STD, dtype=torch.float32).view(3, 1, 1)
     return x.sub(mean).div(std).numpy()                                        # Normalize

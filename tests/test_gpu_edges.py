@@ -127,12 +127,12 @@ def test_decode_odd_frame_sizes_bit_exact(capi, size):
     e.close()
 
 
-def test_non_square_frames_are_refused_loudly(capi):
-    """Resize(224) on a non-square frame scales the shorter side and centre-crops; Procgen never produces one and the
-    decode kernel does not implement it: arp_create must say so instead of mis-scaling."""
+def test_crop_larger_than_the_frame_is_refused_loudly(capi):
+    """use_crop takes CenterCrop(W // 2) (label_reward.py:96,104): on a frame shorter than that torchvision would zero-pad;
+    the library refuses instead of inventing pixels."""
     with pytest.raises(capi.ArpError) as ei:
-        capi.Engine(device=0, patch=16, in_h=48, in_w=80, max_batch=4)
-    assert ei.value.code == capi.ARP_ERR_INVALID and "non-square" in str(ei.value)
+        capi.Engine(device=0, patch=16, in_h=40, in_w=128, use_crop=True, max_batch=4)
+    assert ei.value.code == capi.ARP_ERR_INVALID and "crop" in str(ei.value)
 
 
 def test_label_host_pageable_stager_equals_pinned(capi):
@@ -158,4 +158,39 @@ def test_label_host_pageable_stager_equals_pinned(capi):
     # twice in a row (ring slots and their events are reused across calls)
     again = e.label_host(ob, off, 4)
     assert all(np.array_equal(a[:n], b[:n]) for a, b in zip(pageable, again))
+    # and straight from a file (arp_label_file: the gather threads pread the last stacked frame of every row)
+    import os
+    import tempfile
+    with tempfile.TemporaryDirectory() as d:
+        path = os.path.join(d, "ob.npy")
+        np.save(path, ob)
+        mm = np.load(path, mmap_mode="r")
+        frame = 64 * 64 * 3
+        fd = os.open(path, os.O_RDONLY)
+        try:
+            filed = e.label_file(fd, mm.offset + 2 * frame, T, 3 * frame, off, 4)
+            with pytest.raises(capi.ArpError):                       # reading past the end of the file is an error, not zeros
+                e.label_file(fd, mm.offset + 2 * frame + 3 * frame * 10, T, 3 * frame, off, 4)
+        finally:
+            os.close(fd)
+    assert all(np.array_equal(a[:n], b[:n]) for a, b in zip(pageable, filed))
+    e.close()
+
+
+@pytest.mark.parametrize("H,W,crop", [(64, 96, False), (96, 64, False), (200, 256, False), (256, 200, False),
+                                      (224, 300, False), (100, 37, False), (128, 160, True)])
+def test_decode_non_square_frames_bit_exact(capi, H, W, crop):
+    """Resize(224) takes the SHORTER side to 224 and CenterCrop(224) cuts the longer one (label_reward.py:113-114); with
+    use_crop the square CenterCrop(W // 2) comes first (:96-97). Against the reference's own torchvision / PIL calls."""
+    from oracle import port
+    e = capi.Engine(device=0, patch=16, in_h=H, in_w=W, use_crop=crop, max_batch=4)
+    rng = np.random.default_rng(H * 1000 + W)
+    ob = rng.integers(0, 256, size=(3, 2, H, W, 3), dtype=np.uint8)
+    yy, xx = np.mgrid[0:H, 0:W]
+    ob[0, -1] = np.stack([yy * 255 // H, xx * 255 // W, (yy + xx) * 255 // (H + W)], -1).astype(np.uint8)
+    out = e.decode_only(torch.from_numpy(ob).cuda()).cpu().numpy()
+    tf = port.transform_pil(crop, W)
+    for t in range(3):
+        assert np.array_equal(out[t], tf(ob[t, -1]).numpy()), f"frame {t}"
+    assert np.array_equal(out[1], port.transform_restated(ob[1, -1], crop))
     e.close()
