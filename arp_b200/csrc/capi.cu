@@ -116,12 +116,12 @@ struct ArpHandle {
   // epilogues from per-row moments — no LayerNorm kernels, no normalised copy, no fp32 read-modify-write.
   // false (ARP_PREC_F32RESID): fp32 x, standalone LayerNorm kernels writing a 16-bit copy (round 1's pipeline).
   bool resid16 = true;
-  // Row statistics of the 16-bit stream. true (default): x is updated by 16-bit TMA reduce-add and a small kernel re-reads
-  // it for (rstd, -mean*rstd). false (ARP_FUSED_STATS=1, measurement switch): the residual GEMM adds in registers and
-  // emits the statistics itself (gemm_tcgen05.cuh G2_RESID_STATS) — correct, but measured SLOWER on B200 (out_proj 208 ->
-  // 265 us, c_proj 712 -> 860 us at 1024 frames against 2 x 52 us of statistics kernels saved): the row-per-lane loads of
-  // x cost ~50 us of LSU time and the row-block-major tile order it needs makes c_proj re-read A from DRAM.
-  bool stats_kernel = true;
+  // Row statistics of the 16-bit stream. false (default): the residual GEMMs add in registers and emit the statistics
+  // themselves (gemm_tcgen05.cuh G2_RESID_STATS; one rounding per update, no LayerNorm-class kernel inside the blocks).
+  // true (ARP_FUSED_STATS=0, measurement switch): x is updated by 16-bit TMA reduce-add and row_moments_kernel re-reads it.
+  // Measured on B200 (profiles/r02_stats_ab.json): isolated, c_proj 751 -> 731 us and out_proj 212 -> 255 us at 1024
+  // frames against 2 x 52 us of statistics kernels saved; inside the power-capped step the two forms are within 1 %.
+  bool stats_kernel = false;
   // Snake order: consecutive kernels of a chunk walk the rows in opposite directions, so each starts on what its
   // predecessor wrote last (the tail of a 150-600 MB activation is still in the 126 MB L2). ARP_SNAKE=0 disables.
   bool snake = true;
@@ -585,7 +585,7 @@ extern "C" int arp_create(const ArpConfig* cfg, ArpHandle** out) {
       if (cudaMemset(w.qkv, 0, M * 3 * W * sizeof(bf16)) != cudaSuccess) { h->err = "cudaMemset failed"; return bail(ARP_ERR_CUDA); }
       if (h->resid16) {
         CREATE_TRY(dev_alloc(h, &w.x16, M * W));
-        CREATE_TRY(dev_alloc(h, &w.stats, M));
+        CREATE_TRY(dev_alloc(h, &w.stats, M * (2 * W / 256)));   // up to 2*W/256 partials per row (G2_RESID_STATS)
         w.x = reinterpret_cast<float*>(w.qkv);   // fp32 [M, W] patch-embed output: 4MW of the 6MW bytes, dead before QKV
       } else {
         CREATE_TRY(dev_alloc(h, &w.x, M * W));
@@ -823,7 +823,7 @@ static cudaError_t launch_clustered(K kernel, int grid, int cg, int smem, cudaSt
 }
 
 // LayerNorm fold of one GEMM launch (gemm_tcgen05.cuh G2_LNFOLD): per-row statistics of A, per-column vectors of W
-struct LnFoldArgs { const float2* stats; const float* svec; const float* cvec; };
+struct LnFoldArgs { const float2* stats; const float* svec; const float* cvec; int nparts = 1; };   // nparts: GemmArgs::ln_nparts
 
 // out[M, N] (ldo) = epilogue(a[M, K] · w[N, K]^T). `resid` (same dtype as out; must alias out on the hot path): the
 // output is ACCUMULATED into it by TMA reduce-add. a_rows_alloc: rows addressable behind `a` (>= M); the descriptor
@@ -847,7 +847,8 @@ static int launch_gemm(ArpHandle* h, const bf16* a, int64_t a_rows_alloc, const 
   if (fold) {
     if (out_f32 || act == ACT_RELU || reduce || rowtab || !fold->stats || !fold->svec || !fold->cvec)
       return fail(h, ARP_ERR_INVALID, "bad LayerNorm-folded GEMM");
-    g.ln_stats = fold->stats; g.svec = fold->svec; g.cvec = fold->cvec; g.bias = nullptr;   // cvec carries the bias
+    g.ln_stats = fold->stats; g.ln_nparts = fold->nparts; g.svec = fold->svec; g.cvec = fold->cvec; g.eps = 1e-5f;
+    g.bias = nullptr;   // cvec carries the bias
   }
   // stats_out: the 16-bit in-place residual update done in registers, emitting the updated rows' LayerNorm statistics
   const bool resid_stats = stats_out != nullptr;
@@ -867,8 +868,7 @@ static int launch_gemm(ArpHandle* h, const bf16* a, int64_t a_rows_alloc, const 
   ARP_TRY(get_tmap(h, out, (uint64_t)M, (uint64_t)N, (uint64_t)ldo, 32, &to, out_f32 ? 32 : 64, out_f32 ? 4 : 2));
   const int row_blocks = (int)((M + GEMM_BM * cg - 1) / (GEMM_BM * cg));
   const int tiles = row_blocks * (N / GEMM_BN);
-  // resid_stats: a cluster owns whole row blocks (all column tiles), so the grid is bounded by the row blocks
-  const int grid = std::min((resid_stats ? row_blocks : tiles) * cg, kNumSMs / cg * cg);
+  const int grid = std::min(tiles * cg, kNumSMs / cg * cg);
   const int smem = G2Cfg<cg>::SMEM_BYTES;
   ProfScope prof(h, PC_GEMM, 2.0 * (double)M * N * K,
                  (double)M * K * 2 + (double)N * K * 2 + (double)M * N * osz * (reduce ? 2 : 1), st);
@@ -1052,19 +1052,25 @@ static int encode_blocks_r16(ArpHandle* h, int64_t n, cudaStream_t st) {
                                                                           ws.stats, (int)M, 1e-5f);
     h->launches++;
   }
+  // format of ws.stats: 1 = (rstd, -mean*rstd) per row (statistics kernels), 2*W/256 = partial (mean, M2) per 128 columns
+  // (written by the residual GEMM's epilogue)
+  int parts = 1;
+  const int gemm_parts = 2 * W / 256;
   for (int l = 0; l < c.layers; ++l) {
     const LayerW& L = h->layers[l];
     if (l == c.layers - 1 && h->prune_last) {
       // K and V of every token: rows [W, 3W) of in_proj, written at column W of the qkv buffer
-      const LnFoldArgs f_kv{ws.stats, L.s_qkv + W, L.c_qkv + W};
+      const LnFoldArgs f_kv{ws.stats, L.s_qkv + W, L.c_qkv + W, parts};
       ARP_TRY(launch_gemm(h, ws.x16, Mcap, L.w_qkv_fold + (size_t)W * W, ws.qkv + W, false, ACT_NONE, M, 2 * W, W, 3 * W,
                           nullptr, nullptr, 0, nullptr, 0, st, &f_kv));
       ARP_TRY(last_block_cls(h, L, ws.x16, n, st));
       break;
     }
-    const LnFoldArgs f_qkv{ws.stats, L.s_qkv, L.c_qkv}, f_fc{ws.stats, L.s_fc, L.c_fc};
+    const LnFoldArgs f_qkv{ws.stats, L.s_qkv, L.c_qkv, parts};
     ARP_TRY(launch_gemm(h, ws.x16, Mcap, L.w_qkv_fold, ws.qkv, false, ACT_NONE, M, 3 * W, W, 3 * W, nullptr, nullptr, 0,
                         nullptr, 0, st, &f_qkv));
+    parts = h->stats_kernel ? 1 : gemm_parts;
+    const LnFoldArgs f_fc{ws.stats, L.s_fc, L.c_fc, parts};
     ARP_TRY(launch_attention(h, ws.qkv, ws.attn, (int)n, h->tokens, st, Mcap));
     // x += out_proj(attn) in place; the epilogue also leaves ln_2's row statistics in ws.stats
     ARP_TRY(launch_gemm(h, ws.attn, Mcap, L.w_out, ws.x16, false, ACT_NONE, M, W, W, W, L.b_out, ws.x16, W, nullptr, 0, st,
@@ -1858,9 +1864,17 @@ extern "C" int arp_resid_gemm_stats(ArpHandle* h, const void* a_dev, const void*
                                     float* stats_dev, int64_t M, int32_t N, int32_t K, void* stream) {
   if (!h || !a_dev || !w_dev || !bias_dev || !x_dev || !stats_dev) return fail(h, ARP_ERR_INVALID, "null argument");
   ARP_CUDA(h, cudaSetDevice(h->cfg.device));
-  return launch_gemm(h, static_cast<const bf16*>(a_dev), M, static_cast<const bf16*>(w_dev), x_dev, false, ACT_NONE, M, N, K,
-                     N, bias_dev, x_dev, N, nullptr, 0, static_cast<cudaStream_t>(stream), nullptr,
-                     reinterpret_cast<float2*>(stats_dev));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int nparts = 2 * N / 256;
+  ARP_TRY(ensure_scratch(h, 0, (size_t)M * nparts * sizeof(float2) + 256));     // grows once; stream-ordered reuse
+  float2* parts = reinterpret_cast<float2*>(h->scratch[0]);
+  ARP_TRY(launch_gemm(h, static_cast<const bf16*>(a_dev), M, static_cast<const bf16*>(w_dev), x_dev, false, ACT_NONE, M, N, K,
+                      N, bias_dev, x_dev, N, nullptr, 0, st, nullptr, parts));
+  // the merge the consuming GEMM's epilogue performs, as a kernel (test seam only)
+  merge_row_stats_kernel<<<(unsigned)((M + 255) / 256), 256, 0, st>>>(parts, nparts, reinterpret_cast<float2*>(stats_dev), (int)M, 1e-5f);
+  h->launches++;
+  ARP_CUDA(h, cudaGetLastError());
+  return ARP_OK;
 }
 
 extern "C" int arp_ln_gemm(ArpHandle* h, const void* x_dev, const float* gamma_dev, const float* beta_dev,

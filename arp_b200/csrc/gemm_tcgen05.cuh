@@ -17,12 +17,12 @@
 //     class-token rows of the pruned last block) and on the 16-bit stream of the default path
 //     (x = fl16(x + fl16(acc + bias)) — the same two roundings the reference's own fp16 CUDA route performs).
 //   * G2_RESID_STATS: the 16-bit residual update of the default path, x = fl16(x + acc + bias) with ONE rounding, done in
-//     registers: every lane prefetches its row's x values (16-byte loads issued before the accumulator is waited for),
-//     adds, stores through the same staging / TMA path — and accumulates the row's mean and centred second moment of
-//     the ROUNDED values on the way (two-pass per 64-column unit, Chan's merge across units). Each cluster owns whole
-//     row blocks (all N/256 column tiles back to back), so after the last column tile the two warps that share a row
-//     combine their halves and write (rstd, -mean*rstd) — the LayerNorm the next GEMM folds in. No moments kernel, no
-//     second pass over x.
+//     registers: the warp requests its 32x128-byte tile of x with fully coalesced 16-byte loads BEFORE it waits for the
+//     accumulator, turns it into the row-per-lane layout through its staging buffer, adds, and stores through the same
+//     staging / TMA path — accumulating the mean and centred second moment of the ROUNDED values of its 128 columns on the
+//     way (two-pass per 32 columns, Chan's merge). Each warp writes one partial (mean, M2) per row and tile; the
+//     LayerNorm-folding GEMM that consumes x merges the 2·N/256 partials of a row in its epilogue. No statistics kernel, no
+//     second pass over x, deterministic (every partial has exactly one writer).
 //   * G2_LNFOLD: LayerNorm applied algebraically. A is the RAW residual stream, W' = W·diag(gamma), and
 //       LN(x) W^T + b = rstd_r · acc − rstd_r·mean_r · svec_n + cvec_n,   svec = W'·1,  cvec = W·beta + b,
 //     with (rstd_r, −mean_r·rstd_r) read per row from `ln_stats` (row_moments kernels, layernorm.cuh). No
@@ -45,12 +45,14 @@ struct GemmArgs {
   int period;
   int reverse;             // walk the tiles from the last row block to the first (snake order across kernels, so a
                            // kernel starts on the rows its predecessor wrote last — still in L2)
-  const float2* ln_stats;  // G2_LNFOLD: [M] (rstd, -mean*rstd) of the rows of A
+  const float2* ln_stats;  // G2_LNFOLD: ln_nparts == 1: [M] (rstd, -mean*rstd) of the rows of A (row_moments kernels);
+                           //            ln_nparts  > 1: [M, ln_nparts] partial (mean, M2), each over 128 columns (G2_RESID_STATS)
+  int ln_nparts;
   const float* svec;       // G2_LNFOLD: [N]
   const float* cvec;       // G2_LNFOLD: [N]
   const op_t* resid;       // G2_RESID_STATS: the 16-bit residual stream [M, ldr] (aliases out: updated in place)
   int ldr;
-  float2* stats_out;       // G2_RESID_STATS: [M] (rstd, -mean*rstd) of the updated rows
+  float2* stats_out;       // G2_RESID_STATS: [M, 2*N/256] partial (mean, M2) of the updated rows, one per 128 columns
   float eps;
 };
 
@@ -78,7 +80,7 @@ struct G2Cfg {
   static constexpr int B_ROWS = GEMM_BN / CG;                       // W rows staged per CTA
   static constexpr int STAGE_BYTES = GEMM_A_BYTES + B_ROWS * GEMM_BK * 2;
   static constexpr int STAGES = CG == 1 ? 3 : 6;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + G2_STAGING_BYTES + 1024 + 256 + 1024;   // + row-stat exchange
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + G2_STAGING_BYTES + 1024 + 256;
 };
 
 template <typename OutT, int ACT, int CG, int MODE>
@@ -96,7 +98,6 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   uint64_t* tfull_bar = bars + 2 * STAGES;
   uint64_t* tempty_bar = tfull_bar + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
-  float2* stat_part = reinterpret_cast<float2*>(staging + G2_STAGING_BYTES + 256);   // [4 quarters][32 rows]
   static_assert(MODE != G2_RESID_STATS || sizeof(OutT) == 2, "G2_RESID_STATS updates the 16-bit residual stream");
 
   // warp index through a shuffle: provably warp-uniform, so the MMA / TMA issue paths keep their descriptors in
@@ -111,23 +112,14 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   const int num_n = args.N / GEMM_BN;
   const int num_tiles = num_m * num_n;
   const int num_kb = args.K / GEMM_BK;
-  // Iteration -> tile. Default: tiles go round-robin over the clusters in n-inner order (the clusters that share an A row
-  // block run in the same wave). G2_RESID_STATS: a cluster owns whole row blocks, all num_n column tiles back to back, so
-  // a row's statistics never leave the CTA that updates it.
-  const int my_tiles = MODE == G2_RESID_STATS
-                           ? (cluster_id < num_m ? (num_m - cluster_id + num_clusters - 1) / num_clusters * num_n : 0)
-                           : (cluster_id < num_tiles ? (num_tiles - cluster_id + num_clusters - 1) / num_clusters : 0);
+  // Iteration -> tile: tiles go round-robin over the clusters in n-inner order, so the clusters that share an A row block
+  // run in the same wave and A comes out of L2 for all but the first of them.
+  const int my_tiles = cluster_id < num_tiles ? (num_tiles - cluster_id + num_clusters - 1) / num_clusters : 0;
   auto tile_coords = [&](int it, int& m_blk, int& n_blk) {
-    if (MODE == G2_RESID_STATS) {
-      const int mb = cluster_id + (it / num_n) * num_clusters;
-      m_blk = args.reverse ? num_m - 1 - mb : mb;
-      n_blk = it % num_n;
-    } else {
-      const int tile = cluster_id + it * num_clusters;
-      const int tile_o = args.reverse ? num_tiles - 1 - tile : tile;
-      m_blk = tile_o / num_n;
-      n_blk = tile_o % num_n;
-    }
+    const int tile = cluster_id + it * num_clusters;
+    const int tile_o = args.reverse ? num_tiles - 1 - tile : tile;
+    m_blk = tile_o / num_n;
+    n_blk = tile_o % num_n;
   };
 
   if (warp == 0 && lane == 0) {
@@ -233,24 +225,22 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     int acc = 0;
     uint32_t acc_phase = 0;
     const int sw = lane & 7;
-    float st_n = 0.f, st_mean = 0.f, st_m2 = 0.f;   // G2_RESID_STATS: running count / mean / centred 2nd moment of this lane's row
     for (int it = 0; it < my_tiles; ++it) {
       int m_blk, n_blk;
       tile_coords(it, m_blk, n_blk);
       const int row0 = (m_blk * CG + rank) * GEMM_BM + quarter * 32;
       const int row = row0 + lane;
-      // G2_RESID_STATS: this lane's 128 residual values of the tile, requested before the accumulator is waited for
+      // G2_RESID_STATS: the warp's 32 x 128 residual values of the tile (two 32-row x 128-byte units), requested before the
+      // accumulator is waited for. Coalesced: load i of a unit covers rows 4i..4i+3, lane -> (row 4i + lane/8, chunk lane%8).
       uint4 xo[MODE == G2_RESID_STATS ? 16 : 1];
+      float st_n = 0.f, st_mean = 0.f, st_m2 = 0.f;   // count / mean / centred 2nd moment of this lane's row over the tile's columns
       if (MODE == G2_RESID_STATS) {
-        const uint4* xp = reinterpret_cast<const uint4*>(args.resid + static_cast<size_t>(row) * args.ldr + n_blk * GEMM_BN + half * 128);
-#ifdef ARP_DBG_NOLDG
 #pragma unroll
-        for (int c = 0; c < 16; ++c) xo[c] = make_uint4(0u, 0u, 0u, 0u);
-#else
-#pragma unroll
-        for (int c = 0; c < 16; ++c) xo[c] = row < args.M ? xp[c] : make_uint4(0u, 0u, 0u, 0u);
-#endif
-#ifndef ARP_DBG_NOPREFETCH
+        for (int c = 0; c < 16; ++c) {
+          const int r = row0 + 4 * (c & 7) + (lane >> 3);
+          const op_t* xp = args.resid + static_cast<size_t>(r) * args.ldr + n_blk * GEMM_BN + half * 128 + (c >> 3) * 64 + (lane & 7) * 8;
+          xo[c] = r < args.M ? *reinterpret_cast<const uint4*>(xp) : make_uint4(0u, 0u, 0u, 0u);
+        }
         // the NEXT tile's residual values are pulled into L2 now, a whole tile period ahead: under a saturated HBM the
         // loaded DRAM latency is several microseconds, more than this warp can cover between two of its own tiles
         if (lane == 0 && it + 1 < my_tiles) {
@@ -260,13 +250,38 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
           tma_prefetch_l2_2d(&tmap_out, c2, r2);
           tma_prefetch_l2_2d(&tmap_out, c2 + 64, r2);
         }
-#endif
       }
       float ln_rstd = 1.f, ln_rm = 0.f;        // G2_LNFOLD: the row's 1/std and -mean/std (in flight under the MMAs)
       if (MODE == G2_LNFOLD && row < args.M) {
-        const float2 p = __ldg(args.ln_stats + row);
-        ln_rstd = p.x;
-        ln_rm = p.y;
+        if (args.ln_nparts == 1) {
+          const float2 p = __ldg(args.ln_stats + row);
+          ln_rstd = p.x;
+          ln_rm = p.y;
+        } else {
+          // merge the row's partial (mean, M2) — equal counts of 128 columns each (Chan et al.). All loads are issued
+          // before the first use: a dependent load-add loop would serialise one L2 round trip per partial.
+          const float2* pp = args.ln_stats + static_cast<size_t>(row) * args.ln_nparts;
+          float mean = 0.f, m2 = 0.f;
+          if (args.ln_nparts == 6) {            // width 768: 48 contiguous, 16-byte aligned bytes
+            const float4 a = __ldg(reinterpret_cast<const float4*>(pp));
+            const float4 b = __ldg(reinterpret_cast<const float4*>(pp) + 1);
+            const float4 c = __ldg(reinterpret_cast<const float4*>(pp) + 2);
+            mean = ((a.x + a.z) + (b.x + b.z) + (c.x + c.z)) * (1.0f / 6.0f);
+            const float d0 = a.x - mean, d1 = a.z - mean, d2 = b.x - mean, d3 = b.z - mean, d4 = c.x - mean, d5 = c.z - mean;
+            m2 = ((a.y + a.w) + (b.y + b.w) + (c.y + c.w)) +
+                 128.0f * ((d0 * d0 + d1 * d1) + (d2 * d2 + d3 * d3) + (d4 * d4 + d5 * d5));
+          } else {
+            for (int i = 0; i < args.ln_nparts; ++i) mean += __ldg(pp + i).x;
+            mean *= 1.0f / static_cast<float>(args.ln_nparts);
+            for (int i = 0; i < args.ln_nparts; ++i) {
+              const float2 p = __ldg(pp + i);
+              const float d = p.x - mean;
+              m2 += fmaf(128.0f * d, d, p.y);
+            }
+          }
+          ln_rstd = rsqrtf(m2 / (128.0f * static_cast<float>(args.ln_nparts)) + args.eps);
+          ln_rm = -mean * ln_rstd;
+        }
       }
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
@@ -281,6 +296,13 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
           //   x_new = fl16(x_old + acc + bias); statistics of the ROUNDED values — what is stored and what the next GEMM
           //   multiplies — two-pass per half (they are all in registers), Chan's merge into the running (n, mean, M2)
           if (lane == 0) tma_store_wait_read<0>();     // the staging buffer was last read by the previous unit's store
+          __syncwarp();
+          // coalesced layout -> row-per-lane through the staging buffer (same 128B swizzle as the output: conflict-free)
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int r = 4 * i + (lane >> 3);
+            *reinterpret_cast<uint4*>(sbuf + r * 128 + (((lane & 7) ^ (r & 7)) << 4)) = xo[u * 8 + i];
+          }
           __syncwarp();
           uint4* srow = reinterpret_cast<uint4*>(sbuf + lane * 128);
 #pragma unroll
@@ -300,7 +322,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             float s1 = 0.f;
 #pragma unroll
             for (int c = 0; c < 4; ++c) {
-              const uint4 q = xo[u * 8 + hh * 4 + c];
+              const uint4 q = srow[(hh * 4 + c) ^ sw];
               const uint32_t w4[4] = {q.x, q.y, q.z, q.w};
               const float4 b0 = __ldg(reinterpret_cast<const float4*>(args.bias + n0 + hh * 32 + 8 * c));
               const float4 b1 = __ldg(reinterpret_cast<const float4*>(args.bias + n0 + hh * 32 + 8 * c + 4));
@@ -318,10 +340,6 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
               }
               srow[(hh * 4 + c) ^ sw] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
             }
-#ifdef ARP_DBG_NOSTATS
-            st_mean += s1;
-            continue;
-#endif
             const float mu = s1 * (1.0f / 32.0f);
             float m2 = 0.f;
 #pragma unroll
@@ -423,21 +441,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
           tma_store_commit();
         }
       }
-      if (MODE == G2_RESID_STATS && n_blk == num_n - 1) {
-        // the row block is complete: the warp of the other column half holds the other N/2 columns of the same rows
-        if (half == 1) stat_part[quarter * 32 + lane] = make_float2(st_mean, st_m2);
-        named_bar_sync(1, G2_EPI_WARPS * 32);
-        if (half == 0) {
-          const float2 o = stat_part[quarter * 32 + lane];
-          const float d = o.x - st_mean;
-          const float mean = fmaf(d, 0.5f, st_mean);
-          const float var = (st_m2 + o.y + d * d * (0.5f * st_n)) / (2.0f * st_n);
-          const float rstd = rsqrtf(var + args.eps);
-          if (row < args.M) args.stats_out[row] = make_float2(rstd, -mean * rstd);
-        }
-        named_bar_sync(1, G2_EPI_WARPS * 32);     // stat_part is rewritten at the end of the next row block
-        st_n = st_mean = st_m2 = 0.f;
-      }
+      if (MODE == G2_RESID_STATS && row < args.M)
+        args.stats_out[static_cast<size_t>(row) * (2 * num_n) + n_blk * 2 + half] = make_float2(st_mean, st_m2);
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
     if (lane == 0) tma_store_wait_all<0>();

@@ -126,6 +126,24 @@ row_moments_kernel(const op_t* __restrict__ x, float2* __restrict__ stats, int M
   if (lane == 0) stats[row] = st;
 }
 
+// stats[row] = (rstd, -mean*rstd) from the row's `nparts` partial (mean, M2), each over 128 columns — the merge the
+// LayerNorm-folding GEMM does in its epilogue (gemm_tcgen05.cuh), as a kernel for the test seam
+__global__ void __launch_bounds__(256)
+merge_row_stats_kernel(const float2* __restrict__ parts, int nparts, float2* __restrict__ stats, int M, float eps) {
+  const int row = blockIdx.x * blockDim.x + threadIdx.x;
+  if (row >= M) return;
+  const float2* pp = parts + static_cast<size_t>(row) * nparts;
+  float mean = 0.f, m2 = 0.f;
+  for (int i = 0; i < nparts; ++i) mean += pp[i].x;
+  mean *= 1.0f / static_cast<float>(nparts);
+  for (int i = 0; i < nparts; ++i) {
+    const float d = pp[i].x - mean;
+    m2 += fmaf(128.0f * d, d, pp[i].y);
+  }
+  const float rstd = rsqrtf(m2 / (128.0f * static_cast<float>(nparts)) + eps);
+  stats[row] = make_float2(rstd, -mean * rstd);
+}
+
 // ln_pre of the 16-bit path: x16 = fl16(LN(x0 fp32)) and the first block's ln_1 statistics of x16.
 template <int W>
 __global__ void __launch_bounds__(256)

@@ -220,8 +220,9 @@ ARP_API int arp_gemm_bf16(ArpHandle* h, const void* a_dev, const void* w_dev, vo
                   int32_t N, int32_t K, const float* bias_dev, const void* resid_dev, int32_t act, void* stream);
 /* The default path's residual update: x[M,N] (operand format, in place) = fl16(x + A[M,K] W[N,K]^T + bias) done in the
  * GEMM epilogue's registers, which also writes stats[M][2] = (rstd, -mean*rstd) of every updated row (eps 1e-5, moments
- * of the ROUNDED values over all N columns) — the LayerNorm statistics the next GEMM folds in (out_proj -> ln_2, c_proj ->
- * next ln_1). N % 256 == 0, K % 64 == 0; fp32 stats on the device. Test seam. */
+ * of the ROUNDED values over all N columns; the epilogue emits one partial (mean, M2) per 128 columns and the consuming
+ * GEMM merges them — here a small kernel does) — the LayerNorm statistics the next GEMM folds in (out_proj -> ln_2,
+ * c_proj -> next ln_1). N % 256 == 0, K % 64 == 0; fp32 stats on the device. Test seam. */
 ARP_API int arp_resid_gemm_stats(ArpHandle* h, const void* a_dev, const void* w_dev, const float* bias_dev, void* x_dev,
                          float* stats_dev, int64_t M, int32_t N, int32_t K, void* stream);
 /* out[M,N] = act(LayerNorm(x; gamma, beta) W^T + bias) with the LayerNorm FOLDED into the GEMM as on the default path

@@ -194,3 +194,41 @@ def test_decode_non_square_frames_bit_exact(capi, H, W, crop):
         assert np.array_equal(out[t], tf(ob[t, -1]).numpy()), f"frame {t}"
     assert np.array_equal(out[1], port.transform_restated(ob[1, -1], crop))
     e.close()
+
+
+@pytest.mark.parametrize("switch", ["ARP_SNAKE=0", "ARP_PRUNE_LAST=0", "ARP_FUSED_STATS=0"])
+def test_measurement_switches_keep_parity(capi, switch, monkeypatch):
+    """The three environment switches read at arp_create select measurement variants of the SAME computation (kernel
+    order across a chunk, class-token-only evaluation of the last block, where the LayerNorm row statistics come from).
+    Each must stay inside the product's parity bar against the fp32 oracle — and ARP_SNAKE, which only reorders tiles,
+    must not change a single bit."""
+    from oracle import port
+    from _util import LOGIT_SCALE_RANDOM_INIT, TOL_COS_ABS
+    model = port.clip_shim.build("ViT-B/16", 0)
+    sd = model.state_dict()
+    rng = np.random.default_rng(21)
+    ob = rng.integers(0, 256, size=(40, 1, 64, 64, 3), dtype=np.uint8)
+    text = torch.nn.functional.normalize(torch.randn(2, 512, generator=torch.Generator().manual_seed(1)), dim=1)
+    tf = port.transform_pil(False, 64)
+    with torch.no_grad():
+        f = model.encode_image(torch.stack([tf(im) for im in ob[:, 0]]))
+        ref = (LOGIT_SCALE_RANDOM_INIT * torch.nn.functional.normalize(f, dim=1) @ text.t())[:, 0].numpy()
+
+    def run():
+        e = capi.Engine(device=0, patch=16, in_h=64, in_w=64, max_batch=16)     # 3 chunks, the last one ragged
+        e.load_state_dict(sd)
+        e.set_text(text, LOGIT_SCALE_RANDOM_INIT)
+        r = e.compute_reward(torch.from_numpy(ob).cuda()).cpu().numpy()
+        e.close()
+        return r
+
+    base = run()
+    name, value = switch.split("=")
+    monkeypatch.setenv(name, value)
+    alt = run()
+    assert np.abs(base - ref).max() / LOGIT_SCALE_RANDOM_INIT <= TOL_COS_ABS
+    assert np.abs(alt - ref).max() / LOGIT_SCALE_RANDOM_INIT <= TOL_COS_ABS
+    if name == "ARP_SNAKE":
+        assert np.array_equal(base, alt)
+    else:
+        assert not np.array_equal(base, alt), "the switch did not select another code path"
