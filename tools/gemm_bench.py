@@ -71,16 +71,18 @@ for impl in impls:
         continue
     # in-place residual (the hot-path form) and timing
     for name, N, K, act, odt, res in HOT:
-        a = (torch.randn(M_HOT, K, device=dev) * 0.5).bfloat16()
-        w = (torch.randn(N, K, device=dev) * 0.05).bfloat16()
+        op = capi.operand_dtype()                      # raw pointers below: the library's own 16-bit format
+        a = (torch.randn(M_HOT, K, device=dev) * 0.5).to(op)
+        w = (torch.randn(N, K, device=dev) * 0.05).to(op)
         b = torch.randn(N, device=dev)
+        odt = odt if odt == torch.float32 else op
         x = torch.randn(M_HOT, N, device=dev) if res else None
         import ctypes as C
         out = x if res else torch.empty(M_HOT, N, device=dev, dtype=odt)
 
         def run():
             eng._check(eng._lib.arp_gemm_bf16(eng._h, C.c_void_p(a.data_ptr()), C.c_void_p(w.data_ptr()),
-                                              C.c_void_p(out.data_ptr()), 0 if odt == torch.float32 else 1, M_HOT, N, K,
+                                              C.c_void_p(out.data_ptr()), capi._TORCH_DT[odt], M_HOT, N, K,
                                               C.c_void_p(b.data_ptr()), C.c_void_p(x.data_ptr()) if res else None, act,
                                               C.c_void_p(torch.cuda.current_stream().cuda_stream)))
         if res:
