@@ -19,6 +19,8 @@ import torch.distributed as dist
 
 ROOT = Path(__file__).resolve().parents[1]
 sys.path.insert(0, str(ROOT))
+import os as _os
+_os.environ.setdefault("ARP_ALLOW_STANDIN_TOKENIZER", "1")   # random-init weights: the deterministic stand-in token ids
 from arp_b200 import capi  # noqa: E402
 from arp_b200.sharding import gather_rows, partition_episodes  # noqa: E402
 from arp_b200.text_tower import clip_text_embedding  # noqa: E402

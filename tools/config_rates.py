@@ -12,6 +12,8 @@ import torch
 
 ROOT = Path(__file__).resolve().parents[1]
 sys.path.insert(0, str(ROOT))
+import os as _os
+_os.environ.setdefault("ARP_ALLOW_STANDIN_TOKENIZER", "1")   # random-init weights: the deterministic stand-in token ids
 from arp_b200.instructions import get_clip_instruct  # noqa: E402
 from arp_b200.label_reward import RewardLabeler  # noqa: E402
 from arp_b200.weights import random_adapter_state_dict, random_clip_state_dict  # noqa: E402

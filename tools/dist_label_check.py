@@ -11,6 +11,8 @@ import torch.distributed as dist
 
 ROOT = Path(__file__).resolve().parents[1]
 sys.path.insert(0, str(ROOT))
+import os as _os
+_os.environ.setdefault("ARP_ALLOW_STANDIN_TOKENIZER", "1")   # random-init weights: the deterministic stand-in token ids
 from arp_b200.label_reward import label_reward  # noqa: E402
 from arp_b200.store import NpyStore  # noqa: E402
 from arp_b200.synth import make_dataset, write_dataset  # noqa: E402

@@ -17,6 +17,8 @@ import torch
 
 ROOT = Path(__file__).resolve().parents[1]
 sys.path.insert(0, str(ROOT))
+import os as _os
+_os.environ.setdefault("ARP_ALLOW_STANDIN_TOKENIZER", "1")   # random-init weights: the deterministic stand-in token ids
 sys.path.insert(0, str(ROOT / "oracle" / "shims"))
 
 from arp_b200 import capi  # noqa: E402

@@ -13,6 +13,8 @@ import torch
 
 ROOT = Path(__file__).resolve().parents[1]
 sys.path.insert(0, str(ROOT))
+import os as _os
+_os.environ.setdefault("ARP_ALLOW_STANDIN_TOKENIZER", "1")   # random-init weights: the deterministic stand-in token ids
 from arp_b200 import online  # noqa: E402
 from arp_b200.rtg_dataset import preprocess_rtgs  # noqa: E402
 from arp_b200.weights import random_clip_state_dict  # noqa: E402
