@@ -15,7 +15,7 @@ from arp_b200 import capi  # noqa: E402
 eng = capi.Engine(device=0, max_batch=8)
 lib = eng._lib
 B, L = 512, 197
-qkv = (torch.randn(B * L, 2304, device="cuda") * 1.5).bfloat16()
+qkv = (torch.randn(B * L, 2304, device="cuda") * 1.5).to(capi.operand_dtype())
 ITEMS, EV = 10, 24
 buf = np.zeros(2 * ITEMS * EV, np.int64)
 for _ in range(3):
