@@ -192,13 +192,23 @@ class Engine:
         return True
 
     def load_state_dict(self, state_dict, strict: bool = False) -> list[str]:
-        """Feed every tensor of a CLIP (or adapter) state_dict; returns the names still missing."""
+        """Feed every tensor of a CLIP (or adapter) state_dict; returns the names still missing. Tensors whose storage
+        (data pointer, shape, dtype, in-place version counter) is exactly what this handle uploaded last time are skipped:
+        labeling the same model again — another instruction, another dataset — does not pay for the upload twice. Only the
+        very same tensor OBJECTS count (pass the same state_dict again; the handle keeps them referenced until it is closed)."""
+        seen = getattr(self, "_uploaded", None)
+        if seen is None:
+            seen = self._uploaded = {}
         for k, v in state_dict.items():
             if not torch.is_tensor(v):
                 continue
             if not strict and not self._lib.arp_wants_weight(self._h, k.encode()):
                 continue                      # text tower / bookkeeping entries: never copied to the device
-            self.set_weight(k, v, strict=strict)
+            mark = (v.data_ptr(), tuple(v.shape), v.dtype, v._version, v.device)
+            if k in seen and seen[k][0] == mark and seen[k][1] is v:
+                continue
+            if self.set_weight(k, v, strict=strict):
+                seen[k] = (mark, v)           # the reference keeps the storage alive: its address cannot be recycled
         return self.missing_weights()
 
     def missing_weights(self) -> list[str]:

@@ -178,10 +178,19 @@ class RewardLabeler:
         if not self.goal:
             texts = list(text) if isinstance(text, (list, tuple)) else [text]
             tokens = resolve_tokenizer(tokenizer)(texts)
-            if adapter:
-                emb, scale = adapter_text_embedding(sd, tokens, dev, ensemble=head == capi.HEAD_ADAPTER_ENSEMBLE)
+            # the instruction embedding of the previous call is reused when the very same weight tensors (objects and
+            # in-place version counters) and token ids come back — the cached handle keeps them referenced
+            text_sd = {k: v for k, v in sd.items() if torch.is_tensor(v) and "visual." not in k}
+            sig = (tokens.tolist(), head, [(k, v._version) for k, v in text_sd.items()])
+            cached = getattr(self.engine, "_text_cache", None)
+            if cached is not None and cached[0] == sig and all(cached[1].get(k) is v for k, v in text_sd.items()):
+                emb, scale = cached[2]
             else:
-                emb, scale = clip_text_embedding(sd, tokens, dev)
+                if adapter:
+                    emb, scale = adapter_text_embedding(sd, tokens, dev, ensemble=head == capi.HEAD_ADAPTER_ENSEMBLE)
+                else:
+                    emb, scale = clip_text_embedding(sd, tokens, dev)
+                self.engine._text_cache = (sig, text_sd, (emb, scale))
             self.engine.set_text(emb, scale)
 
     def label_slab(self, ob: np.ndarray, ep_offsets: np.ndarray, num_frames: int):
