@@ -5,26 +5,34 @@
 // Persistent CTAs loop over (frame, head) items. For one item (L = 197 tokens, padded to 208 keys / 2x128 queries):
 //   TMA      Q (two 128x64 tiles), K and V (208x64) of the head -> 128B-swizzled smem, double buffered across items
 //   MMA #1   S[128 x 208] = Q K^T     tcgen05.mma kind::f16, A and B from smem (K-major), fp32 accumulators in TMEM
-//   softmax  one thread per query row: tcgen05.ld the row, max / exp2 / sum in registers — no cross-lane traffic —
-//            and write P back INTO the same TMEM columns as packed bf16 (tcgen05.st)
-//   MMA #2   O[128 x 64] = P V        A operand straight from TMEM, B = V from smem as an MN-major operand
-//   epilogue tcgen05.ld O, scale by 1/rowsum, bf16, one full 128-byte line per thread to HBM
-// TMEM map per query tile t (base = 256 t): S fp32 [base, base+208) -> P bf16x2 [base, base+104); O fp32 [base+128, base+208)
-// (64 head dims + 16 copies of the row sum: V's operand has a second, all-ones N block).
+//   softmax  one thread per query row: tcgen05.ld the row, max / exp2 in registers — no cross-lane traffic —
+//            and write P back INTO the same TMEM columns as packed 16-bit pairs (tcgen05.st)
+//   MMA #2   O[128 x 80] = P [V | 1]  A operand straight from TMEM, B = V from smem as an MN-major operand plus an
+//            all-ones N block: columns 64..79 of O are the row sums of exactly the weights the tensor core used
+//   epilogue tcgen05.ld O, scale by 1/rowsum, 16-bit, staged in smem in the TMA's swizzled layout, ONE bulk tensor
+//            store per warp (rows past the frame's last token are out of bounds in the 3-D map and are not written)
+// TMEM map: query tile t owns S fp32 [NK t, NK t + NK) -> P pairs overwrite [NK t, NK t + NK/2); ONE O accumulator
+// fp32 [NK QT, NK QT + 80) is shared by the two tiles, whose P V / drain windows are half a period apart (o_free
+// barrier). Because O does not overlay S, the thread that issues a tile's P V issues the tile's NEXT Q K^T right behind
+// it (tcgen05.mma executes in issue order: the new S cannot overtake the P it overwrites) — the next S is computed
+// while the warps drain and store O instead of after it.
 // Warp roles (320 threads): 0 = TMA producer, 1 = TMEM owner (alloc / dealloc only), 2..9 = softmax / MMA issue / epilogue
 // (warps 2-5 own query tile 0, warps 6-9 query tile 1; a warp may only touch TMEM lanes 32*(warp%4)..+31).
 //
-// Scheduling (measured with the ARP_ATTN_TRACE timeline, tools/attn_trace.py; MUFU.EX2 = 8 clk per warp
-// instruction per SMSP, tools/micro/):
-//   * no MMA warp: the LAST softmax warp of a slot to finish its P rows issues P V, the last one to drain O issues
-//     the slot's next Q K^T (smem arrival counters). A dedicated MMA warp shares its SMSP with two softmax warps
-//     and took ~400 cycles to notice a barrier plus ~1000 to issue 13 MMAs;
+// Scheduling (measured: ARP_ATTN_TRACE timeline with an observer warp, tools/attn_trace.py; ncu warp-state samples,
+// profiles/r02_attn_*; microbenchmarks tools/micro/tmem_contention.cu, smsp_interference.cu):
+//   * every softmax warp is a serial chain per item — exp2 pass, P V, drain, next S, row maximum — and a slot's period is
+//     the length of that chain, not the MUFU time: what shortens the chain (S behind P V, a cheap epilogue) is what pays;
+//   * no MMA warp: the LAST softmax warp of a slot to finish its P rows issues P V and the next S (smem arrival counter);
 //   * everything the MMA issue needs is derived from a shuffled (provably warp-uniform) warp index, so the
-//     descriptors live in uniform registers: back-to-back UTCHMMA instead of an ELECT / R2UR.BROADCAST loop
-//     (75 cycles per MMA) in front of every one;
+//     descriptors live in uniform registers: back-to-back UTCHMMA instead of an ELECT / R2UR.BROADCAST loop;
 //   * the exp2 pass is taken in turns per SMSP (xu_turn): the two slots' MUFU-bound passes never overlap, which
-//     keeps the slots half a period apart — one slot's row-max / P V / epilogue / Q K^T hide under the other's exp2;
-//   * the exp2 pass uses packed fp32x2 FMA/ADD and an integer round-and-merge for the bf16 pairs (F2FP would
+//     keeps the slots half a period apart (without the turns: +12 % kernel time);
+//   * the tensor pipe is NOT slowed by the other slot's tcgen05.ld / st traffic (Q K^T 655 vs 670 clk), but a warp's
+//     exp2 pass is slowed by whatever its SMSP neighbour issues (tcgen05.ld stream +27 %, epilogue +13 %);
+//   * thirty-two lanes storing 16 bytes to 32 different lines, eight times per warp, held the warps ~1000 clk per
+//     query tile in the LSU: the output goes through smem and the TMA instead;
+//   * the exp2 pass uses packed fp32x2 FMA and an integer truncate-and-merge for the 16-bit pairs (F2FP would
 //     issue on the XU pipe, the one MUFU.EX2 needs).
 #pragma once
 
@@ -32,7 +40,7 @@
 
 namespace arp {
 
-constexpr int ATC_THREADS = 320;
+constexpr int ATC_THREADS = 448;   // 14 warps: TMA, TMEM owner, 8 softmax, 4 epilogue
 constexpr int ATC_DH = 64;
 
 template <int L>
@@ -43,11 +51,15 @@ struct AtcCfg {
   static constexpr int KV_BYTES = NK * ATC_DH * 2;     // 26 KB
   static constexpr int KV_PAD = (KV_BYTES + 1023) / 1024 * 1024;
   static constexpr int BUF_BYTES = QT * Q_BYTES + 2 * KV_PAD;
-  static constexpr int TX_BYTES = QT * Q_BYTES + 2 * KV_BYTES;
-  static constexpr int ONES_BYTES = KV_PAD;            // a second 64-wide N block of "V" that is all 1.0 (row sums)
-  static constexpr int SMEM_BYTES = 2 * BUF_BYTES + ONES_BYTES + 1024 + 256;
-  static constexpr int O_COL = 128;                    // O accumulator column offset inside a tile's TMEM region
+  // the all-ones N block of the P V operand: ONE 16-key step (16 rows x 128 B); every step's descriptor points its
+  // second N block (LBO) at this same tile
+  static constexpr int ONES_BYTES = 16 * 128;
+  static constexpr int STAGE_BYTES = QT * 128 * ATC_DH * 2;   // O rows on their way to the bulk store: 4 KB per warp
+  static constexpr int SMEM_BYTES = 2 * BUF_BYTES + ONES_BYTES + STAGE_BYTES + 1024 + 256;
+  static constexpr int O_COL = QT * NK;                // the shared O accumulator's first TMEM column
   static constexpr int O_N = ATC_DH + 16;              // P V output width: 64 head dims + 16 copies of the row sum
+  static_assert(O_COL + O_N <= 512, "TMEM columns");
+  static_assert(KV_PAD >= (NK / 16 - 1) * 2048, "the ones tile must sit past every step's V rows (positive LBO)");
 };
 
 __device__ __forceinline__ void umma_bf16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc,
@@ -107,6 +119,11 @@ __device__ __forceinline__ uint64_t f32x2_fma(uint64_t a, uint64_t b, uint64_t c
   asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
   return d;
 }
+__device__ __forceinline__ uint64_t f32x2_mul(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
 __device__ __forceinline__ uint64_t f32x2_add(uint64_t a, uint64_t b) {
   uint64_t d;
   asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
@@ -155,49 +172,75 @@ __device__ __forceinline__ void tmem_st_32x16(uint32_t taddr, const uint32_t (&r
       : "memory");
 }
 
+__device__ __forceinline__ void tmem_ld_32x1(uint32_t taddr, uint32_t& r) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(r) : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ float rcp_approx(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
 #ifdef ARP_ATTN_TRACE
 // dev-only timeline of block 0: clock64 stamps kept in shared memory (a plain st.shared per event), dumped at exit.
-// events: 0 S_issue 1 PV_issue 2 S_ready 3 pass1_done 4 turn_acquired 5 P_arrive 6 O_ready 7 epilogue_done (quarter-0
-// warps), then per lane quarter q: 8+q pass2_end, 12+q O_seen, 16+q drained, 20+q P stores retired
-constexpr int ATC_TR_ITEMS = 10, ATC_TR_EVENTS = 24;
+// events: 0 S_issue 1 PV_issue 2 S_ready 3 pass1_done 4 turn_acquired 5 P_arrive 6 O_ready 7 drained (quarter-0
+// warps), then per lane quarter q: 8+q pass2_end, 12+q O_seen, 16+q stored, 20+q P stores retired
+constexpr int ATC_TR_ITEMS = 10, ATC_TR_EVENTS = 36;
 __device__ long long g_attn_trace[2 * ATC_TR_ITEMS * ATC_TR_EVENTS];
 #define ATC_TRACE(ev, slot, item)                                                                              \
   do {                                                                                                         \
     if (blockIdx.x == 0 && (threadIdx.x & 31) == 0 && (item) < ATC_TR_ITEMS)                                   \
       atc_tr[((slot) * ATC_TR_ITEMS + (item)) * ATC_TR_EVENTS + (ev)] = clock64();                             \
   } while (0)
+// the same from whichever lane executes it (inside an elect_one() block) — events 24.. : S issue begin / first MMA out /
+// last MMA out / committed, P V issue begin / last MMA out / committed; 31, 32: an idle observer warp sees S / O ready
+#define ATC_TRACE_T(ev, slot, item)                                                                            \
+  do {                                                                                                         \
+    if (blockIdx.x == 0 && (item) < ATC_TR_ITEMS)                                                              \
+      atc_tr[((slot) * ATC_TR_ITEMS + (item)) * ATC_TR_EVENTS + (ev)] = clock64();                             \
+  } while (0)
 #else
 #define ATC_TRACE(ev, slot, item)
+#define ATC_TRACE_T(ev, slot, item)
 #endif
 
-// qkv: bf16 [rows, 3*width] (tensor maps: box 64x128 for Q, 64xNK for K/V); out: bf16 [B*L, width]
+// qkv: 16-bit [rows, 3*width] (tensor maps: box 64x128 for Q, 64xNK for K/V); out: 16-bit [B*L, width] through tmap_o,
+// a 3-D view [B, L, width] with a 1 x 32 x 64 box
 //
-// Each query tile of an item is an independent "job" with its own TMEM slot (256 columns) and its own
-// S/P/O barriers, so the MMA warp can run tile 1's Q K^T while tile 0's rows are in softmax, and tile 0's
-// P V while tile 1's rows are in softmax.
+// Each query tile of an item is an independent "job" with its own S / P TMEM columns and its own S / O barriers; the
+// tiles share the O accumulator, the MUFU pipe (xu_turn) and the item's K / V.
 template <int L>
 __global__ void __launch_bounds__(ATC_THREADS, 1)
 attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_kv,
-                    op_t* __restrict__ out, int n_frames, int heads, int width, float scale_log2e,
+                    const __grid_constant__ CUtensorMap tmap_o, int n_frames, int heads, int width, float scale_log2e,
                     int reverse) {
   using C = AtcCfg<L>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* ones = smem + 2 * C::BUF_BYTES;     // [NK rows x 128 B] of bf16 1.0: N block 1 of the P V operand
-  uint64_t* bars = reinterpret_cast<uint64_t*>(ones + C::ONES_BYTES);
-  uint64_t* smem_full = bars;        // [2] TMA -> Q K^T issuer: the item's Q/K/V have landed
-  uint64_t* smem_empty = bars + 2;   // [2] tensor core (all P V of the item retired) -> TMA
-  uint64_t* s_full = bars + 4;       // [2 slots] tensor core -> softmax warps: S ready
-  uint64_t* o_full = bars + 8;       // [2] tensor core -> epilogue: O ready
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
+  uint8_t* ones = smem + 2 * C::BUF_BYTES;     // [16 rows x 128 B] of 1.0: N block 1 of every P V step
+  uint8_t* stage = ones + C::ONES_BYTES;       // [QT][4 quarters][32 rows x 128 B] O rows for the bulk store
+  uint64_t* bars = reinterpret_cast<uint64_t*>(stage + C::STAGE_BYTES);
+  // Two ring states per smem buffer. Q and K of an item are dead as soon as the item's Q K^T have run — almost a full
+  // period before its V is (after both slots' P V) — and the NEXT item's Q K^T is issued right behind this item's P V,
+  // so Q / K are refilled early, on their own barrier pair; a 84 KB refill takes ~3000 clk when every SM is loading.
+  uint64_t* qk_full = bars;          // [2] TMA -> Q K^T issuer: the item's Q tiles and K have landed
+  uint64_t* qk_empty = bars + 2;     // [2] tensor core (the item's Q K^T of every slot retired) -> TMA
+  uint64_t* v_full = bars + 4;       // [2] TMA -> P V issuer: the item's V has landed
+  uint64_t* v_empty = bars + 6;      // [2] tensor core (the item's P V of every slot retired) -> TMA
+  uint64_t* s_full = bars + 8;       // [2 slots] tensor core -> softmax warps: S ready
+  uint64_t* o_full = bars + 10;      // [2 slots] tensor core -> the slot's warps: O ready
+  uint64_t* o_free = bars + 12;      // [1] the four warps that drained O -> the next P V issuer (either slot)
   // exp2 turn per TMEM lane quarter (= per SMSP): the two softmax warps that share an SMSP take their MUFU-bound
-  // pass strictly in (item, slot) order, never both at once
-  volatile int* xu_turn = reinterpret_cast<volatile int*>(bars + 13);
-  // arrival counters per slot: the LAST softmax warp to finish its P rows issues P V itself, the last one to drain O
-  // issues the next item's Q K^T — no hand-off to a separate MMA warp (which, sharing an SMSP with a warp in its
-  // exp2 pass, took ~400 cycles to notice a barrier and ~1000 to get 13 MMA instructions issued)
-  int* cnt_p = reinterpret_cast<int*>(bars + 15);   // [2]
-  int* cnt_e = cnt_p + 2;                            // [2]
+  // pass strictly in (item, slot) order, never both at once. Turn n of a quarter may start when phase n - 1 of its
+  // barrier has completed (the warp that finished turn n - 1 arrives); a parked try_wait costs the SMSP next to nothing,
+  // an LDS polling loop cost the neighbour's exp2 pass 8 %.
+  uint64_t* xu_turn = bars + 13;     // [4 quarters]
+  // P rows of a slot written (4 warp arrivals) -> the slot's MMA issuer: the quarter-3 warp of the slot. That quarter
+  // has the least to do (tile 1: rows 224..255 are padding, the warp does no softmax at all; tile 0: its SMSP hosts one
+  // live softmax warp instead of two, so it finishes its pass first), and a parked try_wait notices the last arrival
+  // sooner than the two MEMBAR.SC + ATOMS of a "last one in issues" counter took.
+  uint64_t* p_done = bars + 17;      // [2 slots]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 19);
 
   // warp index through a shuffle: provably warp-uniform for the compiler, so everything derived from it (slot,
   // TMEM addresses, descriptors) lives in uniform registers and an MMA issue is not an ELECT / R2UR.BROADCAST loop
@@ -205,23 +248,30 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
   const int n_items = n_frames * heads;
 #ifdef ARP_ATTN_TRACE
   __shared__ long long atc_tr[2 * ATC_TR_ITEMS * ATC_TR_EVENTS];
+  for (int i = threadIdx.x; i < 2 * ATC_TR_ITEMS * ATC_TR_EVENTS; i += ATC_THREADS) atc_tr[i] = 0;
 #endif
   constexpr int SM_WARPS = 4 * C::QT;   // softmax warps that actually own rows
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_q);
     tma_prefetch_desc(&tmap_kv);
+    tma_prefetch_desc(&tmap_o);
   }
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < 2; ++i) {
-      mbar_init(&smem_full[i], 1);
-      mbar_init(&smem_empty[i], C::QT);
+      mbar_init(&qk_full[i], 1);
+      mbar_init(&qk_empty[i], C::QT);
+      mbar_init(&v_full[i], 1);
+      mbar_init(&v_empty[i], C::QT);
       mbar_init(&s_full[i], 1);
       mbar_init(&o_full[i], 1);
     }
+    for (int i = 0; i < 4; ++i) mbar_init(&xu_turn[i], 1);
+    mbar_init(&p_done[0], 4);
+    mbar_init(&p_done[1], 4);
+    mbar_init(o_free, 4);
     fence_mbar_init();
   }
-  if (warp == 1 && lane < 4) { xu_turn[lane] = 0; cnt_p[lane] = 0; }   // cnt_p[0..1], cnt_e[0..1] are contiguous
   for (int i = threadIdx.x; i < C::ONES_BYTES / 16; i += ATC_THREADS)      // swizzle-invariant: every element is 1.0
     reinterpret_cast<uint4*>(ones)[i] = make_uint4(kOnes2, kOnes2, kOnes2, kOnes2);
   fence_proxy_async_smem();                                                // generic-proxy writes -> tensor-core reads
@@ -234,24 +284,29 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
   // ---- MMA issue (one elected thread of a softmax warp) ----
   constexpr uint32_t idesc_s = umma_idesc_bf16(128, C::NK);          // Q K^T: both operands K-major
   constexpr uint32_t idesc_o = umma_idesc_bf16(128, C::O_N, 0, 1);    // P [V | 1]: A from TMEM, B MN-major, N = 80
-  auto issue_s = [&](uint32_t sbuf, int t) {
+  auto issue_s = [&](uint32_t sbuf, int t, [[maybe_unused]] int tr_item) {
     const uint64_t dk = umma_desc_kmajor_sw128(sbuf + C::QT * C::Q_BYTES);
     const uint64_t dq = umma_desc_kmajor_sw128(sbuf + t * C::Q_BYTES);
+    ATC_TRACE_T(24, t, tr_item);
 #pragma unroll
-    for (int k = 0; k < ATC_DH / 16; ++k)
-      umma_bf16_ss(tmem_base + t * 256, dq + 2 * k, dk + 2 * k, idesc_s, k != 0);
+    for (int k = 0; k < ATC_DH / 16; ++k) umma_bf16_ss(tmem_base + t * C::NK, dq + 2 * k, dk + 2 * k, idesc_s, k != 0);
     umma_commit(&s_full[t]);
+    umma_commit(&qk_empty[(sbuf - smem_u32(smem)) / C::BUF_BYTES]);   // Q / K of the buffer: free once every slot's S ran
+    ATC_TRACE_T(27, t, tr_item);
   };
-  auto issue_pv = [&](uint32_t sbuf, int t) {
-    // N block 0 = the item's V tile, N block 1 (LBO away) = the shared all-ones tile: O[:, 64..79] = sum_k P[:, k],
-    // the softmax denominator of exactly the bf16 weights the tensor core used
+  auto issue_pv = [&](uint32_t sbuf, int t, [[maybe_unused]] int tr_item) {
+    // N block 0 = 16 keys of the item's V tile, N block 1 (LBO away) = the all-ones tile: O[:, 64..79] = sum_k P[:, k],
+    // the softmax denominator of exactly the 16-bit weights the tensor core used. A step advances V by 16 rows x 128 B
+    // and shortens LBO by as much, so that block 1 stays on the one ones tile.
     const uint32_t v_addr = sbuf + C::QT * C::Q_BYTES + C::KV_PAD;
     const uint64_t dv = umma_desc_mnmajor_sw128(v_addr, smem_u32(ones) - v_addr);
+    constexpr uint64_t kStep = (2048ull >> 4) - ((2048ull >> 4) << 16);   // start += 2048 B, LBO -= 2048 B
+    ATC_TRACE_T(28, t, tr_item);
 #pragma unroll
-    for (int k = 0; k < C::NK / 16; ++k)
-      // 16 keys per MMA: A advances 8 packed columns, V advances 16 rows x 128 B = 2048 B
-      umma_bf16_ts(tmem_base + t * 256 + C::O_COL, tmem_base + t * 256 + k * 8, dv + k * (2048 >> 4), idesc_o, k != 0);
+    for (int k = 0; k < C::NK / 16; ++k)   // 16 keys per MMA: A advances 8 packed columns
+      umma_bf16_ts(tmem_base + C::O_COL, tmem_base + t * C::NK + k * 8, dv + k * kStep, idesc_o, k != 0);
     umma_commit(&o_full[t]);
+    ATC_TRACE_T(30, t, tr_item);
   };
 
   if (warp == 0) {
@@ -260,42 +315,69 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
     for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
       const int b = it & 1;
       const uint32_t ph = (it >> 1) & 1;
-      mbar_wait(&smem_empty[b], ph ^ 1);
+      const int item_o = reverse ? n_items - 1 - item : item;   // snake order across kernels (L2 reuse)
+      const int frame = item_o / heads, head = item_o - frame * heads;
+      uint8_t* buf = smem + b * C::BUF_BYTES;
+      const int row = frame * L;
+      mbar_wait(&qk_empty[b], ph ^ 1);
       if (lane == 0) {
-        const int item_o = reverse ? n_items - 1 - item : item;   // snake order across kernels (L2 reuse)
-        const int frame = item_o / heads, head = item_o - frame * heads;
-        uint8_t* buf = smem + b * C::BUF_BYTES;
-        const int row = frame * L;
-        mbar_arrive_expect_tx(&smem_full[b], C::TX_BYTES);
+        mbar_arrive_expect_tx(&qk_full[b], C::QT * C::Q_BYTES + C::KV_BYTES);
 #pragma unroll
         for (int t = 0; t < C::QT; ++t)
-          tma_load_2d(buf + t * C::Q_BYTES, &tmap_q, &smem_full[b], head * ATC_DH, row + t * 128);
-        tma_load_2d(buf + C::QT * C::Q_BYTES, &tmap_kv, &smem_full[b], width + head * ATC_DH, row);
-        tma_load_2d(buf + C::QT * C::Q_BYTES + C::KV_PAD, &tmap_kv, &smem_full[b], 2 * width + head * ATC_DH, row);
+          tma_load_2d(buf + t * C::Q_BYTES, &tmap_q, &qk_full[b], head * ATC_DH, row + t * 128);
+        tma_load_2d(buf + C::QT * C::Q_BYTES, &tmap_kv, &qk_full[b], width + head * ATC_DH, row);
+      }
+      __syncwarp();
+      mbar_wait(&v_empty[b], ph ^ 1);
+      if (lane == 0) {
+        mbar_arrive_expect_tx(&v_full[b], C::KV_BYTES);
+        tma_load_2d(buf + C::QT * C::Q_BYTES + C::KV_PAD, &tmap_kv, &v_full[b], 2 * width + head * ATC_DH, row);
       }
       __syncwarp();
     }
+#ifdef ARP_ATTN_TRACE
+  } else if (warp == 1) {
+    // dev-only observer: an otherwise idle warp polls the S-ready / O-ready barriers and stamps when each phase completes
+    if (lane == 0 && blockIdx.x == 0) {
+      int cnt[4] = {0, 0, 0, 0}, total = 0;
+      const int n_mine_o = n_items > 0 ? (n_items - 1) / static_cast<int>(gridDim.x) + 1 : 0;
+      const int lim = n_mine_o < ATC_TR_ITEMS ? n_mine_o : ATC_TR_ITEMS;
+      const long long t0 = clock64();
+      while (total < 4 * lim && clock64() - t0 < 4000000) {
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+          uint64_t* bar = b < 2 ? &s_full[b] : &o_full[b - 2];
+          if (cnt[b] < lim && mbar_test_wait(bar, cnt[b] & 1)) {
+            atc_tr[((b & 1) * ATC_TR_ITEMS + cnt[b]) * ATC_TR_EVENTS + (b < 2 ? 31 : 32)] = clock64();
+            ++cnt[b];
+            ++total;
+          }
+        }
+      }
+    }
+#endif
   } else if (warp >= 2 && warp - 2 < SM_WARPS) {
     // ===================== softmax + epilogue: one thread per query row =====================
     const int qt = (warp - 2) >> 2;
     const int quarter = warp & 3;
-    const int qrow = qt * 128 + quarter * 32 + lane;     // query index inside the frame
-    const uint32_t t_s = tmem_base + qt * 256 + (static_cast<uint32_t>(quarter * 32) << 16);
+    const uint32_t lane_off = static_cast<uint32_t>(quarter * 32) << 16;
+    const uint32_t t_s = tmem_base + qt * C::NK + lane_off;
     constexpr int NFULL = C::NK / 32;                    // full 32-column chunks
     constexpr int TAIL = C::NK % 32;                     // 16 or 0
     const int n_mine = n_items > static_cast<int>(blockIdx.x) ? (n_items - 1 - static_cast<int>(blockIdx.x)) / static_cast<int>(gridDim.x) + 1 : 0;
+    // a warp whose 32 rows are all padding (tile 1, rows 224..255 when L = 197) keeps the barrier / turn protocol but
+    // does no softmax: whatever sits in its P rows only reaches O rows that are never stored
+    const bool warp_live = qt * 128 + quarter * 32 < L;
     if (quarter == 0 && n_mine > 0) {      // the slot's first Q K^T
-      mbar_wait(&smem_full[0], 0);
+      mbar_wait(&qk_full[0], 0);
       tc_fence_after();
-      if (elect_one()) issue_s(smem_u32(smem), qt);
+      if (elect_one()) issue_s(smem_u32(smem), qt, 0);
       ATC_TRACE(0, qt, 0);
       __syncwarp();
     }
     uint32_t it = 0;
     for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
       const uint32_t ph = it & 1;
-      const int item_o = reverse ? n_items - 1 - item : item;
-      const int frame = item_o / heads, head = item_o - frame * heads;
       mbar_wait(&s_full[qt], ph);
       tc_fence_after();
       if (quarter == 0) ATC_TRACE(2, qt, it);
@@ -303,9 +385,6 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
       constexpr int NCLEAN = (L / 32 < NFULL) ? L / 32 : NFULL;   // full chunks whose 32 columns are all real keys
       // ---- pass 1: row maximum over the L real keys (two 32-column loads in flight per wait) ----
       float m = -INFINITY;
-      // a warp whose 32 rows are all padding (tile 1, rows 224..255 when L = 197) keeps the barrier / turn protocol but
-      // does no softmax: whatever sits in its P rows only reaches O rows that are never stored
-      const bool warp_live = qt * 128 + quarter * 32 < L;
       if (warp_live) {
         uint32_t a[32], bq[32];
 #pragma unroll 1
@@ -346,16 +425,14 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
       }
       const float mo = m * scale_log2e + kPExpOffset;   // exp2 argument offset: row maximum (+ the fp16 pre-scale)
       if (quarter == 0) ATC_TRACE(3, qt, it);
-      if (C::QT == 2) {     // wait for this warp's exp2 turn
+#ifndef ARP_ATTN_NOTURN
+#define ARP_ATTN_NOTURN 0
+#endif
+      if (C::QT == 2 && !ARP_ATTN_NOTURN) {     // wait for this warp's exp2 turn
         const int my_turn = 2 * static_cast<int>(it) + qt;
-        if (lds_volatile(xu_turn + quarter) != my_turn) {
-          const long long t0 = clock64();
-          while (lds_volatile(xu_turn + quarter) != my_turn) {
-            if (clock64() - t0 > ARP_WATCHDOG_CYCLES) __trap();
-          }
-        }
+        if (my_turn > 0) mbar_wait(&xu_turn[quarter], (my_turn - 1) & 1);
       }
-      // ---- pass 2: p = exp2(s*scale - max*scale); P (bf16 pairs) overwrites the S columns it came from.
+      // ---- pass 2: p = exp2(s*scale - max*scale); P (16-bit pairs) overwrites the S columns it came from.
       //      Two register buffers ping-pong: the load of the next chunk is in flight while this one is processed. ----
       if (quarter == 0) ATC_TRACE(4, qt, it);
       const uint64_t scale2 = f32x2_pack(scale_log2e, scale_log2e), nmo2 = f32x2_pack(-mo, -mo);
@@ -401,84 +478,105 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
           tmem_st_32x8(t_s + NFULL * 16, pk);
         }
       }
-      if (C::QT == 2) {     // hand the exp2 turn to the other slot's warp of this quarter
+      if (C::QT == 2 && !ARP_ATTN_NOTURN) {     // hand the exp2 turn to the other slot's warp of this quarter
         __syncwarp();
-        if (lane == 0) sts_volatile(xu_turn + quarter, 2 * static_cast<int>(it) + qt + 1);
+        if (lane == 0) mbar_arrive(&xu_turn[quarter]);
       }
       ATC_TRACE(8 + quarter, qt, it);
       tmem_st_wait();
       ATC_TRACE(20 + quarter, qt, it);
       tc_fence_before();
       __syncwarp();
-      {
-        // the last of the slot's four warps to get here issues P V (its P rows and everyone else's are in TMEM)
-        int last = 0;
-        if (lane == 0) {
-          __threadfence_block();
-          last = (atoms_add(&cnt_p[qt], 1) & 3) == 3;
-          __threadfence_block();
-        }
-        last = __shfl_sync(0xffffffffu, last, 0);
-        if (last) {
-          tc_fence_after();
-          if (elect_one()) {
-            issue_pv(smem_u32(smem + (it & 1) * C::BUF_BYTES), qt);
-            umma_commit(&smem_empty[it & 1]);   // the item's smem is free once BOTH slots' P V have retired (count = QT)
+      if (lane == 0) mbar_arrive(&p_done[qt]);   // release: this warp's P rows are in TMEM
+      if (quarter == 3) {
+        // the slot's MMA issuer: P V as soon as all four warps' P rows are written and, right behind it, the slot's NEXT
+        // Q K^T
+        mbar_wait(&p_done[qt], ph);
+        // the shared O accumulator must have been drained by its previous user: P V number n (slots alternate, the
+        // turn protocol orders them) waits for drain n - 1
+        const int n_pv = C::QT * static_cast<int>(it) + qt;
+        if (n_pv > 0) mbar_wait(o_free, (n_pv - 1) & 1);
+        mbar_wait(&v_full[it & 1], (it >> 1) & 1);
+        tc_fence_after();
+        const uint32_t nx = it + 1;
+        const bool has_next = static_cast<int>(nx) < n_mine;
+        if (elect_one()) {
+          issue_pv(smem_u32(smem + (it & 1) * C::BUF_BYTES), qt, it);
+          umma_commit(&v_empty[it & 1]);   // the item's V is free once BOTH slots' P V have retired (count = QT)
+          if (has_next) {
+            mbar_wait(&qk_full[nx & 1], (nx >> 1) & 1);
+            issue_s(smem_u32(smem + (nx & 1) * C::BUF_BYTES), qt, nx);
           }
-          ATC_TRACE(1, qt, it);
-          __syncwarp();
         }
+        ATC_TRACE(1, qt, it);
+        __syncwarp();
       }
       if (quarter == 0) ATC_TRACE(5, qt, it);
-      // ---- epilogue: O / rowsum -> bf16 -> HBM (each thread owns one 128-byte output line) ----
-      mbar_wait(&o_full[qt], ph);
-      tc_fence_after();
-      if (quarter == 0) ATC_TRACE(6, qt, it);
-      ATC_TRACE(12 + quarter, qt, it);
-      uint32_t o0[32], o1[32], osum[16];
-      tmem_ld_32x32(t_s + C::O_COL, o0);
-      tmem_ld_32x32(t_s + C::O_COL + 32, o1);
-      tmem_ld_32x16(t_s + C::O_COL + ATC_DH, osum);      // 16 copies of the row sum (the ones block of the operand)
-      tmem_ld_wait();
-      const float inv = 1.0f / __uint_as_float(osum[0]);
-      tc_fence_before();
-      __syncwarp();
-      {
-        // the last warp to have drained its O rows issues the slot's next Q K^T (S overwrites the P / O columns)
-        int last = 0;
+    }
+  } else if (warp >= 2 + 8) {
+    // ===================== epilogue warps: O / rowsum -> 16 bits -> smem -> bulk tensor store =====================
+    // One warp per TMEM lane quarter serves BOTH slots (their O windows alternate in the shared accumulator). Taking the
+    // drain, the scaling and the store out of the softmax warps shortens THEIR per-item chain to exp2 pass -> P V ->
+    // next S -> row maximum, which is what sets the kernel's period.
+    const int quarter = warp & 3;
+    const uint32_t t_o = tmem_base + C::O_COL + (static_cast<uint32_t>(quarter * 32) << 16);
+    uint32_t it = 0;
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
+      const int item_o = reverse ? n_items - 1 - item : item;
+      const int frame = item_o / heads, head = item_o - frame * heads;
+#pragma unroll
+      for (int qt = 0; qt < C::QT; ++qt) {
+        const bool warp_live = qt * 128 + quarter * 32 < L;   // tile 1, rows 224..255: nothing to store
+        uint8_t* my_stage = stage + (qt * 4 + quarter) * 4096;
+        mbar_wait(&o_full[qt], it & 1);
+        tc_fence_after();
+        ATC_TRACE(12 + quarter, qt, it);
+        uint32_t o0[32], o1[32], osum = 0;
+        if (warp_live) {
+          tmem_ld_32x32(t_o, o0);
+          tmem_ld_32x32(t_o + 32, o1);
+          tmem_ld_32x1(t_o + ATC_DH, osum);       // a copy of the row sum (the ones block of the operand)
+          tmem_ld_wait();
+        }
+        tc_fence_before();
+        __syncwarp();
         if (lane == 0) {
-          __threadfence_block();
-          last = (atoms_add(&cnt_e[qt], 1) & 3) == 3;
-          __threadfence_block();
+          mbar_arrive(o_free);                    // O may be overwritten by the other slot's P V (count = 4 warps)
+          // the bulk store that last read this staging buffer (this slot, an item ago) is done; the other slot's may fly
+          if (C::QT == 2) tma_store_wait_read<1>(); else tma_store_wait_read<0>();
         }
-        last = __shfl_sync(0xffffffffu, last, 0);
-        if (last && static_cast<int>(it) + 1 < n_mine) {
-          const uint32_t nx = it + 1;
-          mbar_wait(&smem_full[nx & 1], (nx >> 1) & 1);
-          tc_fence_after();
-          if (elect_one()) issue_s(smem_u32(smem + (nx & 1) * C::BUF_BYTES), qt);
-          ATC_TRACE(0, qt, nx);
+        __syncwarp();
+        if (warp_live) {
+          // one 128-byte output row per thread in the TMA's 128B-swizzled layout — chunk c of row r sits at chunk
+          // c ^ (r & 7): conflict-free 16-byte shared stores
+          const float inv = rcp_approx(__uint_as_float(osum));
+          const uint64_t inv2 = f32x2_pack(inv, inv);
+          uint4* srow = reinterpret_cast<uint4*>(my_stage + lane * 128);
+          const int sw = lane & 7;
+          auto pack2 = [&](uint32_t lo, uint32_t hi) {
+            float a, b;
+            f32x2_unpack(f32x2_mul(f32x2_pack(__uint_as_float(lo), __uint_as_float(hi)), inv2), a, b);
+            return pack_op(a, b);
+          };
+#pragma unroll
+          for (int c = 0; c < 4; ++c)
+            srow[c ^ sw] = make_uint4(pack2(o0[8 * c], o0[8 * c + 1]), pack2(o0[8 * c + 2], o0[8 * c + 3]),
+                                      pack2(o0[8 * c + 4], o0[8 * c + 5]), pack2(o0[8 * c + 6], o0[8 * c + 7]));
+#pragma unroll
+          for (int c = 0; c < 4; ++c)
+            srow[(4 + c) ^ sw] = make_uint4(pack2(o1[8 * c], o1[8 * c + 1]), pack2(o1[8 * c + 2], o1[8 * c + 3]),
+                                            pack2(o1[8 * c + 4], o1[8 * c + 5]), pack2(o1[8 * c + 6], o1[8 * c + 7]));
+          fence_proxy_async_smem();
           __syncwarp();
+          if (lane == 0) {
+            tma_store_3d(&tmap_o, my_stage, head * ATC_DH, qt * 128 + quarter * 32, frame);
+            tma_store_commit();
+          }
         }
-      }
-      if (quarter == 0) ATC_TRACE(7, qt, it);
-      ATC_TRACE(16 + quarter, qt, it);
-      if (qrow < L) {
-        uint4* dst = reinterpret_cast<uint4*>(out + (static_cast<size_t>(frame) * L + qrow) * width + head * ATC_DH);
-#pragma unroll
-        for (int c = 0; c < 4; ++c)
-          dst[c] = make_uint4(pack_op(__uint_as_float(o0[8 * c]) * inv, __uint_as_float(o0[8 * c + 1]) * inv),
-                              pack_op(__uint_as_float(o0[8 * c + 2]) * inv, __uint_as_float(o0[8 * c + 3]) * inv),
-                              pack_op(__uint_as_float(o0[8 * c + 4]) * inv, __uint_as_float(o0[8 * c + 5]) * inv),
-                              pack_op(__uint_as_float(o0[8 * c + 6]) * inv, __uint_as_float(o0[8 * c + 7]) * inv));
-#pragma unroll
-        for (int c = 0; c < 4; ++c)
-          dst[4 + c] = make_uint4(pack_op(__uint_as_float(o1[8 * c]) * inv, __uint_as_float(o1[8 * c + 1]) * inv),
-                                  pack_op(__uint_as_float(o1[8 * c + 2]) * inv, __uint_as_float(o1[8 * c + 3]) * inv),
-                                  pack_op(__uint_as_float(o1[8 * c + 4]) * inv, __uint_as_float(o1[8 * c + 5]) * inv),
-                                  pack_op(__uint_as_float(o1[8 * c + 6]) * inv, __uint_as_float(o1[8 * c + 7]) * inv));
+        ATC_TRACE(16 + quarter, qt, it);
       }
     }
+    if (lane == 0) tma_store_wait_read<0>();   // the staged rows must outlive the last bulk store's reads
   }
 
   tc_fence_before();

@@ -804,6 +804,33 @@ static int get_tmap(ArpHandle* h, const void* ptr, uint64_t rows, uint64_t cols,
   return ARP_OK;
 }
 
+// 3-D view [frames, tokens, width] of the attention output with a (1 frame) x 32 tokens x 64 columns box, 128B swizzle:
+// one softmax warp's 32 query rows of one head. Rows past `tokens` are out of bounds in dimension 1 and are NOT written,
+// so a partially filled warp (tokens = 197: rows 192..196) never touches the next frame's rows.
+static int get_tmap_attn_out(ArpHandle* h, const void* ptr, uint64_t frames, uint64_t tokens, uint64_t width,
+                             const CUtensorMap** out) {
+  TmapKey key{ptr, frames, tokens, width, 32, 64, 0x30002u};
+  auto it = h->tmaps.find(key);
+  if (it == h->tmaps.end()) {
+    if (h->tmaps.size() > 4096) h->tmaps.clear();
+    CUtensorMap m;
+    cuuint64_t gdim[3] = {width, tokens, frames};
+    cuuint64_t gstr[2] = {width * 2, tokens * width * 2};
+    cuuint32_t box[3] = {64, 32, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    if ((reinterpret_cast<uintptr_t>(ptr) & 15) || (gstr[0] & 15))
+      return fail(h, ARP_ERR_INVALID, "attention output must be 16-byte aligned with a 16-byte multiple row pitch");
+    CUresult r = get_encode_tiled()(&m, ARP_OP_FP16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3,
+                                    const_cast<void*>(ptr), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(h, ARP_ERR_CUDA, "cuTensorMapEncodeTiled (attention output) failed (%d)", (int)r);
+    it = h->tmaps.emplace(key, m).first;
+  }
+  *out = &it->second;
+  return ARP_OK;
+}
+
 template <typename K>
 static cudaError_t launch_clustered(K kernel, int grid, int cg, int smem, cudaStream_t st, const CUtensorMap& ta,
                                     const CUtensorMap& tb, const CUtensorMap& to, const GemmArgs& g) {
@@ -961,15 +988,16 @@ static int launch_attention(ArpHandle* h, const bf16* qkv, bf16* out, int B, int
   const int W = h->cfg.width;
   const uint64_t rows = rows_alloc > 0 ? (uint64_t)rows_alloc : (uint64_t)B * tokens;
   const int nk = (tokens + 15) / 16 * 16;
-  const CUtensorMap *tq, *tkv;
+  const CUtensorMap *tq, *tkv, *to;
   ARP_TRY(get_tmap(h, qkv, rows, 3 * W, 3 * W, 128, &tq));
   ARP_TRY(get_tmap(h, qkv, rows, 3 * W, 3 * W, nk, &tkv));
+  ARP_TRY(get_tmap_attn_out(h, out, (uint64_t)B, (uint64_t)tokens, (uint64_t)W, &to));
   const int grid = std::min(B * h->cfg.heads, kNumSMs);
   const int rev = h->snake ? (h->dir ^= 1) : 0;
   if (tokens == 197)
-    attention_tc_kernel<197><<<grid, ATC_THREADS, AtcCfg<197>::SMEM_BYTES, st>>>(*tq, *tkv, out, B, h->cfg.heads, W, scale_log2e, rev);
+    attention_tc_kernel<197><<<grid, ATC_THREADS, AtcCfg<197>::SMEM_BYTES, st>>>(*tq, *tkv, *to, B, h->cfg.heads, W, scale_log2e, rev);
   else
-    attention_tc_kernel<50><<<grid, ATC_THREADS, AtcCfg<50>::SMEM_BYTES, st>>>(*tq, *tkv, out, B, h->cfg.heads, W, scale_log2e, rev);
+    attention_tc_kernel<50><<<grid, ATC_THREADS, AtcCfg<50>::SMEM_BYTES, st>>>(*tq, *tkv, *to, B, h->cfg.heads, W, scale_log2e, rev);
   h->launches++;
   ARP_CUDA(h, cudaGetLastError());
   return ARP_OK;
