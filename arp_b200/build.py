@@ -90,5 +90,21 @@ def build(force: bool = False, verbose: bool = False) -> Path:
     return LIB
 
 
+JITTER_LIB = LIBDIR / "libarp_b200_jitter.so"
+
+
+def build_jitter() -> Path:
+    """Test-only variant (-DARP_ATTN_JITTER: random sleeps at every hand-off of the attention kernel), rebuilt when the
+    sources change. Loaded by tests/test_gpu_edges.py::test_attention_protocol_survives_jitter in a subprocess."""
+    LIBDIR.mkdir(exist_ok=True)
+    stamp = LIBDIR / "libarp_b200_jitter.stamp"
+    digest = _sources_digest()
+    if JITTER_LIB.exists() and stamp.exists() and stamp.read_text().split() == [digest, _file_digest(JITTER_LIB)]:
+        return JITTER_LIB
+    build_variant(JITTER_LIB, ["ARP_ATTN_JITTER"])
+    stamp.write_text(f"{digest} {_file_digest(JITTER_LIB)}")
+    return JITTER_LIB
+
+
 if __name__ == "__main__":
     print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

@@ -12,26 +12,33 @@
 //   epilogue tcgen05.ld O, scale by 1/rowsum, 16-bit, staged in smem in the TMA's swizzled layout, ONE bulk tensor
 //            store per warp (rows past the frame's last token are out of bounds in the 3-D map and are not written)
 // TMEM map: query tile t owns S fp32 [NK t, NK t + NK) -> P pairs overwrite [NK t, NK t + NK/2); ONE O accumulator
-// fp32 [NK QT, NK QT + 80) is shared by the two tiles, whose P V / drain windows are half a period apart (o_free
-// barrier). Because O does not overlay S, the thread that issues a tile's P V issues the tile's NEXT Q K^T right behind
+// fp32 [NK QT, NK QT + 80) is shared by the two tiles, whose P V / drain windows are half a period apart (o_drained
+// barriers). Because O does not overlay S, the thread that issues a tile's P V issues the tile's NEXT Q K^T right behind
 // it (tcgen05.mma executes in issue order: the new S cannot overtake the P it overwrites) — the next S is computed
 // while the warps drain and store O instead of after it.
-// Warp roles (320 threads): 0 = TMA producer, 1 = TMEM owner (alloc / dealloc only), 2..9 = softmax / MMA issue / epilogue
-// (warps 2-5 own query tile 0, warps 6-9 query tile 1; a warp may only touch TMEM lanes 32*(warp%4)..+31).
+// Warp roles (448 threads): 0 = TMA producer, 1 = TMEM owner (alloc / dealloc only), 2..9 = softmax (warps 2-5 own query
+// tile 0, warps 6-9 query tile 1; the quarter-3 warp of a tile also issues its MMAs), 10..13 = epilogue, one per TMEM
+// lane quarter (a warp may only touch TMEM lanes 32*(warp%4)..+31).
 //
-// Scheduling (measured: ARP_ATTN_TRACE timeline with an observer warp, tools/attn_trace.py; ncu warp-state samples,
-// profiles/r02_attn_*; microbenchmarks tools/micro/tmem_contention.cu, smsp_interference.cu):
-//   * every softmax warp is a serial chain per item — exp2 pass, P V, drain, next S, row maximum — and a slot's period is
-//     the length of that chain, not the MUFU time: what shortens the chain (S behind P V, a cheap epilogue) is what pays;
-//   * no MMA warp: the LAST softmax warp of a slot to finish its P rows issues P V and the next S (smem arrival counter);
+// Scheduling (measured: ARP_ATTN_TRACE timeline with an observer warp, tools/attn_trace.py; ncu warp-state samples;
+// microbenchmarks tools/micro/tmem_contention.cu, smsp_interference.cu; numbers in profiles/r02_attn_*):
+//   * every softmax warp is a serial chain per item — exp2 pass, P V, next S, row maximum — and until that chain is
+//     shorter than the other slot's exp2 pass its length, not the MUFU time, is the slot's period. Three things cut it
+//     from ~3800 to ~2100 clk: the next S right behind P V (above), the epilogue on warps of its own, and mbarrier
+//     hand-offs instead of MEMBAR.SC + ATOMS counters / LDS polling. Now the period is two exp2 passes per SMSP;
+//   * a fixed MMA issuer per slot, the quarter-3 warp: tile 1's has no live row (rows 224..255), tile 0's shares its SMSP
+//     with that idle warp and finishes its pass first. It parks on the slot's p_done barrier (4 warp arrivals);
 //   * everything the MMA issue needs is derived from a shuffled (provably warp-uniform) warp index, so the
 //     descriptors live in uniform registers: back-to-back UTCHMMA instead of an ELECT / R2UR.BROADCAST loop;
-//   * the exp2 pass is taken in turns per SMSP (xu_turn): the two slots' MUFU-bound passes never overlap, which
-//     keeps the slots half a period apart (without the turns: +12 % kernel time);
+//   * the exp2 pass is taken in turns per SMSP (xu_turn barriers): the two slots' MUFU-bound passes never overlap, which
+//     keeps the slots half a period apart (free-running: +2 % now, +12 % before the chain was shortened);
 //   * the tensor pipe is NOT slowed by the other slot's tcgen05.ld / st traffic (Q K^T 655 vs 670 clk), but a warp's
-//     exp2 pass is slowed by whatever its SMSP neighbour issues (tcgen05.ld stream +27 %, epilogue +13 %);
-//   * thirty-two lanes storing 16 bytes to 32 different lines, eight times per warp, held the warps ~1000 clk per
-//     query tile in the LSU: the output goes through smem and the TMA instead;
+//     exp2 pass is slowed by whatever its SMSP neighbours issue (a tcgen05.ld stream +27 %, the epilogue +13 %, an LDS
+//     polling loop +8 %, a parked try_wait +2 %);
+//   * thirty-two lanes storing 16 bytes to 32 different lines, eight times per warp, held the warps in the LSU: the
+//     output goes through smem and the TMA instead;
+//   * a refill of the item's 84 KB takes ~3000 clk with every SM loading: Q / K (dead after the item's S) and V (dead
+//     after its P V) are released and refilled separately, so the S issued behind P V never waits for its operands;
 //   * the exp2 pass uses packed fp32x2 FMA and an integer truncate-and-merge for the 16-bit pairs (F2FP would
 //     issue on the XU pipe, the one MUFU.EX2 needs).
 #pragma once
@@ -181,6 +188,21 @@ __device__ __forceinline__ float rcp_approx(float x) {
   return y;
 }
 
+// Test-only build (-DARP_ATTN_JITTER, tests/test_gpu_edges.py::test_attention_protocol_survives_jitter): every warp
+// sleeps a pseudo-random 0..8 us at each hand-off point, so that a protocol which only holds for the usual relative
+// speeds of the warps (the epilogue outrunning the softmax, a barrier never more than a phase behind its waiter) fails
+// in the test instead of under a profiler or a sanitizer.
+#ifdef ARP_ATTN_JITTER
+__device__ __forceinline__ void atc_jitter(uint32_t salt) {
+  uint32_t h = (static_cast<uint32_t>(clock64()) ^ (salt * 2654435761u) ^ (threadIdx.x >> 5) * 40503u ^ blockIdx.x * 9176u);
+  h ^= h >> 13; h *= 0x5bd1e995u; h ^= h >> 15;
+  if (h & 1) __nanosleep((h >> 1) & 8191);
+}
+#define ATC_JITTER(salt) atc_jitter(salt)
+#else
+#define ATC_JITTER(salt)
+#endif
+
 #ifdef ARP_ATTN_TRACE
 // dev-only timeline of block 0: clock64 stamps kept in shared memory (a plain st.shared per event), dumped at exit.
 // events: 0 S_issue 1 PV_issue 2 S_ready 3 pass1_done 4 turn_acquired 5 P_arrive 6 O_ready 7 drained (quarter-0
@@ -229,18 +251,22 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
   uint64_t* v_empty = bars + 6;      // [2] tensor core (the item's P V of every slot retired) -> TMA
   uint64_t* s_full = bars + 8;       // [2 slots] tensor core -> softmax warps: S ready
   uint64_t* o_full = bars + 10;      // [2 slots] tensor core -> the slot's warps: O ready
-  uint64_t* o_free = bars + 12;      // [1] the four warps that drained O -> the next P V issuer (either slot)
+  // [2 slots] the four epilogue warps have drained the slot's O -> the OTHER slot's P V issuer. One barrier per slot: a
+  // parity wait is only sound if the waiter is never more than one phase ahead of the barrier, which holds when each
+  // issuer walks the other slot's barrier phase by phase — and does not on a single barrier whose phases alternate
+  // between two waiters (compute-sanitizer's timing found that one).
+  uint64_t* o_drained = bars + 12;   // bars + 12, + 13
   // exp2 turn per TMEM lane quarter (= per SMSP): the two softmax warps that share an SMSP take their MUFU-bound
   // pass strictly in (item, slot) order, never both at once. Turn n of a quarter may start when phase n - 1 of its
   // barrier has completed (the warp that finished turn n - 1 arrives); a parked try_wait costs the SMSP next to nothing,
   // an LDS polling loop cost the neighbour's exp2 pass 8 %.
-  uint64_t* xu_turn = bars + 13;     // [4 quarters]
+  uint64_t* xu_turn = bars + 14;     // [4 quarters]
   // P rows of a slot written (4 warp arrivals) -> the slot's MMA issuer: the quarter-3 warp of the slot. That quarter
   // has the least to do (tile 1: rows 224..255 are padding, the warp does no softmax at all; tile 0: its SMSP hosts one
   // live softmax warp instead of two, so it finishes its pass first), and a parked try_wait notices the last arrival
   // sooner than the two MEMBAR.SC + ATOMS of a "last one in issues" counter took.
-  uint64_t* p_done = bars + 17;      // [2 slots]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 19);
+  uint64_t* p_done = bars + 18;      // [2 slots]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 20);
 
   // warp index through a shuffle: provably warp-uniform for the compiler, so everything derived from it (slot,
   // TMEM addresses, descriptors) lives in uniform registers and an MMA issue is not an ELECT / R2UR.BROADCAST loop
@@ -269,7 +295,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
     for (int i = 0; i < 4; ++i) mbar_init(&xu_turn[i], 1);
     mbar_init(&p_done[0], 4);
     mbar_init(&p_done[1], 4);
-    mbar_init(o_free, 4);
+    mbar_init(&o_drained[0], 4);
+    mbar_init(&o_drained[1], 4);
     fence_mbar_init();
   }
   for (int i = threadIdx.x; i < C::ONES_BYTES / 16; i += ATC_THREADS)      // swizzle-invariant: every element is 1.0
@@ -319,6 +346,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
       const int frame = item_o / heads, head = item_o - frame * heads;
       uint8_t* buf = smem + b * C::BUF_BYTES;
       const int row = frame * L;
+      ATC_JITTER(8 + it);
       mbar_wait(&qk_empty[b], ph ^ 1);
       if (lane == 0) {
         mbar_arrive_expect_tx(&qk_full[b], C::QT * C::Q_BYTES + C::KV_BYTES);
@@ -378,6 +406,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
     uint32_t it = 0;
     for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
       const uint32_t ph = it & 1;
+      ATC_JITTER(1 + it);
       mbar_wait(&s_full[qt], ph);
       tc_fence_after();
       if (quarter == 0) ATC_TRACE(2, qt, it);
@@ -386,22 +415,26 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
       // ---- pass 1: row maximum over the L real keys (two 32-column loads in flight per wait) ----
       float m = -INFINITY;
       if (warp_live) {
-        uint32_t a[32], bq[32];
+        uint32_t a[32], bq[32], cq[32];
+        // three 32-column loads in flight per wait: the pass is bound by tcgen05.ld round trips, not by its 104 FMNMX3
 #pragma unroll 1
-        for (int c = 0; c + 1 < NCLEAN; c += 2) {
+        for (int c = 0; c + 2 < NCLEAN; c += 3) {
           tmem_ld_32x32(t_s + c * 32, a);
           tmem_ld_32x32(t_s + c * 32 + 32, bq);
+          tmem_ld_32x32(t_s + c * 32 + 64, cq);
           tmem_ld_wait();
-          float m0 = m, m1 = -INFINITY;
+          float m0 = m, m1 = -INFINITY, m2 = -INFINITY;
 #pragma unroll
           for (int j = 0; j < 32; j += 2) {
             m0 = fmaxf(m0, fmaxf(__uint_as_float(a[j]), __uint_as_float(a[j + 1])));
             m1 = fmaxf(m1, fmaxf(__uint_as_float(bq[j]), __uint_as_float(bq[j + 1])));
+            m2 = fmaxf(m2, fmaxf(__uint_as_float(cq[j]), __uint_as_float(cq[j + 1])));
           }
-          m = fmaxf(m0, m1);
+          m = fmaxf(m0, fmaxf(m1, m2));
         }
-        if (NCLEAN & 1) {
-          tmem_ld_32x32(t_s + (NCLEAN - 1) * 32, a);
+#pragma unroll
+        for (int c = NCLEAN / 3 * 3; c < NCLEAN; ++c) {
+          tmem_ld_32x32(t_s + c * 32, a);
           tmem_ld_wait();
 #pragma unroll
           for (int j = 0; j < 32; j += 2) m = fmaxf(m, fmaxf(__uint_as_float(a[j]), __uint_as_float(a[j + 1])));
@@ -423,12 +456,10 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
             if (NFULL * 32 + j < L) m = fmaxf(m, __uint_as_float(r[j]));
         }
       }
+      ATC_JITTER(2 + it);
       const float mo = m * scale_log2e + kPExpOffset;   // exp2 argument offset: row maximum (+ the fp16 pre-scale)
       if (quarter == 0) ATC_TRACE(3, qt, it);
-#ifndef ARP_ATTN_NOTURN
-#define ARP_ATTN_NOTURN 0
-#endif
-      if (C::QT == 2 && !ARP_ATTN_NOTURN) {     // wait for this warp's exp2 turn
+      if (C::QT == 2) {     // wait for this warp's exp2 turn
         const int my_turn = 2 * static_cast<int>(it) + qt;
         if (my_turn > 0) mbar_wait(&xu_turn[quarter], (my_turn - 1) & 1);
       }
@@ -478,11 +509,12 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
           tmem_st_32x8(t_s + NFULL * 16, pk);
         }
       }
-      if (C::QT == 2 && !ARP_ATTN_NOTURN) {     // hand the exp2 turn to the other slot's warp of this quarter
+      if (C::QT == 2) {     // hand the exp2 turn to the other slot's warp of this quarter
         __syncwarp();
         if (lane == 0) mbar_arrive(&xu_turn[quarter]);
       }
       ATC_TRACE(8 + quarter, qt, it);
+      ATC_JITTER(3 + it);
       tmem_st_wait();
       ATC_TRACE(20 + quarter, qt, it);
       tc_fence_before();
@@ -491,11 +523,12 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
       if (quarter == 3) {
         // the slot's MMA issuer: P V as soon as all four warps' P rows are written and, right behind it, the slot's NEXT
         // Q K^T
-        mbar_wait(&p_done[qt], ph);
-        // the shared O accumulator must have been drained by its previous user: P V number n (slots alternate, the
-        // turn protocol orders them) waits for drain n - 1
-        const int n_pv = C::QT * static_cast<int>(it) + qt;
-        if (n_pv > 0) mbar_wait(o_free, (n_pv - 1) & 1);
+        mbar_wait(&p_done[qt], ph);   // parked: a busy-polling issuer was no faster (137 vs 136 us)
+        ATC_JITTER(4 + it);
+        // the shared O accumulator must have been drained by its previous user (slots alternate, the turn protocol orders
+        // them): slot 1 follows slot 0 of the same item, slot 0 follows the last slot of the previous item
+        if (qt > 0) mbar_wait(&o_drained[qt - 1], ph);
+        else if (it > 0) mbar_wait(&o_drained[C::QT - 1], ph ^ 1);
         mbar_wait(&v_full[it & 1], (it >> 1) & 1);
         tc_fence_after();
         const uint32_t nx = it + 1;
@@ -528,9 +561,11 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
       for (int qt = 0; qt < C::QT; ++qt) {
         const bool warp_live = qt * 128 + quarter * 32 < L;   // tile 1, rows 224..255: nothing to store
         uint8_t* my_stage = stage + (qt * 4 + quarter) * 4096;
+        ATC_JITTER(5 + it);
         mbar_wait(&o_full[qt], it & 1);
         tc_fence_after();
         ATC_TRACE(12 + quarter, qt, it);
+        ATC_JITTER(6 + it);
         uint32_t o0[32], o1[32], osum = 0;
         if (warp_live) {
           tmem_ld_32x32(t_o, o0);
@@ -541,11 +576,12 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
         tc_fence_before();
         __syncwarp();
         if (lane == 0) {
-          mbar_arrive(o_free);                    // O may be overwritten by the other slot's P V (count = 4 warps)
+          mbar_arrive(&o_drained[qt]);            // O may be overwritten by the next P V (count = 4 warps)
           // the bulk store that last read this staging buffer (this slot, an item ago) is done; the other slot's may fly
           if (C::QT == 2) tma_store_wait_read<1>(); else tma_store_wait_read<0>();
         }
         __syncwarp();
+        ATC_JITTER(7 + it);
         if (warp_live) {
           // one 128-byte output row per thread in the TMA's 128B-swizzled layout — chunk c of row r sits at chunk
           // c ^ (r & 7): conflict-free 16-byte shared stores

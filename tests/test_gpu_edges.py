@@ -3,6 +3,9 @@
 What the domain offers at sizes the CPU oracle cannot reach: a frame's reward may not depend on where the frame sits
 (which chunk, which row of a GEMM tile, which episode), re-labeling is idempotent, and the return-to-go our library
 produced must be reproduced bit for bit by the oracle's scan over OUR rewards."""
+import os
+from pathlib import Path
+
 import numpy as np
 import pytest
 import torch
@@ -232,3 +235,45 @@ def test_measurement_switches_keep_parity(capi, switch, monkeypatch):
         assert np.array_equal(base, alt)
     else:
         assert not np.array_equal(base, alt), "the switch did not select another code path"
+
+
+_JITTER_SCRIPT = r"""
+import sys, torch
+sys.path.insert(0, sys.argv[1])
+from arp_b200 import capi
+eng = capi.Engine(device=0, max_batch=8)
+worst = 0.0
+for rep in range(3):
+    for B, L in ((40, 197), (13, 197), (1, 197), (30, 50)):
+        g = torch.Generator(device="cuda").manual_seed(1000 * rep + B)
+        qkv = (torch.randn(B * L, 2304, device="cuda", generator=g) * 1.5).to(capi.operand_dtype())
+        out = eng.attention(qkv, B, L)
+        torch.cuda.synchronize()
+        q, k, v = qkv.float().view(B, L, 3, 12, 64).permute(2, 0, 3, 1, 4)
+        ref = (torch.softmax(q @ k.transpose(-1, -2) * 0.125, -1) @ v).permute(0, 2, 1, 3).reshape(B * L, 768)
+        assert torch.isfinite(out.float()).all(), (rep, B, L)
+        worst = max(worst, float((out.float() - ref).abs().max() / ref.abs().max()))
+eng.close()
+print("JITTER_WORST", worst)
+"""
+
+
+@pytest.mark.gpu
+def test_attention_protocol_survives_jitter(tmp_path):
+    """The attention kernel's barrier protocol (turns, shared O accumulator, split smem rings) must not depend on the
+    warps' usual relative speeds: the -DARP_ATTN_JITTER build sleeps a random 0..8 us at every hand-off. Several items
+    per CTA (B = 40: 480 items over 148 CTAs) so that every ring and every parity wraps. A protocol hole shows up as a
+    watchdog trap, a hang (timeout) or wrong numbers. Found the hard way: a single O-drained barrier shared by both
+    slots let a waiter run two phases ahead of it as soon as the epilogue warps were slowed down."""
+    import subprocess
+    import sys
+    from arp_b200.build import build_jitter
+    lib = build_jitter()
+    script = tmp_path / "jitter.py"
+    script.write_text(_JITTER_SCRIPT)
+    root = str(Path(__file__).resolve().parents[1])
+    res = subprocess.run([sys.executable, str(script), root], env={**os.environ, "ARP_B200_LIB": str(lib)},
+                         capture_output=True, text=True, timeout=600)
+    assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-2000:]
+    worst = float(res.stdout.split("JITTER_WORST")[1])
+    assert worst < 2e-2

@@ -24,7 +24,7 @@ torch.cuda.synchronize()
 n = lib.arp_debug_attn_trace(C.c_void_p(buf.ctypes.data), len(buf))
 tr = buf.reshape(2, ITEMS, EV)
 t0 = tr[tr > 0].min()
-names = ["S_issue", "PV_issue", "S_ready", "pass1_done", "turn", "P_arrive", "O_ready", "epi_done"] + [f"pass2_end.q{q}" for q in range(4)] + [f"O_seen.q{q}" for q in range(4)] + [f"drained.q{q}" for q in range(4)] + [f"st_waited.q{q}" for q in range(4)] + ["Sx_begin", "Sx_mma1", "Sx_mma4", "Sx_commit", "PVx_begin", "PVx_mma13", "PVx_commit", "OBS_S_ready", "OBS_O_ready", "staged.q0", "fenced.q0", "tma_issued.q0"]
+names = ["S_issue", "PV_issue", "S_ready", "pass1_done", "turn", "P_arrive", "-", "-"] + [f"pass2_end.q{q}" for q in range(4)] + [f"O_seen.q{q}" for q in range(4)] + [f"stored.q{q}" for q in range(4)] + [f"st_waited.q{q}" for q in range(4)] + ["Sx_begin", "-", "-", "Sx_commit", "PVx_begin", "-", "PVx_commit", "OBS_S_ready", "OBS_O_ready", "-", "-", "-"]
 rows = [(tr[s, i, e] - t0, s, i, names[e]) for s in range(2) for i in range(ITEMS) for e in range(EV) if tr[s, i, e] > 0]
 for t, s, i, nm in sorted(rows):
     if 3 <= i < 6 and nm != '-':
