@@ -110,32 +110,6 @@ __device__ __forceinline__ uint64_t umma_desc_mnmajor_sw128(uint32_t smem_addr, 
   return d;
 }
 
-// Packed fp32x2 arithmetic (sm_100): one issue slot for two elements. A lone warp issues at most every other cycle,
-// and the exp2 pass is issue-bound once its F2FP conversions are off the XU pipe — halving the FFMA / FADD count
-// is what lets the pass run at the MUFU rate (8 clk per warp instruction).
-__device__ __forceinline__ uint64_t f32x2_pack(float lo, float hi) {
-  uint64_t r;
-  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
-  return r;
-}
-__device__ __forceinline__ void f32x2_unpack(uint64_t v, float& lo, float& hi) {
-  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
-}
-__device__ __forceinline__ uint64_t f32x2_fma(uint64_t a, uint64_t b, uint64_t c) {
-  uint64_t d;
-  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
-  return d;
-}
-__device__ __forceinline__ uint64_t f32x2_mul(uint64_t a, uint64_t b) {
-  uint64_t d;
-  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
-  return d;
-}
-__device__ __forceinline__ uint64_t f32x2_add(uint64_t a, uint64_t b) {
-  uint64_t d;
-  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
-  return d;
-}
 // Two fp32 -> packed bf16 pair WITHOUT F2FP (which issues on the XU pipe, the same pipe as MUFU.EX2): adding 0x8000
 // to the bit pattern rounds the magnitude to nearest (ties away from zero; finite inputs), then the two high halves
 // are merged with a shift and a LOP3 on the ALU pipe.
@@ -509,7 +483,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
           tmem_st_32x8(t_s + NFULL * 16, pk);
         }
       }
-      if (C::QT == 2) {     // hand the exp2 turn to the other slot's warp of this quarter
+      if (C::QT == 2) {     // hand the exp2 turn to the other slot's warp of this quarter (earlier, mid-pass: 4-8 % slower)
         __syncwarp();
         if (lane == 0) mbar_arrive(&xu_turn[quarter]);
       }

@@ -85,6 +85,33 @@ __device__ __forceinline__ uint32_t pack_op(float lo, float hi) {
   return *reinterpret_cast<uint32_t*>(&v);
 }
 
+// Packed fp32x2 arithmetic (sm_100): one issue slot for two elements, each lane rounded exactly like the scalar
+// instruction. A lone warp issues at most every other cycle, so instruction count is time in the attention kernel's exp2
+// pass and in the GEMM epilogues (10-12 thread instructions per output element before packing).
+__device__ __forceinline__ uint64_t f32x2_pack(float lo, float hi) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void f32x2_unpack(uint64_t v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ uint64_t f32x2_fma(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ uint64_t f32x2_mul(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ uint64_t f32x2_add(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+
 // ----------------------------------------------------------------------------
 // mbarrier
 // ----------------------------------------------------------------------------
