@@ -11,7 +11,7 @@ from arp_b200 import capi  # noqa: E402
 
 dev = torch.device("cuda", 0)
 impls = [3]   # one implementation ships: CTA pairs (cta_group::2)
-M_HOT = 197 * 512
+M_HOT = 197 * int(os.environ.get('GEMM_BENCH_FRAMES', '512'))
 
 
 def relerr(a, b):
@@ -44,6 +44,7 @@ CASES = [  # M, N, K, act, bias, resid, out dtype
     (100, 13312, 6656, 2, True, False, torch.bfloat16),
 ]
 HOT = [("qkv", 2304, 768, 0, torch.bfloat16, False), ("fc_gelu", 3072, 768, 1, torch.bfloat16, False),
+       ("fc_noact", 3072, 768, 0, torch.bfloat16, False), ("fc_relu", 3072, 768, 2, torch.bfloat16, False),
        ("proj_res", 768, 3072, 0, torch.float32, True), ("out_res", 768, 768, 0, torch.float32, True)]
 
 for impl in impls:
