@@ -16,9 +16,15 @@
 // barriers). Because O does not overlay S, the thread that issues a tile's P V issues the tile's NEXT Q K^T right behind
 // it (tcgen05.mma executes in issue order: the new S cannot overtake the P it overwrites) — the next S is computed
 // while the warps drain and store O instead of after it.
+// Query tile 1 (rows 128..196) is SPREAD over the four TMEM lane quarters — five 16-row TMA boxes put rows 128 + 16q.. in
+// lanes 0..15 of quarter q and rows 176..196 in lanes 0..20 of quarter 3 — and its softmax reads S with the 16-lane
+// tcgen05.ld.16x256b shape, which hands every row to four threads (row maximum = 4-thread shuffle; P goes back with the
+// matching 16x128b store): a quarter's pass is 104 MUFU instructions per thread instead of 208, and the busiest SMSP
+// carries 364 per item instead of 416 (197 rows are 24.6 eight-row units; 7 on one SMSP, 6 on the others is the optimum).
 // Warp roles (448 threads): 0 = TMA producer, 1 = TMEM owner (alloc / dealloc only), 2..9 = softmax (warps 2-5 own query
 // tile 0, warps 6-9 query tile 1; the quarter-3 warp of a tile also issues its MMAs), 10..13 = epilogue, one per TMEM
-// lane quarter (a warp may only touch TMEM lanes 32*(warp%4)..+31).
+// lane quarter (a warp may only touch TMEM lanes 32*(warp%4)..+31); the quarter-3 epilogue warp also does the softmax
+// of tile 1's last five rows (lanes 16..20 of quarter 3), in tile 1's turn, beside the softmax warp of that quarter.
 //
 // Scheduling (measured: ARP_ATTN_TRACE timeline with an observer warp, tools/attn_trace.py; ncu warp-state samples;
 // microbenchmarks tools/micro/tmem_contention.cu, smsp_interference.cu; numbers in profiles/r02_attn_*):
@@ -65,6 +71,14 @@ struct AtcCfg {
   static constexpr int SMEM_BYTES = 2 * BUF_BYTES + ONES_BYTES + STAGE_BYTES + 1024 + 256;
   static constexpr int O_COL = QT * NK;                // the shared O accumulator's first TMEM column
   static constexpr int O_N = ATC_DH + 16;              // P V output width: 64 head dims + 16 copies of the row sum
+  // Query tile 1 (rows 128..L-1) is SPREAD over the four TMEM lane quarters — 16 rows in lanes 0..15 of quarters 0..2, the
+  // rest (21 for L = 197) in lanes 0..20 of quarter 3 — and its softmax reads S with the 16-lane tcgen05.ld shape, which
+  // hands every row to FOUR threads: a quarter's pass costs 104 MUFU instructions (156 in quarter 3) instead of 208, and
+  // no SMSP carries two full exp2 passes per item any more (416 -> 364 MUFU instructions on the busiest one).
+  static constexpr bool SPREAD = QT == 2;
+  static constexpr int Q1_LOADS = 5;                   // 16-row boxes of tile 1: quarters 0..2 one each, quarter 3 two
+  static constexpr int QK_TX_BYTES = SPREAD ? Q_BYTES + Q1_LOADS * 16 * 128 + KV_BYTES : QT * Q_BYTES + KV_BYTES;
+  static_assert(!SPREAD || (L - 176 > 16 && L - 176 <= 24 && NK % 64 == 16), "tile-1 spread is laid out for 193..200 tokens");
   static_assert(O_COL + O_N <= 512, "TMEM columns");
   static_assert(KV_PAD >= (NK / 16 - 1) * 2048, "the ones tile must sit past every step's V rows (positive LBO)");
 };
@@ -153,6 +167,41 @@ __device__ __forceinline__ void tmem_st_32x16(uint32_t taddr, const uint32_t (&r
       : "memory");
 }
 
+// 16-lane shapes (lane / column of every register verified on the part: tools/micro/tmem_shapes.cu). With lane base
+// L0 in the address, thread t of tcgen05.ld.16x256b.xN holds, for step i < N: lane L0 + t/4, columns 8i + 2(t%4), +1 in
+// registers 4i, 4i+1 and lane L0 + 8 + t/4, same columns, in 4i+2, 4i+3. tcgen05.st.16x128b.xN writes register 2i to
+// lane L0 + t/4, column 4i + t%4 and 2i+1 to lane L0 + 8 + t/4: exactly where the packed pair of the loaded columns goes.
+__device__ __forceinline__ void tmem_ld_16x256_x8(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.16x256b.x8.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_16x256_x2(uint32_t taddr, uint32_t (&r)[8]) {
+  asm volatile("tcgen05.ld.sync.aligned.16x256b.x2.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_st_16x128_x8(uint32_t taddr, const uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.16x128b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, "
+      "%15, %16};" ::"r"(taddr),
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+      "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_16x128_x2(uint32_t taddr, const uint32_t (&r)[4]) {
+  asm volatile("tcgen05.st.sync.aligned.16x128b.x2.b32 [%0], {%1, %2, %3, %4};" ::"r"(taddr), "r"(r[0]), "r"(r[1]),
+               "r"(r[2]), "r"(r[3])
+               : "memory");
+}
 __device__ __forceinline__ void tmem_ld_32x1(uint32_t taddr, uint32_t& r) {
   asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(r) : "r"(taddr) : "memory");
 }
@@ -208,7 +257,8 @@ __device__ long long g_attn_trace[2 * ATC_TR_ITEMS * ATC_TR_EVENTS];
 template <int L>
 __global__ void __launch_bounds__(ATC_THREADS, 1)
 attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_kv,
-                    const __grid_constant__ CUtensorMap tmap_o, int n_frames, int heads, int width, float scale_log2e,
+                    const __grid_constant__ CUtensorMap tmap_o, const __grid_constant__ CUtensorMap tmap_q16,
+                    const __grid_constant__ CUtensorMap tmap_o16, int n_frames, int heads, int width, float scale_log2e,
                     int reverse) {
   using C = AtcCfg<L>;
   extern __shared__ uint8_t smem_raw[];
@@ -240,7 +290,13 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
   // live softmax warp instead of two, so it finishes its pass first), and a parked try_wait notices the last arrival
   // sooner than the two MEMBAR.SC + ATOMS of a "last one in issues" counter took.
   uint64_t* p_done = bars + 18;      // [2 slots]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 20);
+  // spread layout: tile 0's quarter-3 warp has finished its exp2 pass (= tile 1's turn on that SMSP begins) -> the quarter-3
+  // epilogue warp, which does the softmax of tile 1's last rows (the second 16-lane group of quarter 3)
+  // (two barriers, used by alternate items: tile 0 may finish the NEXT item's pass before that warp has looked — its
+  // pass after that needs the warp's own drain — so with one barrier the waiter could fall two phases behind, where a
+  // parity wait blocks for good; the jitter test found it)
+  uint64_t* rem_go = bars + 20;      // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 22);
 
   // warp index through a shuffle: provably warp-uniform for the compiler, so everything derived from it (slot,
   // TMEM addresses, descriptors) lives in uniform registers and an MMA issue is not an ELECT / R2UR.BROADCAST loop
@@ -256,6 +312,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
     tma_prefetch_desc(&tmap_q);
     tma_prefetch_desc(&tmap_kv);
     tma_prefetch_desc(&tmap_o);
+    tma_prefetch_desc(&tmap_q16);
+    tma_prefetch_desc(&tmap_o16);
   }
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < 2; ++i) {
@@ -268,13 +326,22 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
     }
     for (int i = 0; i < 4; ++i) mbar_init(&xu_turn[i], 1);
     mbar_init(&p_done[0], 4);
-    mbar_init(&p_done[1], 4);
+    mbar_init(&p_done[1], C::SPREAD ? 5 : 4);   // + the quarter-3 epilogue warp (rows 192.. of tile 1)
+    mbar_init(&rem_go[0], 1);
+    mbar_init(&rem_go[1], 1);
     mbar_init(&o_drained[0], 4);
     mbar_init(&o_drained[1], 4);
     fence_mbar_init();
   }
   for (int i = threadIdx.x; i < C::ONES_BYTES / 16; i += ATC_THREADS)      // swizzle-invariant: every element is 1.0
     reinterpret_cast<uint4*>(ones)[i] = make_uint4(kOnes2, kOnes2, kOnes2, kOnes2);
+  if (C::SPREAD) {
+    // lanes 16..31 of quarters 0..2 of tile 1 are never loaded: keep their Q rows finite (zero) for the tensor core
+    for (int i = threadIdx.x; i < 2 * 3 * 2048 / 16; i += ATC_THREADS) {
+      const int b = i / (3 * 128), q = (i / 128) % 3, w = i % 128;
+      reinterpret_cast<uint4*>(smem + b * C::BUF_BYTES + C::Q_BYTES + q * 4096 + 2048)[w] = make_uint4(0u, 0u, 0u, 0u);
+    }
+  }
   fence_proxy_async_smem();                                                // generic-proxy writes -> tensor-core reads
   if (warp == 1) tmem_alloc<512>(tmem_slot);
   tc_fence_before();
@@ -310,6 +377,85 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
     ATC_TRACE_T(30, t, tr_item);
   };
 
+  // ---- query tile 1, spread over the lane quarters (AtcCfg::SPREAD): softmax of one 16-lane group ----
+  // A thread serves rows t/4 ("A": registers 4i, 4i+1 of a load) and 8 + t/4 ("B": 4i+2, 4i+3) of the group, columns
+  // 8i + 2(t%4), +1 of every 8-column step: a row's maximum is a 4-thread shuffle reduction, its P words go back with the
+  // matching 16x128b store shape.
+  const bool sp_c0 = 192 + 2 * (lane & 3) < L, sp_c1 = 193 + 2 * (lane & 3) < L;   // this thread's real columns of the last load
+  auto spread_rowmax = [&](uint32_t tg, float& row_a, float& row_b) {
+    auto max16 = [](const uint32_t (&r)[32], float& ma, float& mb) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        ma = fmaxf(ma, fmaxf(__uint_as_float(r[4 * i]), __uint_as_float(r[4 * i + 1])));
+        mb = fmaxf(mb, fmaxf(__uint_as_float(r[4 * i + 2]), __uint_as_float(r[4 * i + 3])));
+      }
+    };
+    uint32_t a[32], bq[32], tl[8];
+    float a0 = -INFINITY, a1 = -INFINITY, b0m = -INFINITY, b1m = -INFINITY;
+    tmem_ld_16x256_x8(tg, a);
+    tmem_ld_16x256_x8(tg + 64, bq);
+    tmem_ld_wait();
+    max16(a, a0, b0m);
+    max16(bq, a1, b1m);
+    tmem_ld_16x256_x8(tg + 128, a);
+    tmem_ld_16x256_x2(tg + 192, tl);
+    tmem_ld_wait();
+    max16(a, a0, b0m);
+    if (sp_c0) { a1 = fmaxf(a1, __uint_as_float(tl[0])); b1m = fmaxf(b1m, __uint_as_float(tl[2])); }
+    if (sp_c1) { a1 = fmaxf(a1, __uint_as_float(tl[1])); b1m = fmaxf(b1m, __uint_as_float(tl[3])); }
+    float ma = fmaxf(a0, a1), mb = fmaxf(b0m, b1m);
+    ma = fmaxf(ma, __shfl_xor_sync(0xffffffffu, ma, 1));
+    mb = fmaxf(mb, __shfl_xor_sync(0xffffffffu, mb, 1));
+    ma = fmaxf(ma, __shfl_xor_sync(0xffffffffu, ma, 2));
+    mb = fmaxf(mb, __shfl_xor_sync(0xffffffffu, mb, 2));
+    row_a = ma;
+    row_b = mb;
+  };
+  // p = exp2(s*scale - max*scale) of the group, P written in place; BOTH = rows A and B, otherwise row A only (row B's words
+  // are written as zero). The next 64 columns are in flight while these are exponentiated.
+  auto spread_exp = [&](uint32_t tg, float max_a, float max_b, bool both) {
+    const float mo_a = max_a * scale_log2e + kPExpOffset, mo_b = max_b * scale_log2e + kPExpOffset;
+    const uint64_t sc2 = f32x2_pack(scale_log2e, scale_log2e), na2 = f32x2_pack(-mo_a, -mo_a), nb2 = f32x2_pack(-mo_b, -mo_b);
+    auto chunk16 = [&](const uint32_t (&src)[32], int blk) {
+      uint32_t pk[16];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        float x0, x1;
+        f32x2_unpack(f32x2_fma(f32x2_pack(__uint_as_float(src[4 * i]), __uint_as_float(src[4 * i + 1])), sc2, na2), x0, x1);
+        pk[2 * i] = pack_bf16_trunc(ex2_approx(x0), ex2_approx(x1));
+        if (both) {
+          f32x2_unpack(f32x2_fma(f32x2_pack(__uint_as_float(src[4 * i + 2]), __uint_as_float(src[4 * i + 3])), sc2, nb2), x0, x1);
+          pk[2 * i + 1] = pack_bf16_trunc(ex2_approx(x0), ex2_approx(x1));
+        } else {
+          pk[2 * i + 1] = 0u;
+        }
+      }
+      tmem_st_16x128_x8(tg + blk * 32, pk);      // P words 32 blk .. + 31 <- S columns 64 blk .. + 63
+    };
+    uint32_t b0[32], b1[32], tl[8];
+    tmem_ld_16x256_x8(tg, b0);
+    tmem_ld_wait();
+    tmem_ld_16x256_x8(tg + 64, b1);
+    chunk16(b0, 0);
+    tmem_ld_wait();
+    tmem_ld_16x256_x8(tg + 128, b0);
+    chunk16(b1, 1);
+    tmem_ld_wait();
+    tmem_ld_16x256_x2(tg + 192, tl);
+    chunk16(b0, 2);
+    tmem_ld_wait();
+    uint32_t pk4[4] = {0u, 0u, 0u, 0u};
+    const float pa0 = sp_c0 ? ex2_approx(fmaf(__uint_as_float(tl[0]), scale_log2e, -mo_a)) : 0.f;
+    const float pa1 = sp_c1 ? ex2_approx(fmaf(__uint_as_float(tl[1]), scale_log2e, -mo_a)) : 0.f;
+    pk4[0] = pack_bf16_trunc(pa0, pa1);
+    if (both) {
+      const float pb0 = sp_c0 ? ex2_approx(fmaf(__uint_as_float(tl[2]), scale_log2e, -mo_b)) : 0.f;
+      const float pb1 = sp_c1 ? ex2_approx(fmaf(__uint_as_float(tl[3]), scale_log2e, -mo_b)) : 0.f;
+      pk4[1] = pack_bf16_trunc(pb0, pb1);
+    }
+    tmem_st_16x128_x2(tg + 96, pk4);             // P words 96..103 <- S columns 192..207 (padding -> 0)
+  };
+
   if (warp == 0) {
     // ===================== TMA producer =====================
     uint32_t it = 0;
@@ -323,10 +469,20 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
       ATC_JITTER(8 + it);
       mbar_wait(&qk_empty[b], ph ^ 1);
       if (lane == 0) {
-        mbar_arrive_expect_tx(&qk_full[b], C::QT * C::Q_BYTES + C::KV_BYTES);
+        mbar_arrive_expect_tx(&qk_full[b], C::QK_TX_BYTES);
+        if (C::SPREAD) {
+          tma_load_2d(buf, &tmap_q, &qk_full[b], head * ATC_DH, row);
+          uint8_t* q1 = buf + C::Q_BYTES;
 #pragma unroll
-        for (int t = 0; t < C::QT; ++t)
-          tma_load_2d(buf + t * C::Q_BYTES, &tmap_q, &qk_full[b], head * ATC_DH, row + t * 128);
+          for (int q = 0; q < 3; ++q)      // rows 128 + 16 q .. + 15 -> lanes 0..15 of quarter q
+            tma_load_2d(q1 + q * 4096, &tmap_q16, &qk_full[b], head * ATC_DH, row + 128 + 16 * q);
+          tma_load_2d(q1 + 3 * 4096, &tmap_q16, &qk_full[b], head * ATC_DH, row + 176);          // quarter 3: rows 176..207
+          tma_load_2d(q1 + 3 * 4096 + 2048, &tmap_q16, &qk_full[b], head * ATC_DH, row + 192);
+        } else {
+#pragma unroll
+          for (int t = 0; t < C::QT; ++t)
+            tma_load_2d(buf + t * C::Q_BYTES, &tmap_q, &qk_full[b], head * ATC_DH, row + t * 128);
+        }
         tma_load_2d(buf + C::QT * C::Q_BYTES, &tmap_kv, &qk_full[b], width + head * ATC_DH, row);
       }
       __syncwarp();
@@ -369,7 +525,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
     const int n_mine = n_items > static_cast<int>(blockIdx.x) ? (n_items - 1 - static_cast<int>(blockIdx.x)) / static_cast<int>(gridDim.x) + 1 : 0;
     // a warp whose 32 rows are all padding (tile 1, rows 224..255 when L = 197) keeps the barrier / turn protocol but
     // does no softmax: whatever sits in its P rows only reaches O rows that are never stored
-    const bool warp_live = qt * 128 + quarter * 32 < L;
+    const bool spread = C::SPREAD && qt == 1;          // warp-uniform: the 16-lane path of query tile 1
+    const bool warp_live = spread || qt * 128 + quarter * 32 < L;
     if (quarter == 0 && n_mine > 0) {      // the slot's first Q K^T
       mbar_wait(&qk_full[0], 0);
       tc_fence_after();
@@ -388,7 +545,12 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
       constexpr int NCLEAN = (L / 32 < NFULL) ? L / 32 : NFULL;   // full chunks whose 32 columns are all real keys
       // ---- pass 1: row maximum over the L real keys (two 32-column loads in flight per wait) ----
       float m = -INFINITY;
-      if (warp_live) {
+      // spread path: row maxima of this quarter's 16-lane group; a thread serves rows t/4 ("A") and 8 + t/4 ("B"), a
+      // quarter of their columns each
+      float mA = -INFINITY, mB = -INFINITY;
+      if (spread) {
+        spread_rowmax(t_s, mA, mB);
+      } else if (warp_live) {
         uint32_t a[32], bq[32], cq[32];
         // three 32-column loads in flight per wait: the pass is bound by tcgen05.ld round trips, not by its 104 FMNMX3
 #pragma unroll 1
@@ -456,7 +618,9 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
         }
         tmem_st_32x16(t_s + c * 16, pk);
       };
-      if (warp_live) {
+      if (spread) {
+        spread_exp(t_s, mA, mB, true);
+      } else if (warp_live) {
         uint32_t b0[32], b1[32];
         tmem_ld_32x32(t_s, b0);
         tmem_ld_wait();
@@ -485,7 +649,10 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
       }
       if (C::QT == 2) {     // hand the exp2 turn to the other slot's warp of this quarter (earlier, mid-pass: 4-8 % slower)
         __syncwarp();
-        if (lane == 0) mbar_arrive(&xu_turn[quarter]);
+        if (lane == 0) {
+          mbar_arrive(&xu_turn[quarter]);
+          if (C::SPREAD && qt == 0 && quarter == 3) mbar_arrive(&rem_go[it & 1]);
+        }
       }
       ATC_TRACE(8 + quarter, qt, it);
       ATC_JITTER(3 + it);
@@ -531,9 +698,27 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
     for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
       const int item_o = reverse ? n_items - 1 - item : item;
       const int frame = item_o / heads, head = item_o - frame * heads;
+      if (C::SPREAD && quarter == 3) {
+        // Tile 1's rows 192.. sit in lanes 16..23 of quarter 3, a second 16-lane group that would double that quarter's
+        // pass (it was the kernel's longest: 2480 against 1350 clk). This warp is idle now — tile 0's O comes ~1000 clk
+        // later — so it takes the group: both warps feed the SMSP's MUFU pipe during tile 1's turn.
+        const uint32_t tg2 = tmem_base + C::NK + (static_cast<uint32_t>(96 + 16) << 16);
+        ATC_JITTER(9 + it);
+        mbar_wait(&s_full[1], it & 1);
+        mbar_wait(&rem_go[it & 1], (it >> 1) & 1);
+        tc_fence_after();
+        float mg, unused;
+        spread_rowmax(tg2, mg, unused);
+        spread_exp(tg2, mg, mg, false);
+        tmem_st_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&p_done[1]);
+      }
 #pragma unroll
       for (int qt = 0; qt < C::QT; ++qt) {
-        const bool warp_live = qt * 128 + quarter * 32 < L;   // tile 1, rows 224..255: nothing to store
+        const bool spread = C::SPREAD && qt == 1;               // tile 1: 16 rows per quarter (21 in quarter 3)
+        const bool warp_live = spread || qt * 128 + quarter * 32 < L;
         uint8_t* my_stage = stage + (qt * 4 + quarter) * 4096;
         ATC_JITTER(5 + it);
         mbar_wait(&o_full[qt], it & 1);
@@ -579,7 +764,12 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
           fence_proxy_async_smem();
           __syncwarp();
           if (lane == 0) {
-            tma_store_3d(&tmap_o, my_stage, head * ATC_DH, qt * 128 + quarter * 32, frame);
+            if (spread) {      // lanes 0..15 -> rows 128 + 16 q ..; quarter 3: lanes 0..31 -> rows 176..207, clipped at L
+              tma_store_3d(&tmap_o16, my_stage, head * ATC_DH, 128 + 16 * quarter, frame);
+              if (quarter == 3) tma_store_3d(&tmap_o16, my_stage + 2048, head * ATC_DH, 192, frame);
+            } else {
+              tma_store_3d(&tmap_o, my_stage, head * ATC_DH, qt * 128 + quarter * 32, frame);
+            }
             tma_store_commit();
           }
         }

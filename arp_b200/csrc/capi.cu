@@ -808,15 +808,15 @@ static int get_tmap(ArpHandle* h, const void* ptr, uint64_t rows, uint64_t cols,
 // one softmax warp's 32 query rows of one head. Rows past `tokens` are out of bounds in dimension 1 and are NOT written,
 // so a partially filled warp (tokens = 197: rows 192..196) never touches the next frame's rows.
 static int get_tmap_attn_out(ArpHandle* h, const void* ptr, uint64_t frames, uint64_t tokens, uint64_t width,
-                             const CUtensorMap** out) {
-  TmapKey key{ptr, frames, tokens, width, 32, 64, 0x30002u};
+                             const CUtensorMap** out, uint32_t box_rows = 32) {
+  TmapKey key{ptr, frames, tokens, width, box_rows, 64, 0x30002u};
   auto it = h->tmaps.find(key);
   if (it == h->tmaps.end()) {
     if (h->tmaps.size() > 4096) h->tmaps.clear();
     CUtensorMap m;
     cuuint64_t gdim[3] = {width, tokens, frames};
     cuuint64_t gstr[2] = {width * 2, tokens * width * 2};
-    cuuint32_t box[3] = {64, 32, 1};
+    cuuint32_t box[3] = {64, box_rows, 1};
     cuuint32_t estr[3] = {1, 1, 1};
     if ((reinterpret_cast<uintptr_t>(ptr) & 15) || (gstr[0] & 15))
       return fail(h, ARP_ERR_INVALID, "attention output must be 16-byte aligned with a 16-byte multiple row pitch");
@@ -988,16 +988,18 @@ static int launch_attention(ArpHandle* h, const bf16* qkv, bf16* out, int B, int
   const int W = h->cfg.width;
   const uint64_t rows = rows_alloc > 0 ? (uint64_t)rows_alloc : (uint64_t)B * tokens;
   const int nk = (tokens + 15) / 16 * 16;
-  const CUtensorMap *tq, *tkv, *to;
+  const CUtensorMap *tq, *tkv, *to, *tq16, *to16;
   ARP_TRY(get_tmap(h, qkv, rows, 3 * W, 3 * W, 128, &tq));
   ARP_TRY(get_tmap(h, qkv, rows, 3 * W, 3 * W, nk, &tkv));
   ARP_TRY(get_tmap_attn_out(h, out, (uint64_t)B, (uint64_t)tokens, (uint64_t)W, &to));
+  ARP_TRY(get_tmap(h, qkv, rows, 3 * W, 3 * W, 16, &tq16));            // 16-row boxes: query tile 1 spread over the quarters
+  ARP_TRY(get_tmap_attn_out(h, out, (uint64_t)B, (uint64_t)tokens, (uint64_t)W, &to16, 16));
   const int grid = std::min(B * h->cfg.heads, kNumSMs);
   const int rev = h->snake ? (h->dir ^= 1) : 0;
   if (tokens == 197)
-    attention_tc_kernel<197><<<grid, ATC_THREADS, AtcCfg<197>::SMEM_BYTES, st>>>(*tq, *tkv, *to, B, h->cfg.heads, W, scale_log2e, rev);
+    attention_tc_kernel<197><<<grid, ATC_THREADS, AtcCfg<197>::SMEM_BYTES, st>>>(*tq, *tkv, *to, *tq16, *to16, B, h->cfg.heads, W, scale_log2e, rev);
   else
-    attention_tc_kernel<50><<<grid, ATC_THREADS, AtcCfg<50>::SMEM_BYTES, st>>>(*tq, *tkv, *to, B, h->cfg.heads, W, scale_log2e, rev);
+    attention_tc_kernel<50><<<grid, ATC_THREADS, AtcCfg<50>::SMEM_BYTES, st>>>(*tq, *tkv, *to, *tq16, *to16, B, h->cfg.heads, W, scale_log2e, rev);
   h->launches++;
   ARP_CUDA(h, cudaGetLastError());
   return ARP_OK;

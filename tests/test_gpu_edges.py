@@ -243,7 +243,7 @@ sys.path.insert(0, sys.argv[1])
 from arp_b200 import capi
 eng = capi.Engine(device=0, max_batch=8)
 worst = 0.0
-for rep in range(3):
+for rep in range(6):
     for B, L in ((40, 197), (13, 197), (1, 197), (30, 50)):
         g = torch.Generator(device="cuda").manual_seed(1000 * rep + B)
         qkv = (torch.randn(B * L, 2304, device="cuda", generator=g) * 1.5).to(capi.operand_dtype())
@@ -264,7 +264,8 @@ def test_attention_protocol_survives_jitter(tmp_path):
     warps' usual relative speeds: the -DARP_ATTN_JITTER build sleeps a random 0..8 us at every hand-off. Several items
     per CTA (B = 40: 480 items over 148 CTAs) so that every ring and every parity wraps. A protocol hole shows up as a
     watchdog trap, a hang (timeout) or wrong numbers. Found the hard way: a single O-drained barrier shared by both
-    slots let a waiter run two phases ahead of it as soon as the epilogue warps were slowed down."""
+    slots let a waiter run two phases ahead of it as soon as the epilogue warps were slowed down; later a single
+    "tile 1's turn begins" barrier let its waiter fall two phases behind (this test caught that one)."""
     import subprocess
     import sys
     from arp_b200.build import build_jitter
