@@ -285,10 +285,10 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
   // barrier has completed (the warp that finished turn n - 1 arrives); a parked try_wait costs the SMSP next to nothing,
   // an LDS polling loop cost the neighbour's exp2 pass 8 %.
   uint64_t* xu_turn = bars + 14;     // [4 quarters]
-  // P rows of a slot written (4 warp arrivals) -> the slot's MMA issuer: the quarter-3 warp of the slot. That quarter
-  // has the least to do (tile 1: rows 224..255 are padding, the warp does no softmax at all; tile 0: its SMSP hosts one
-  // live softmax warp instead of two, so it finishes its pass first), and a parked try_wait notices the last arrival
-  // sooner than the two MEMBAR.SC + ATOMS of a "last one in issues" counter took.
+  // P rows of a slot written (4 warp arrivals, 5 for the spread tile 1) -> the slot's MMA issuer: the quarter-3 warp of the
+  // slot. Its SMSP carries the most exp2 work (364 MUFU instructions per item), so it is usually the LAST of the slot's
+  // warps to arrive and finds the phase complete without parking; and a parked try_wait notices the last arrival sooner
+  // than the two MEMBAR.SC + ATOMS of a "last one in issues" counter took.
   uint64_t* p_done = bars + 18;      // [2 slots]
   // spread layout: tile 0's quarter-3 warp has finished its exp2 pass (= tile 1's turn on that SMSP begins) -> the quarter-3
   // epilogue warp, which does the softmax of tile 1's last rows (the second 16-lane group of quarter 3)

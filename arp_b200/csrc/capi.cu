@@ -243,6 +243,10 @@ static int dev_alloc(ArpHandle* h, T** p, size_t count) {
   void* q = nullptr;
   ARP_CUDA(h, cudaMalloc(&q, count * sizeof(T) + 256));
   h->allocs.push_back(q);
+  // Zeroed once: a partially filled chunk's last frame reads a few rows past its own (the attention kernel's 208-key V
+  // box, tile 1's query rows) — rows that must be FINITE (their softmax weight is exactly 0, and 0 x NaN is NaN). Rows
+  // ever written by the kernels are finite; never-written rows are these zeros.
+  ARP_CUDA(h, cudaMemset(q, 0, count * sizeof(T) + 256));
   *p = reinterpret_cast<T*>(q);
   return ARP_OK;
 }
