@@ -68,7 +68,8 @@ __host__ __device__ inline int dec_smem_bytes(int src_w, int max_rows, int h_ksi
 
 __device__ __forceinline__ uint8_t clip8(int v) { return static_cast<uint8_t>(min(255, max(0, v))); }
 
-// Both Pillow passes of one band with the tap count known at compile time (KS = 5 when upscaling, 7 for 256 -> 224):
+// Both Pillow passes of one band with the tap count known at compile time (KS = the largest window that occurs: 4 when
+// upscaling, 5 for 256 -> 224; the host re-packs Pillow's wider, zero-padded coefficient rows):
 // one thread per output COLUMN. Its KS horizontal coefficients live in registers for every staged row, the tap loops are
 // fully unrolled (entries past a pixel's tap count are 0 in the tables, so all KS taps are always applied; the few
 // bytes read past a row's end are multiplied by 0), and the vertical coefficients of an output row are a shared-memory
@@ -187,7 +188,7 @@ decode_kernel(const DecodeArgs a) {
     int* t_vmin = t_hk + DEC_OUT * a.h_ksize;
     int* t_vcnt = t_vmin + DEC_BAND;
     int* t_vk = t_vcnt + DEC_BAND;
-    const bool fast = a.h_ksize == a.v_ksize && (a.h_ksize == 5 || a.h_ksize == 7);
+    const bool fast = a.h_ksize == a.v_ksize && a.h_ksize >= 3 && a.h_ksize <= 8;
     if (!fast) {
       for (int i = tid; i < DEC_OUT; i += DEC_THREADS) { t_hmin[i] = a.h_min[i]; t_hcnt[i] = a.h_cnt[i]; }
       for (int i = tid; i < DEC_OUT * a.h_ksize; i += DEC_THREADS) t_hk[i] = a.h_k[i];
@@ -196,8 +197,14 @@ decode_kernel(const DecodeArgs a) {
     for (int i = tid; i < DEC_BAND * a.v_ksize; i += DEC_THREADS) t_vk[i] = a.v_k[y0 * a.v_ksize + i];
     __syncthreads();
     if (fast) {
-      if (a.h_ksize == 7) bicubic_band_fast<7>(a, s_in, s_tmp, nrows, row_bytes, r_lo, y0, t_vmin, t_vk, put);
-      else bicubic_band_fast<5>(a, s_in, s_tmp, nrows, row_bytes, r_lo, y0, t_vmin, t_vk, put);
+      switch (a.h_ksize) {   // taps per output pixel after the host's re-packing: 5 for 256 -> 224, 4 when upscaling
+        case 3: bicubic_band_fast<3>(a, s_in, s_tmp, nrows, row_bytes, r_lo, y0, t_vmin, t_vk, put); break;
+        case 4: bicubic_band_fast<4>(a, s_in, s_tmp, nrows, row_bytes, r_lo, y0, t_vmin, t_vk, put); break;
+        case 5: bicubic_band_fast<5>(a, s_in, s_tmp, nrows, row_bytes, r_lo, y0, t_vmin, t_vk, put); break;
+        case 6: bicubic_band_fast<6>(a, s_in, s_tmp, nrows, row_bytes, r_lo, y0, t_vmin, t_vk, put); break;
+        case 7: bicubic_band_fast<7>(a, s_in, s_tmp, nrows, row_bytes, r_lo, y0, t_vmin, t_vk, put); break;
+        default: bicubic_band_fast<8>(a, s_in, s_tmp, nrows, row_bytes, r_lo, y0, t_vmin, t_vk, put); break;
+      }
     } else {
 
     // pass 1: horizontal, every staged row -> uint8 tmp[r][x][c]
