@@ -515,7 +515,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
     }
 #endif
   } else if (warp >= 2 && warp - 2 < SM_WARPS) {
-    // ===================== softmax + epilogue: one thread per query row =====================
+    // ===================== softmax: tile 0 one thread per query row, tile 1 (spread) four threads per row =====================
     const int qt = (warp - 2) >> 2;
     const int quarter = warp & 3;
     const uint32_t lane_off = static_cast<uint32_t>(quarter * 32) << 16;
@@ -523,8 +523,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
     constexpr int NFULL = C::NK / 32;                    // full 32-column chunks
     constexpr int TAIL = C::NK % 32;                     // 16 or 0
     const int n_mine = n_items > static_cast<int>(blockIdx.x) ? (n_items - 1 - static_cast<int>(blockIdx.x)) / static_cast<int>(gridDim.x) + 1 : 0;
-    // a warp whose 32 rows are all padding (tile 1, rows 224..255 when L = 197) keeps the barrier / turn protocol but
-    // does no softmax: whatever sits in its P rows only reaches O rows that are never stored
+    // a warp whose 32 rows are all padding (L = 50: rows 64..127 of the only tile) keeps the barrier protocol but does no
+    // softmax: whatever sits in its P rows only reaches O rows that are never stored
     const bool spread = C::SPREAD && qt == 1;          // warp-uniform: the 16-lane path of query tile 1
     const bool warp_live = spread || qt * 128 + quarter * 32 < L;
     if (quarter == 0 && n_mine > 0) {      // the slot's first Q K^T
@@ -543,7 +543,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
       if (quarter == 0) ATC_TRACE(2, qt, it);
       // Only the last (partial or padded) chunk can contain key columns >= L; the others need no masking.
       constexpr int NCLEAN = (L / 32 < NFULL) ? L / 32 : NFULL;   // full chunks whose 32 columns are all real keys
-      // ---- pass 1: row maximum over the L real keys (two 32-column loads in flight per wait) ----
+      // ---- pass 1: row maximum over the L real keys ----
       float m = -INFINITY;
       // spread path: row maxima of this quarter's 16-lane group; a thread serves rows t/4 ("A") and 8 + t/4 ("B"), a
       // quarter of their columns each
