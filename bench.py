@@ -442,7 +442,7 @@ def main():
         "by_class_ms": {k: round(v["total_ms"], 3) for k, v in prof.items() if v["launches"]},
         "hbm_bound_classes": {k: {"achieved_gbs": v["bytes"] / (v["total_ms"] * 1e-3) / 1e9,
                                   "frac_of_hbm_peak": v["bytes"] / (v["total_ms"] * 1e-3) / 1e9 / peaks["hbm_gbs"]}
-                              for k, v in prof.items() if k in ("layernorm", "decode", "scan") and v["launches"]},
+                              for k, v in prof.items() if k in ("layernorm", "decode", "scan", "attention") and v["launches"]},
         # the reference's work per frame (35.127 GFLOP) over our time, and what we actually execute
         # (the last block is computed for the class-token row only): both per GPU
         "whole_step_tflops_reference_work": total_frames / world * GFLOP_PER_FRAME_B16 / (ms_per_step * 1e-3) / 1e3,
